@@ -1,0 +1,254 @@
+"""ctypes binding of libdlwpcs.so (include/dlwpcs.h).  torch supplies device memory and the current stream only.
+
+There is no CPU fallback: if the shared library is missing or a CUDA tensor is not supplied, the calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libdlwpcs.so')
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_CAPPED_LEAKY_RELU = 0, 1
+SRC_SAME, SRC_POOL2, SRC_UP2 = 0, 1, 2
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ('batch', 'n', 'halo', 'cin', 'cout', 'kh', 'kw', 'stride_h', 'stride_w',
+                                               'dil_h', 'dil_w', 'same', 'flip_north_pole', 'independent_north_pole',
+                                               'use_bias', 'act')] + \
+               [('act_slope', ctypes.c_float), ('act_max', ctypes.c_float)] + \
+               [(n, ctypes.c_int32) for n in ('x_dtype', 'y_dtype', 'c0', 'mode0', 'c1', 'mode1')]
+
+
+class ConvWeights(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('w_eq', 'w_pol', 'w_np', 'b_eq', 'b_pol', 'b_np')]
+
+
+class ConvWgrads(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('dw_eq', 'dw_pol', 'dw_np', 'db_eq', 'db_pol', 'db_np')]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises ImportError with build instructions if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError('libdlwpcs.so not found at %s -- build it with `python -m dlwp_cs_b200.build` '
+                          '(there is no CPU fallback)' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+    dp, wp, gp = ctypes.POINTER(ConvDesc), ctypes.POINTER(ConvWeights), ctypes.POINTER(ConvWgrads)
+    sigs = {
+        'dlwpcs_version': (i32, []),
+        'dlwpcs_last_error': (ctypes.c_char_p, []),
+        'dlwpcs_conv_out_edge': (i32, [i32, i32, i32, i32, i32]),
+        'dlwpcs_pad_lut_host': (i32, [i32, i32, vp]),
+        'dlwpcs_pad_fwd': (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
+        'dlwpcs_pad_bwd': (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
+        'dlwpcs_packed_weight_bytes': (i64, [dp, i32]),
+        'dlwpcs_pack_weights': (i32, [dp, wp, i32, vp, vp]),
+        'dlwpcs_conv2d_fwd': (i32, [dp, vp, vp, vp, vp, vp]),
+        'dlwpcs_dgrad_workspace_bytes': (i64, [dp]),
+        'dlwpcs_conv2d_dgrad': (i32, [dp, vp, vp, vp, vp, vp, vp]),
+        'dlwpcs_wgrad_workspace_bytes': (i64, [dp]),
+        'dlwpcs_conv2d_wgrad': (i32, [dp, vp, vp, vp, gp, vp, vp]),
+        'dlwpcs_act_fwd': (i32, [vp, vp, i64, i32, f32, f32, i32, vp]),
+        'dlwpcs_act_bwd': (i32, [vp, vp, vp, i64, i32, f32, f32, i32, vp]),
+        'dlwpcs_conv2d_fwd_host': (i32, [dp, wp, vp, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)          # AttributeError here == header and library out of sync
+        fn.restype, fn.argtypes = res, args
+    if lib.dlwpcs_version() != 1:
+        raise ImportError('libdlwpcs.so version mismatch')
+    _lib = lib
+    return lib
+
+
+EXPORTED = ('dlwpcs_version', 'dlwpcs_last_error', 'dlwpcs_conv_out_edge', 'dlwpcs_pad_lut_host', 'dlwpcs_pad_fwd',
+            'dlwpcs_pad_bwd', 'dlwpcs_packed_weight_bytes', 'dlwpcs_pack_weights', 'dlwpcs_conv2d_fwd',
+            'dlwpcs_dgrad_workspace_bytes', 'dlwpcs_conv2d_dgrad', 'dlwpcs_wgrad_workspace_bytes',
+            'dlwpcs_conv2d_wgrad', 'dlwpcs_act_fwd', 'dlwpcs_act_bwd', 'dlwpcs_conv2d_fwd_host')
+
+
+class DlwpcsError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise DlwpcsError(load().dlwpcs_last_error().decode() or 'libdlwpcs error %d' % rc)
+
+
+def dtype_code(dt):
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise DlwpcsError('unsupported dtype %s (float32 or bfloat16)' % (dt,))
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise DlwpcsError('dlwp_cs_b200 runs on CUDA tensors only (got a %s tensor); there is no CPU path'
+                              % t.device.type)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def pad_lut(n, p):
+    """Halo index table (6, n+2p, n+2p) int32 -- host only."""
+    h = n + 2 * p
+    out = np.empty((6, h, h), dtype=np.int32)
+    check(load().dlwpcs_pad_lut_host(n, p, out.ctypes.data_as(ctypes.c_void_p)))
+    return out
+
+
+def conv_out_edge(edge_in, k, stride, dilation, same):
+    r = load().dlwpcs_conv_out_edge(edge_in, k, stride, dilation, int(bool(same)))
+    if r < 0:
+        raise DlwpcsError('bad arguments to conv_out_edge')
+    return r
+
+
+def make_desc(batch, n, cin, cout, kernel_size=(3, 3), strides=(1, 1), dilation=(1, 1), halo=0, same=False,
+              flip_north_pole=True, independent_north_pole=False, use_bias=True, act=ACT_NONE, act_slope=0.1,
+              act_max=10.0, x_dtype=F32, y_dtype=F32, c0=None, mode0=SRC_SAME, c1=0, mode1=SRC_SAME):
+    d = ConvDesc()
+    d.batch, d.n, d.halo, d.cin, d.cout = batch, n, halo, cin, cout
+    d.kh, d.kw = kernel_size
+    d.stride_h, d.stride_w = strides
+    d.dil_h, d.dil_w = dilation
+    d.same = int(bool(same))
+    d.flip_north_pole = int(bool(flip_north_pole))
+    d.independent_north_pole = int(bool(independent_north_pole))
+    d.use_bias = int(bool(use_bias))
+    d.act, d.act_slope, d.act_max = act, act_slope, act_max
+    d.x_dtype, d.y_dtype = x_dtype, y_dtype
+    d.c0 = cin - c1 if c0 is None else c0
+    d.mode0, d.c1, d.mode1 = mode0, c1, mode1
+    return d
+
+
+def out_shape(d):
+    hin = d.n + 2 * d.halo
+    return (d.batch, 6, conv_out_edge(hin, d.kh, d.stride_h, d.dil_h, d.same),
+            conv_out_edge(hin, d.kw, d.stride_w, d.dil_w, d.same), d.cout)
+
+
+def pack_weights(d, w_eq, w_pol, w_np=None, b_eq=None, b_pol=None, b_np=None, transposed=False):
+    """HWIO float32 parameters -> the packed device buffer the kernels read (uint8 tensor)."""
+    lib = load()
+    ws = [w_eq, w_pol, w_np, b_eq, b_pol, b_np]
+    require_cuda(*ws)
+    ws = [None if t is None else t.detach().to(torch.float32).contiguous() for t in ws]
+    nbytes = lib.dlwpcs_packed_weight_bytes(ctypes.byref(d), int(transposed))
+    if nbytes < 0:
+        check(1)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=w_eq.device)
+    cw = ConvWeights(*[t.data_ptr() if t is not None else None for t in ws])
+    check(lib.dlwpcs_pack_weights(ctypes.byref(d), ctypes.byref(cw), int(transposed), ptr(packed), stream_ptr()))
+    return packed
+
+
+def conv2d_fwd(d, x0, x1, packed, out=None):
+    require_cuda(x0, x1, packed)
+    shp = out_shape(d)
+    ydt = torch.float32 if d.y_dtype == F32 else torch.bfloat16
+    y = out if out is not None else torch.empty(shp, dtype=ydt, device=x0.device)
+    check(load().dlwpcs_conv2d_fwd(ctypes.byref(d), ptr(x0), ptr(x1), ptr(packed), ptr(y), stream_ptr()))
+    return y
+
+
+def conv2d_dgrad(d, dy, y, packed_t):
+    require_cuda(dy, y, packed_t)
+    lib = load()
+    nbytes = lib.dlwpcs_dgrad_workspace_bytes(ctypes.byref(d))
+    if nbytes < 0:
+        check(1)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dy.device)
+    dx = torch.empty((d.batch, 6, d.n, d.n, d.cin), dtype=torch.float32, device=dy.device)
+    check(lib.dlwpcs_conv2d_dgrad(ctypes.byref(d), ptr(dy), ptr(y), ptr(packed_t), ptr(dx), ptr(ws), stream_ptr()))
+    return dx
+
+
+def conv2d_wgrad(d, x0, dy, y):
+    """Returns (dw_eq, dw_pol, dw_np|None, db_eq|None, db_pol|None, db_np|None), float32 HWIO."""
+    require_cuda(x0, dy, y)
+    lib = load()
+    nbytes = lib.dlwpcs_wgrad_workspace_bytes(ctypes.byref(d))
+    if nbytes < 0:
+        check(1)
+    dev = x0.device
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    wshape = (d.kh, d.kw, d.cin, d.cout)
+    mk = lambda shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    dw_eq, dw_pol = mk(wshape), mk(wshape)
+    dw_np = mk(wshape) if d.independent_north_pole else None
+    db_eq = mk((d.cout,)) if d.use_bias else None
+    db_pol = mk((d.cout,)) if d.use_bias else None
+    db_np = mk((d.cout,)) if (d.use_bias and d.independent_north_pole) else None
+    outs = (dw_eq, dw_pol, dw_np, db_eq, db_pol, db_np)
+    g = ConvWgrads(*[t.data_ptr() if t is not None else None for t in outs])
+    check(lib.dlwpcs_conv2d_wgrad(ctypes.byref(d), ptr(x0), ptr(dy), ptr(y), ctypes.byref(g), ptr(ws), stream_ptr()))
+    return outs
+
+
+def pad_fwd(x, p):
+    require_cuda(x)
+    b, six, n, n2, c = x.shape
+    y = torch.empty((b, 6, n + 2 * p, n + 2 * p, c), dtype=x.dtype, device=x.device)
+    check(load().dlwpcs_pad_fwd(ptr(x), ptr(y), b, n, c, p, dtype_code(x.dtype), stream_ptr()))
+    return y
+
+
+def pad_bwd(dy, p):
+    require_cuda(dy)
+    b, six, h, h2, c = dy.shape
+    n = h - 2 * p
+    dx = torch.empty((b, 6, n, n, c), dtype=dy.dtype, device=dy.device)
+    check(load().dlwpcs_pad_bwd(ptr(dy), ptr(dx), b, n, c, p, dtype_code(dy.dtype), stream_ptr()))
+    return dx
+
+
+def act_fwd(x, act, slope, maxv):
+    require_cuda(x)
+    y = torch.empty_like(x)
+    check(load().dlwpcs_act_fwd(ptr(x), ptr(y), x.numel(), act, slope, maxv, dtype_code(x.dtype), stream_ptr()))
+    return y
+
+
+def act_bwd(dy, y, act, slope, maxv):
+    require_cuda(dy, y)
+    dx = torch.empty_like(dy)
+    check(load().dlwpcs_act_bwd(ptr(dy), ptr(y), ptr(dx), dy.numel(), act, slope, maxv, dtype_code(dy.dtype),
+                                stream_ptr()))
+    return dx
+
+
+def conv2d_fwd_host(d, x, w_eq, w_pol, w_np=None, b_eq=None, b_pol=None, b_np=None):
+    """numpy in / numpy out through the host-buffer C entry point (H2D + kernels + D2H inside the call)."""
+    lib = load()
+    arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float32) for a in
+            (w_eq, w_pol, w_np, b_eq, b_pol, b_np)]
+    cw = ConvWeights(*[a.ctypes.data if a is not None else None for a in arrs])
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.empty(out_shape(d), dtype=np.float32)
+    check(lib.dlwpcs_conv2d_fwd_host(ctypes.byref(d), ctypes.byref(cw), x.ctypes.data_as(ctypes.c_void_p),
+                                     y.ctypes.data_as(ctypes.c_void_p)))
+    return y

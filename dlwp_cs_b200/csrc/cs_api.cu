@@ -1,0 +1,493 @@
+// libdlwpcs C ABI: error reporting, halo tables, geometry, standalone padding / activation kernels and the dispatch of
+// the convolution entry points onto the fp32 (cs_fp32.cu) and tcgen05 bf16 (cs_tc.cu) kernels.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include "cs_common.cuh"
+
+namespace dlwpcs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Halo index table.  Restates the two-stage composition of CubeSpherePadding2D.call (reference DLWP/custom.py:1198-1308)
+// as index arithmetic: stage 1 fills rows from the polar / equatorial neighbours (1203-1249), stage 2 fills columns
+// reading the row-padded faces, and -- for the two polar faces -- rows p:2p / -2p:-p of the fully padded faces 3 and 1
+// (1291-1301).  Verified against the reference code itself in tests/test_lib_cpu.py.
+// ---------------------------------------------------------------------------------------------------------------------
+void build_pad_lut(int n, int p, std::vector<int32_t> &lut) {
+  const int H = n + 2 * p;
+  auto src = [n](int f, int i, int j) { return f * n * n + i * n + j; };
+  // stage 1: s1[f][r][c], r in [0,H), c in [0,n)
+  std::vector<int32_t> s1((size_t)6 * H * n);
+  for (int f = 0; f < 6; ++f)
+    for (int r = 0; r < H; ++r)
+      for (int c = 0; c < n; ++c) {
+        int v;
+        if (r >= p && r < n + p) {
+          v = src(f, r - p, c);
+        } else if (r < p) {  // top halo, a = r
+          const int a = r;
+          switch (f) {
+            case 0: v = src(4, n - p + a, c); break;
+            case 1: v = src(4, n - 1 - c, n - p + a); break;
+            case 2: v = src(4, p - 1 - a, n - 1 - c); break;
+            case 3: v = src(4, c, p - 1 - a); break;
+            case 4: v = src(2, p - 1 - a, n - 1 - c); break;
+            default: v = src(0, n - p + a, c); break;
+          }
+        } else {  // bottom halo
+          const int a = r - (n + p);
+          switch (f) {
+            case 0: v = src(5, a, c); break;
+            case 1: v = src(5, c, n - 1 - a); break;
+            case 2: v = src(5, n - 1 - a, n - 1 - c); break;
+            case 3: v = src(5, n - 1 - c, a); break;
+            case 4: v = src(0, a, c); break;
+            default: v = src(2, n - 1 - a, n - 1 - c); break;
+          }
+        }
+        s1[((size_t)f * H + r) * n + c] = v;
+      }
+  lut.assign((size_t)6 * H * H, 0);
+  auto S1 = [&](int f, int r, int c) { return s1[((size_t)f * H + r) * n + c]; };
+  auto OUT = [&](int f, int r, int c) -> int32_t & { return lut[((size_t)f * H + r) * H + c]; };
+  for (int f = 0; f < 4; ++f)  // periodic equatorial belt
+    for (int r = 0; r < H; ++r)
+      for (int c = 0; c < H; ++c) {
+        if (c < p) OUT(f, r, c) = S1((f + 3) % 4, r, n - p + c);
+        else if (c < n + p) OUT(f, r, c) = S1(f, r, c - p);
+        else OUT(f, r, c) = S1((f + 1) % 4, r, c - (n + p));
+      }
+  for (int r = 0; r < H; ++r)
+    for (int c = 0; c < H; ++c) {
+      if (c < p) {  // left halo column a = c
+        OUT(4, r, c) = OUT(3, 2 * p - 1 - c, r);
+        OUT(5, r, c) = OUT(3, H - 2 * p + c, H - 1 - r);
+      } else if (c < n + p) {
+        OUT(4, r, c) = S1(4, r, c - p);
+        OUT(5, r, c) = S1(5, r, c - p);
+      } else {
+        const int a = c - (n + p);
+        OUT(4, r, c) = OUT(1, p + a, H - 1 - r);
+        OUT(5, r, c) = OUT(1, H - p - 1 - a, r);
+      }
+    }
+}
+
+namespace {
+std::mutex g_mu;
+std::map<std::tuple<int, int, int>, HaloTables> g_tables;
+}  // namespace
+
+const HaloTables *get_halo_tables(int n, int p) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("cudaGetDevice failed");
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto key = std::make_tuple(dev, n, p);
+  auto it = g_tables.find(key);
+  if (it != g_tables.end()) return &it->second;
+  std::vector<int32_t> lut;
+  build_pad_lut(n, p, lut);
+  const int H = n + 2 * p;
+  const int nsrc = 6 * n * n, npad = 6 * H * H;
+  std::vector<int32_t> start(nsrc + 1, 0), items(npad);
+  for (int q = 0; q < npad; ++q) start[lut[q] + 1]++;
+  for (int s = 0; s < nsrc; ++s) start[s + 1] += start[s];
+  std::vector<int32_t> fill(start.begin(), start.end() - 1);
+  for (int q = 0; q < npad; ++q) items[fill[lut[q]]++] = q;  // ascending q within each source: deterministic order
+  HaloTables t;
+  t.n = n;
+  t.p = p;
+  // Plain cudaMalloc + synchronous copies: must not run inside a stream capture -- callers warm the cache first.
+  cudaError_t e = cudaMalloc(&t.lut, sizeof(int32_t) * npad);
+  if (e == cudaSuccess) e = cudaMalloc(&t.inv_start, sizeof(int32_t) * (nsrc + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&t.inv_items, sizeof(int32_t) * npad);
+  if (e == cudaSuccess) e = cudaMemcpy(t.lut, lut.data(), sizeof(int32_t) * npad, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(t.inv_start, start.data(), sizeof(int32_t) * (nsrc + 1), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(t.inv_items, items.data(), sizeof(int32_t) * npad, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("halo table upload failed: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
+  auto res = g_tables.emplace(key, t);
+  return &res.first->second;
+}
+
+static int out_edge(int edge_in, int k, int stride, int dilation, int same) {
+  const int keff = (k - 1) * dilation + 1;
+  const int o = same ? edge_in : edge_in - keff + 1;
+  return (o + stride - 1) / stride;
+}
+
+int derive_geometry(const dlwpcs_conv_desc *d, Geometry *g) {
+  CS_CHECK(d != nullptr, "null descriptor");
+  CS_CHECK(d->batch >= 0 && d->n > 0, "bad batch/n (%d,%d)", d->batch, d->n);
+  CS_CHECK(d->halo >= 0 && d->halo <= d->n, "halo %d out of range for face edge %d", d->halo, d->n);
+  CS_CHECK(d->cin > 0 && d->cout > 0, "bad channel counts (%d,%d)", d->cin, d->cout);
+  CS_CHECK(d->kh > 0 && d->kw > 0 && d->stride_h > 0 && d->stride_w > 0 && d->dil_h > 0 && d->dil_w > 0,
+           "kernel_size / strides / dilation_rate must be positive");
+  CS_CHECK(d->c0 + d->c1 == d->cin && d->c0 > 0 && d->c1 >= 0, "c0 + c1 (%d+%d) must equal cin (%d)", d->c0, d->c1,
+           d->cin);
+  CS_CHECK(d->mode0 >= 0 && d->mode0 <= 2 && d->mode1 >= 0 && d->mode1 <= 2, "bad source mode");
+  if (d->mode0 == DLWPCS_SRC_UP2 || (d->c1 > 0 && d->mode1 == DLWPCS_SRC_UP2))
+    CS_CHECK(d->n % 2 == 0, "nearest-upsampled source needs an even face edge");
+  g->Hin = g->Win = d->n + 2 * d->halo;
+  const int keh = (d->kh - 1) * d->dil_h + 1, kew = (d->kw - 1) * d->dil_w + 1;
+  g->Hout = out_edge(g->Hin, d->kh, d->stride_h, d->dil_h, d->same);
+  g->Wout = out_edge(g->Win, d->kw, d->stride_w, d->dil_w, d->same);
+  CS_CHECK(g->Hout > 0 && g->Wout > 0, "kernel (%dx%d, dilation %dx%d) larger than the face (%d)", d->kh, d->kw,
+           d->dil_h, d->dil_w, g->Hin);
+  int pt = 0, pl = 0;
+  if (d->same) {
+    const int th = (g->Hout - 1) * d->stride_h + keh - g->Hin, tw = (g->Wout - 1) * d->stride_w + kew - g->Win;
+    pt = (th > 0 ? th : 0) / 2;
+    pl = (tw > 0 ? tw : 0) / 2;
+  }
+  g->pt[0] = g->pt[1] = g->pt[2] = pt;
+  // custom.py:969/995 reverse the rows of face 5 before and after the conv.  In unflipped coordinates that is the
+  // kernel flipped along kh (done at weight packing) with this top offset -- exact for every stride / 'same' / dilation.
+  if (d->flip_north_pole) g->pt[2] = (g->Hout - 1) * d->stride_h + (d->kh - 1) * d->dil_h - (g->Hin - 1) - pt;
+  g->pl = pl;
+  g->taps = d->kh * d->kw;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// standalone padding kernels
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename V>
+__global__ void pad_fwd_kernel(const V *__restrict__ x, V *__restrict__ y, const int32_t *__restrict__ lut, int npad,
+                               int nsrc, int vec_per_px, long long total) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int v = (int)(i % vec_per_px);
+    const long long q = i / vec_per_px;
+    const int qp = (int)(q % npad);
+    const long long b = q / npad;
+    y[i] = x[(b * nsrc + lut[qp]) * vec_per_px + v];
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void pad_bwd_kernel(const T *__restrict__ dy, T *__restrict__ dx, const int32_t *__restrict__ inv_start,
+                               const int32_t *__restrict__ inv_items, int npad, int nsrc, int c, long long total) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int ch = (int)(i % c);
+    const long long s = i / c;
+    const int sp = (int)(s % nsrc);
+    const long long b = s / nsrc;
+    float acc = 0.f;
+    for (int k = inv_start[sp]; k < inv_start[sp + 1]; ++k) acc += to_f<T>(dy[(b * npad + inv_items[k]) * c + ch]);
+    dx[i] = from_f<T>(acc);
+  }
+}
+
+__device__ __forceinline__ float act_apply(float v, int act, float slope, float maxv) {
+  if (act == DLWPCS_ACT_CAPPED_LEAKY_RELU) v = v < 0.f ? slope * v : fminf(v, maxv);
+  return v;
+}
+// derivative expressed through the OUTPUT y (y<0 <=> x<0 for slope>0; y==max <=> x>=max)
+__device__ __forceinline__ float act_grad_from_y(float y, int act, float slope, float maxv) {
+  if (act == DLWPCS_ACT_CAPPED_LEAKY_RELU) return y < 0.f ? slope : (y < maxv ? 1.f : 0.f);
+  return 1.f;
+}
+
+template <typename T>
+__global__ void act_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, long long n, int act, float slope,
+                               float maxv) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = from_f<T>(act_apply(to_f<T>(x[i]), act, slope, maxv));
+}
+template <typename T>
+__global__ void act_bwd_kernel(const T *__restrict__ dy, const T *__restrict__ y, T *__restrict__ dx, long long n,
+                               int act, float slope, float maxv) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dx[i] = from_f<T>(to_f<T>(dy[i]) * act_grad_from_y(to_f<T>(y[i]), act, slope, maxv));
+}
+
+static int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace dlwpcs
+
+using namespace dlwpcs;
+
+extern "C" {
+
+int dlwpcs_version(void) { return DLWPCS_VERSION; }
+const char *dlwpcs_last_error(void) { return g_err; }
+
+int dlwpcs_conv_out_edge(int edge_in, int k, int stride, int dilation, int same) {
+  if (edge_in <= 0 || k <= 0 || stride <= 0 || dilation <= 0) return -1;
+  return out_edge(edge_in, k, stride, dilation, same);
+}
+
+int dlwpcs_pad_lut_host(int n, int p, int32_t *lut) {
+  CS_CHECK(n > 0 && p >= 0 && p <= n && lut != nullptr, "bad arguments to dlwpcs_pad_lut_host (n=%d, p=%d)", n, p);
+  std::vector<int32_t> v;
+  build_pad_lut(n, p, v);
+  memcpy(lut, v.data(), v.size() * sizeof(int32_t));
+  return 0;
+}
+
+static int elem_size(int dtype) { return dtype == DLWPCS_F32 ? 4 : (dtype == DLWPCS_BF16 ? 2 : 0); }
+
+int dlwpcs_pad_fwd(const void *x, void *y, int batch, int n, int c, int p, int dtype, void *stream) {
+  const int es = elem_size(dtype);
+  CS_CHECK(es != 0, "unsupported dtype %d", dtype);
+  CS_CHECK(batch >= 0 && n > 0 && c > 0 && p >= 0 && p <= n, "bad arguments to dlwpcs_pad_fwd");
+  if (batch == 0) return 0;
+  CS_CHECK(x && y, "null tensor pointer");
+  const HaloTables *t = get_halo_tables(n, p);
+  if (!t) return 3;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = n + 2 * p, npad = 6 * H * H, nsrc = 6 * n * n;
+  const int row_bytes = c * es;
+  const bool al16 = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  if (row_bytes % 16 == 0 && al16) {
+    const int vpp = row_bytes / 16;
+    const long long total = (long long)batch * npad * vpp;
+    pad_fwd_kernel<uint4><<<grid_for(total, 256), 256, 0, st>>>((const uint4 *)x, (uint4 *)y, t->lut, npad, nsrc, vpp,
+                                                                  total);
+  } else if (row_bytes % 4 == 0) {
+    const int vpp = row_bytes / 4;
+    const long long total = (long long)batch * npad * vpp;
+    pad_fwd_kernel<uint32_t><<<grid_for(total, 256), 256, 0, st>>>((const uint32_t *)x, (uint32_t *)y, t->lut, npad,
+                                                                     nsrc, vpp, total);
+  } else {
+    const int vpp = row_bytes / 2;
+    const long long total = (long long)batch * npad * vpp;
+    pad_fwd_kernel<uint16_t><<<grid_for(total, 256), 256, 0, st>>>((const uint16_t *)x, (uint16_t *)y, t->lut, npad,
+                                                                     nsrc, vpp, total);
+  }
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dlwpcs_pad_bwd(const void *dy, void *dx, int batch, int n, int c, int p, int dtype, void *stream) {
+  CS_CHECK(elem_size(dtype) != 0, "unsupported dtype %d", dtype);
+  CS_CHECK(batch >= 0 && n > 0 && c > 0 && p >= 0 && p <= n, "bad arguments to dlwpcs_pad_bwd");
+  if (batch == 0) return 0;
+  CS_CHECK(dy && dx, "null tensor pointer");
+  const HaloTables *t = get_halo_tables(n, p);
+  if (!t) return 3;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = n + 2 * p, npad = 6 * H * H, nsrc = 6 * n * n;
+  const long long total = (long long)batch * nsrc * c;
+  if (dtype == DLWPCS_F32)
+    pad_bwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float *)dy, (float *)dx, t->inv_start,
+                                                                  t->inv_items, npad, nsrc, c, total);
+  else
+    pad_bwd_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(
+        (const __nv_bfloat16 *)dy, (__nv_bfloat16 *)dx, t->inv_start, t->inv_items, npad, nsrc, c, total);
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dlwpcs_act_fwd(const void *x, void *y, int64_t count, int act, float slope, float maxv, int dtype, void *stream) {
+  CS_CHECK(elem_size(dtype) != 0 && x && y && count >= 0, "bad arguments to dlwpcs_act_fwd");
+  if (count == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DLWPCS_F32)
+    act_fwd_kernel<float><<<grid_for(count, 256), 256, 0, st>>>((const float *)x, (float *)y, count, act, slope, maxv);
+  else
+    act_fwd_kernel<__nv_bfloat16><<<grid_for(count, 256), 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y,
+                                                                          count, act, slope, maxv);
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dlwpcs_act_bwd(const void *dy, const void *y, void *dx, int64_t count, int act, float slope, float maxv, int dtype,
+                   void *stream) {
+  CS_CHECK(elem_size(dtype) != 0 && dy && y && dx && count >= 0, "bad arguments to dlwpcs_act_bwd");
+  if (count == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DLWPCS_F32)
+    act_bwd_kernel<float><<<grid_for(count, 256), 256, 0, st>>>((const float *)dy, (const float *)y, (float *)dx, count,
+                                                                  act, slope, maxv);
+  else
+    act_bwd_kernel<__nv_bfloat16><<<grid_for(count, 256), 256, 0, st>>>(
+        (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)y, (__nv_bfloat16 *)dx, count, act, slope, maxv);
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int check_common(const dlwpcs_conv_desc *d, Geometry *g) {
+  if (int rc = derive_geometry(d, g)) return rc;
+  CS_CHECK(elem_size(d->x_dtype) && elem_size(d->y_dtype), "unsupported dtype");
+  return 0;
+}
+
+static int64_t fp32_packed_floats(const dlwpcs_conv_desc *d, int transposed) {
+  const int64_t w = 3LL * d->kh * d->kw * d->cin * d->cout;
+  return transposed ? w : w + 3LL * d->cout;
+}
+
+int64_t dlwpcs_packed_weight_bytes(const dlwpcs_conv_desc *d, int transposed) {
+  Geometry g;
+  if (check_common(d, &g)) return -1;
+  if (d->x_dtype == DLWPCS_BF16 && !transposed) return tc_packed_weight_bytes(d, g);
+  return fp32_packed_floats(d, transposed) * 4;
+}
+
+int dlwpcs_pack_weights(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, int transposed, void *packed,
+                        void *stream) {
+  Geometry g;
+  if (int rc = check_common(d, &g)) return rc;
+  CS_CHECK(w && packed && w->w_eq && w->w_pol, "null weights");
+  CS_CHECK(!d->independent_north_pole || w->w_np, "independent_north_pole needs w_np");
+  CS_CHECK(transposed || !d->use_bias || (w->b_eq && w->b_pol && (!d->independent_north_pole || w->b_np)),
+           "use_bias needs biases");
+  if (d->x_dtype == DLWPCS_BF16 && !transposed) return tc_pack_weights(d, g, w, packed, (cudaStream_t)stream);
+  return fp32_pack_weights(d, w, transposed, (float *)packed, (cudaStream_t)stream);
+}
+
+int dlwpcs_conv2d_fwd(const dlwpcs_conv_desc *d, const void *x0, const void *x1, const void *packed_w, void *y,
+                      void *stream) {
+  Geometry g;
+  if (int rc = check_common(d, &g)) return rc;
+  if (d->batch == 0) return 0;
+  CS_CHECK(x0 && packed_w && y && (d->c1 == 0 || x1), "null tensor pointer");
+  if (d->x_dtype == DLWPCS_BF16) {
+    const char *why = "";
+    CS_CHECK(tc_supported(d, g, &why), "bf16 tensor-core path does not support this configuration: %s", why);
+    return tc_conv_fwd(d, g, x0, x1, packed_w, y, (cudaStream_t)stream);
+  }
+  CS_CHECK(d->y_dtype == DLWPCS_F32, "float32 input requires float32 output");
+  return fp32_conv_fwd(d, g, (const float *)x0, (const float *)x1, (const float *)packed_w, (float *)y,
+                       (cudaStream_t)stream);
+}
+
+static int check_bwd(const dlwpcs_conv_desc *d, Geometry *g) {
+  if (int rc = check_common(d, g)) return rc;
+  CS_CHECK(d->x_dtype == DLWPCS_F32 && d->y_dtype == DLWPCS_F32, "backward kernels are float32");
+  CS_CHECK(d->stride_h == 1 && d->stride_w == 1, "backward is implemented for strides == 1 only (all cubed-sphere "
+           "models in the reference use stride 1: Azure/train_cs.py:200-207)");
+  CS_CHECK(d->c1 == 0 && d->mode0 == DLWPCS_SRC_SAME, "backward takes a single un-resampled input source");
+  return 0;
+}
+
+int64_t dlwpcs_dgrad_workspace_bytes(const dlwpcs_conv_desc *d) {
+  Geometry g;
+  if (check_bwd(d, &g)) return -1;
+  return d->halo > 0 ? (int64_t)d->batch * 6 * g.Hin * g.Win * d->cin * 4 : 0;
+}
+
+int dlwpcs_conv2d_dgrad(const dlwpcs_conv_desc *d, const void *dy, const void *y, const void *packed_w_t, void *dx,
+                        void *workspace, void *stream) {
+  Geometry g;
+  if (int rc = check_bwd(d, &g)) return rc;
+  CS_CHECK(dy && packed_w_t && dx && (d->halo == 0 || workspace), "null pointer");
+  CS_CHECK(d->act == DLWPCS_ACT_NONE || y, "activation derivative needs the forward output y");
+  if (d->batch == 0) return 0;
+  return fp32_conv_dgrad(d, g, (const float *)dy, (const float *)y, (const float *)packed_w_t, (float *)dx, workspace,
+                         (cudaStream_t)stream);
+}
+
+int64_t dlwpcs_wgrad_workspace_bytes(const dlwpcs_conv_desc *d) {
+  Geometry g;
+  if (check_bwd(d, &g)) return -1;
+  return fp32_wgrad_workspace_bytes(d, g);
+}
+
+int dlwpcs_conv2d_wgrad(const dlwpcs_conv_desc *d, const void *x0, const void *dy, const void *y,
+                        const dlwpcs_conv_wgrads *out, void *workspace, void *stream) {
+  Geometry g;
+  if (int rc = check_bwd(d, &g)) return rc;
+  CS_CHECK(x0 && dy && out && workspace && out->dw_eq && out->dw_pol, "null pointer");
+  CS_CHECK(!d->independent_north_pole || out->dw_np, "independent_north_pole needs dw_np");
+  CS_CHECK(!d->use_bias || (out->db_eq && out->db_pol && (!d->independent_north_pole || out->db_np)),
+           "use_bias needs bias gradient buffers");
+  CS_CHECK(d->act == DLWPCS_ACT_NONE || y, "activation derivative needs the forward output y");
+  CS_CHECK(d->batch > 0, "wgrad needs a non-empty batch");
+  return fp32_conv_wgrad(d, g, (const float *)x0, (const float *)dy, (const float *)y, out, workspace,
+                         (cudaStream_t)stream);
+}
+
+int dlwpcs_conv2d_fwd_host(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, const void *x_host, void *y_host) {
+  Geometry g;
+  if (int rc = check_common(d, &g)) return rc;
+  CS_CHECK(w && x_host && y_host, "null pointer");
+  CS_CHECK(d->c1 == 0 && d->mode0 == DLWPCS_SRC_SAME, "host entry point takes one un-resampled input");
+  const int kk = d->kh * d->kw;
+  const size_t wbytes = (size_t)kk * d->cin * d->cout * 4, bbytes = (size_t)d->cout * 4;
+  const size_t xbytes = (size_t)d->batch * 6 * d->n * d->n * d->cin * elem_size(d->x_dtype);
+  const size_t ybytes = (size_t)d->batch * 6 * g.Hout * g.Wout * d->cout * elem_size(d->y_dtype);
+  const int64_t pbytes = dlwpcs_packed_weight_bytes(d, 0);
+  if (pbytes < 0) return 1;
+  if (d->halo > 0 && !get_halo_tables(d->n, d->halo)) return 3;
+  char *dev = nullptr;
+  const size_t wtot = 3 * wbytes + 3 * bbytes;
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t total = al(wtot) + al((size_t)pbytes) + al(xbytes) + al(ybytes);
+  CS_CUDA(cudaMalloc(&dev, total));
+  char *dw = dev, *dp = dw + al(wtot), *dxp = dp + al((size_t)pbytes), *dyp = dxp + al(xbytes);
+  dlwpcs_conv_weights dv = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int rc = 0;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](const float *src, size_t off, size_t bytes) -> const float * {
+    if (!src) return nullptr;
+    if (e == cudaSuccess) e = cudaMemcpy(dw + off, src, bytes, cudaMemcpyHostToDevice);
+    return (const float *)(dw + off);
+  };
+  dv.w_eq = up(w->w_eq, 0, wbytes);
+  dv.w_pol = up(w->w_pol, wbytes, wbytes);
+  dv.w_np = up(w->w_np, 2 * wbytes, wbytes);
+  dv.b_eq = up(w->b_eq, 3 * wbytes, bbytes);
+  dv.b_pol = up(w->b_pol, 3 * wbytes + bbytes, bbytes);
+  dv.b_np = up(w->b_np, 3 * wbytes + 2 * bbytes, bbytes);
+  if (e == cudaSuccess) e = cudaMemcpy(dxp, x_host, xbytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("host->device copy failed: %s", cudaGetErrorString(e));
+    rc = 2;
+  }
+  if (!rc) rc = dlwpcs_pack_weights(d, &dv, 0, dp, nullptr);
+  if (!rc) rc = dlwpcs_conv2d_fwd(d, dxp, nullptr, dp, dyp, nullptr);
+  if (!rc) {
+    e = cudaMemcpy(y_host, dyp, ybytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+      set_error("device->host copy failed: %s", cudaGetErrorString(e));
+      rc = 2;
+    }
+  }
+  cudaFree(dev);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// Shared declarations of libdlwpcs (internal).  See include/dlwpcs.h for the public C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <vector>
+#include "dlwpcs.h"
+
+namespace dlwpcs {
+
+void set_error(const char *fmt, ...);
+
+#define CS_CHECK(cond, ...)          \
+  do {                               \
+    if (!(cond)) {                   \
+      ::dlwpcs::set_error(__VA_ARGS__); \
+      return 1;                      \
+    }                                \
+  } while (0)
+
+#define CS_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      ::dlwpcs::set_error("%s failed: %s", #expr, cudaGetErrorString(e__));             \
+      return 2;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+// ---- halo tables (CubeSpherePadding2D as an index map), cached per (device, n, p) --------------------------------
+struct HaloTables {
+  int n, p;
+  int32_t *lut;        // device [6*(n+2p)^2]  padded position -> flat source pixel f*n*n + i*n + j
+  int32_t *inv_start;  // device [6*n*n + 1]   CSR over source pixels
+  int32_t *inv_items;  // device [6*(n+2p)^2]  padded positions reading each source pixel
+};
+void build_pad_lut(int n, int p, std::vector<int32_t> &lut);
+const HaloTables *get_halo_tables(int n, int p);  // nullptr on error (message set)
+
+// ---- geometry derived from a conv descriptor ----------------------------------------------------------------------
+struct Geometry {
+  int Hin, Win;     // edge the conv sees (n + 2*halo)
+  int Hout, Wout;
+  int pt[3];        // zero rows above, per face group {equatorial, south pole, north pole}; may be negative (offset)
+  int pl;           // zero columns left
+  int taps;
+};
+int derive_geometry(const dlwpcs_conv_desc *d, Geometry *g);
+
+static inline int face_group_host(int f) { return f < 4 ? 0 : f - 3; }
+
+// fp32 path (cs_fp32.cu)
+int fp32_pack_weights(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, int transposed, float *packed,
+                      cudaStream_t st);
+int fp32_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const float *x0, const float *x1, const float *packed,
+                  float *y, cudaStream_t st);
+int fp32_conv_dgrad(const dlwpcs_conv_desc *d, const Geometry &g, const float *dy, const float *y,
+                    const float *packed_t, float *dx, void *workspace, cudaStream_t st);
+int fp32_conv_wgrad(const dlwpcs_conv_desc *d, const Geometry &g, const float *x0, const float *dy, const float *y,
+                    const dlwpcs_conv_wgrads *out, void *workspace, cudaStream_t st);
+int64_t fp32_wgrad_workspace_bytes(const dlwpcs_conv_desc *d, const Geometry &g);
+
+// tensor-core path (cs_tc.cu)
+int64_t tc_packed_weight_bytes(const dlwpcs_conv_desc *d, const Geometry &g);
+int tc_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, void *packed,
+                    cudaStream_t st);
+int tc_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed,
+                void *y, cudaStream_t st);
+bool tc_supported(const dlwpcs_conv_desc *d, const Geometry &g, const char **why);
+
+}  // namespace dlwpcs

@@ -1,0 +1,128 @@
+"""Differentiable operators over libdlwpcs: the halo exchange and the (optionally halo-fused) per-face convolution.
+
+Forward semantics follow the reference's DLWP/custom.py:1082-1308 (CubeSpherePadding2D.call) and 921-1002
+(CubeSphereConv2D.call); backward is what TensorFlow autodiff derives from those: dgrad with the halo
+scatter-add, wgrad reduced over the faces sharing a kernel.  All tensors here are channels_last (B,6,H,W,C).
+"""
+import torch
+
+from . import _lib
+
+ACTIVATIONS = {None: (_lib.ACT_NONE, 0.0, 0.0), 'linear': (_lib.ACT_NONE, 0.0, 0.0),
+               'relu': (_lib.ACT_CAPPED_LEAKY_RELU, 0.0, float('inf'))}
+
+
+def resolve_activation(activation):
+    """-> (act code, slope, max) for activations the kernels fuse, or None if it has to be applied separately.
+    ('capped_leaky_relu', slope, max) is keras ReLU(negative_slope, max_value) of Azure/train_cs.py:199."""
+    if isinstance(activation, (tuple, list)) and len(activation) == 3 and activation[0] == 'capped_leaky_relu':
+        return (_lib.ACT_CAPPED_LEAKY_RELU, float(activation[1]), float(activation[2]))
+    try:
+        return ACTIVATIONS.get(activation)
+    except TypeError:
+        return None
+
+
+def _check_cl(x):
+    if x.dim() != 5 or x.shape[1] != 6:
+        raise ValueError('expected a (batch, 6, height, width, channels) tensor, got %r' % (tuple(x.shape),))
+    if x.shape[2] != x.shape[3]:
+        raise ValueError('cubed-sphere faces must be square, got %dx%d' % (x.shape[2], x.shape[3]))
+
+
+class _CubeSpherePad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p):
+        ctx.p = p
+        return _lib.pad_fwd(x.contiguous(), p)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _lib.pad_bwd(dy.contiguous(), ctx.p), None
+
+
+def cube_sphere_pad(x, p):
+    """CubeSpherePadding2D.call on a channels_last tensor (float32 or bfloat16)."""
+    _check_cl(x)
+    if p == 0:
+        return x
+    if p < 0 or p > x.shape[2]:
+        raise ValueError('padding %d out of range for face edge %d' % (p, x.shape[2]))
+    return _CubeSpherePad.apply(x, int(p))
+
+
+class _CubeSphereConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w_eq, w_pol, w_np, b_eq, b_pol, b_np, cfg):
+        x = x.contiguous()
+        b, _, n, _, cin = x.shape
+        kh, kw, wcin, cout = w_eq.shape
+        if wcin != cin:
+            raise ValueError('input has %d channels, kernel expects %d' % (cin, wcin))
+        d = _lib.make_desc(b, n, cin, cout, (kh, kw), cfg['strides'], cfg['dilation'], cfg['halo'], cfg['same'],
+                           cfg['flip_north_pole'], w_np is not None, b_eq is not None, cfg['act'][0], cfg['act'][1],
+                           cfg['act'][2], _lib.dtype_code(x.dtype), _lib.dtype_code(cfg.get('out_dtype', x.dtype)))
+        packed = _lib.pack_weights(d, w_eq, w_pol, w_np, b_eq, b_pol, b_np)
+        y = _lib.conv2d_fwd(d, x, None, packed)
+        ctx.d = d
+        ctx.has = (w_np is not None, b_eq is not None, b_np is not None)
+        ctx.save_for_backward(x, y, w_eq, w_pol, w_np)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, w_eq, w_pol, w_np = ctx.saved_tensors
+        d = ctx.d
+        if d.x_dtype != _lib.F32:
+            raise _lib.DlwpcsError('backward is float32 in this build')
+        dy = dy.contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            packed_t = _lib.pack_weights(d, w_eq, w_pol, w_np, transposed=True)
+            dx = _lib.conv2d_dgrad(d, dy, y, packed_t)
+        dw_eq = dw_pol = dw_np = db_eq = db_pol = db_np = None
+        if any(ctx.needs_input_grad[1:7]):
+            dw_eq, dw_pol, dw_np, db_eq, db_pol, db_np = _lib.conv2d_wgrad(d, x, dy, y)
+        return dx, dw_eq, dw_pol, dw_np, db_eq, db_pol, db_np, None
+
+
+def cube_sphere_conv2d(x, equatorial_kernel, polar_kernel, north_pole_kernel=None, equatorial_bias=None,
+                       polar_bias=None, north_pole_bias=None, strides=(1, 1), padding='valid', dilation_rate=(1, 1),
+                       flip_north_pole=True, halo=0, activation=None, out_dtype=None):
+    """
+    CubeSphereConv2D.call on a channels_last tensor.  `halo` > 0 additionally performs CubeSpherePadding2D(halo) inside
+    the kernel's load stage (x is then the un-padded tensor).  `activation`: None / 'linear' / 'relu' /
+    ('capped_leaky_relu', slope, max) are fused into the epilogue.
+    """
+    _check_cl(x)
+    act = resolve_activation(activation)
+    if act is None:
+        raise ValueError('activation %r cannot be fused; apply it to the output instead' % (activation,))
+    padding = padding.lower()
+    if padding not in ('valid', 'same'):
+        raise ValueError('The `padding` argument must be one of "valid", "same". Received: %s' % padding)
+    cfg = dict(strides=tuple(strides), dilation=tuple(dilation_rate), halo=int(halo), same=padding == 'same',
+               flip_north_pole=bool(flip_north_pole), act=act)
+    if out_dtype is not None:
+        cfg['out_dtype'] = out_dtype
+    return _CubeSphereConv.apply(x, equatorial_kernel, polar_kernel, north_pole_kernel, equatorial_bias, polar_bias,
+                                 north_pole_bias, cfg)
+
+
+class _Act(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        y = _lib.act_fwd(x.contiguous(), *act)
+        ctx.act = act
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return _lib.act_bwd(dy.contiguous(), y, *ctx.act), None
+
+
+def capped_leaky_relu(x, negative_slope=0.1, max_value=10.0):
+    """keras ReLU(negative_slope, max_value) (Azure/train_cs.py:199) as a standalone op."""
+    return _Act.apply(x, (_lib.ACT_CAPPED_LEAKY_RELU, float(negative_slope), float(max_value)))

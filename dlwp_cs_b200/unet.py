@@ -1,0 +1,203 @@
+"""
+The Weyn-2020 cubed-sphere U-Net (``unet2`` of the reference's Azure/train_cs.py:196-228, 277-305) on the engine's
+layers, and a device-resident autoregressive rollout (the loop of DLWP/model/models.py:446-454 without the two
+host<->device copies per step).
+
+  * ``CubeSphereUNet2``  -- nn.Module; training / generic forward through the differentiable operators.
+  * ``RolloutEngine``    -- inference: one kernel launch per CubeSphereConv2D (11 per step); the halo exchange, the
+    average pooling, the nearest up-sampling, the channel concatenation, bias and the capped leaky ReLU all live in that
+    kernel's load stage / epilogue; state, forcing and the forecast ring stay in HBM; the whole multi-step rollout is
+    replayed from one CUDA graph.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .custom import CubeSphereConv2D
+from . import functional as F_cs
+
+RELU = ('capped_leaky_relu', 0.1, 10.0)      # keras ReLU(negative_slope=0.1, max_value=10.) train_cs.py:199
+
+
+def unet2_layer_specs(in_channels, out_channels, base=32):
+    """(name, kernel, Cin, Cout) in execution order -- train_cs.py:209-228 + 277-305."""
+    b = base
+    return [('conv_2d_1', 3, in_channels, b), ('conv_2d_1_2', 3, b, b), ('conv_2d_2', 3, b, 2 * b),
+            ('conv_2d_2_2', 3, 2 * b, 2 * b), ('conv_2d_5_2', 3, 2 * b, 4 * b), ('conv_2d_5', 3, 4 * b, 2 * b),
+            ('conv_2d_6_2', 3, 4 * b, 2 * b), ('conv_2d_6', 3, 2 * b, b), ('conv_2d_7', 3, 2 * b, b),
+            ('conv_2d_7_2', 3, b, b), ('conv_2d_8', 1, b, out_channels)]
+
+
+def _avg_pool(x):      # AveragePooling3D((1,2,2)), channels_last
+    b, f, h, w, c = x.shape
+    return x.reshape(b, f, h // 2, 2, w // 2, 2, c).mean(dim=(3, 5))
+
+
+def _upsample(x):      # UpSampling3D((1,2,2))
+    return x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+
+
+class CubeSphereUNet2(nn.Module):
+    """``unet2``: 10 halo-padded 3x3 CubeSphereConv2D + capped leaky ReLU, two 2x2 poolings with skip connections, and a
+    1x1 output convolution.  channels_last (B,6,N,N,C); N divisible by 4."""
+
+    def __init__(self, in_channels, out_channels, base=32, independent_north_pole=False):
+        super().__init__()
+        self.in_channels, self.out_channels, self.base = in_channels, out_channels, base
+        self.independent_north_pole = independent_north_pole
+        for name, k, ci, co in unet2_layer_specs(in_channels, out_channels, base):
+            last = name == 'conv_2d_8'
+            setattr(self, name, CubeSphereConv2D(
+                co, k, padding='valid', data_format='channels_last', dilation_rate=1,
+                activation='linear' if last else RELU, independent_north_pole=independent_north_pole,
+                flip_north_pole=not independent_north_pole,      # train_cs.py:205-206
+                in_channels=ci, fuse_padding=0 if last else 1, name='output' if last else name))
+
+    def layers_in_order(self):
+        return [getattr(self, s[0]) for s in unet2_layer_specs(self.in_channels, self.out_channels, self.base)]
+
+    def forward(self, x):
+        x0 = self.conv_2d_1_2(self.conv_2d_1(x))
+        x1 = self.conv_2d_2_2(self.conv_2d_2(_avg_pool(x0)))
+        x2 = self.conv_2d_5(self.conv_2d_5_2(_avg_pool(x1)))
+        t = torch.cat([_upsample(x2), x1], dim=-1)
+        t = self.conv_2d_6(self.conv_2d_6_2(t))
+        t = torch.cat([_upsample(t), x0], dim=-1)
+        t = self.conv_2d_7_2(self.conv_2d_7(t))
+        return self.conv_2d_8(t)
+
+    def load_oracle_params(self, params):
+        """params: dict 'layer.equatorial_kernel' -> tensor, as produced by oracle.make_unet2_params (tests / bench)."""
+        with torch.no_grad():
+            for name, p in self.named_parameters():
+                p.copy_(params[name].to(p.dtype))
+
+
+class RolloutEngine(object):
+    """
+    Device-resident forecast loop for a ``CubeSphereUNet2``.
+
+        eng = RolloutEngine(model, batch, n, steps, forcing_channels=4, dtype=torch.bfloat16)
+        ring = eng.run(state, forcing)            # (steps, B, 6, N, N, Cout) on the device
+
+    state: (B,6,N,N,Cout) prognostic channels; forcing: (B,6,N,N,Cf) or per-step (steps,B,6,N,N,Cf) channels appended to
+    the network input each step (insolation / constants, train_cs.py:396-407); the output of step t is the prognostic
+    input of step t+1 (models.py:450-453).
+    """
+
+    def __init__(self, model, batch, n, steps, forcing_channels=0, dtype=torch.float32, use_graph=True,
+                 per_step_forcing=False, device=None):
+        if n % 4 != 0:
+            raise ValueError('unet2 pools twice: face edge must be divisible by 4')
+        self.model, self.batch, self.n, self.steps = model, batch, n, steps
+        self.cf = forcing_channels
+        self.cp = model.out_channels
+        if self.cp + self.cf != model.in_channels:
+            raise ValueError('prognostic (%d) + forcing (%d) channels != model input channels (%d)'
+                             % (self.cp, self.cf, model.in_channels))
+        self.dtype = dtype
+        self.device = device or next(model.parameters()).device
+        if self.device.type != 'cuda':
+            raise _lib.DlwpcsError('RolloutEngine needs the model on a CUDA device')
+        self.use_graph = use_graph
+        self.per_step_forcing = per_step_forcing
+        dt = _lib.dtype_code(dtype)
+        b, base = batch, model.base
+        mk = lambda edge, c: torch.empty((b, 6, edge, edge, c), dtype=dtype, device=self.device)
+        self.state = mk(n, self.cp)
+        fshape = ((steps,) if per_step_forcing else ()) + (b, 6, n, n, max(self.cf, 1))
+        self.forcing = torch.zeros(fshape, dtype=dtype, device=self.device)
+        self.ring = torch.empty((steps, b, 6, n, n, self.cp), dtype=dtype, device=self.device)
+        self.buf = dict(a=mk(n, base), x0=mk(n, base), b=mk(n // 2, 2 * base), x1=mk(n // 2, 2 * base),
+                        c=mk(n // 4, 4 * base), x2=mk(n // 4, 2 * base), d=mk(n // 2, 2 * base), e=mk(n // 2, base),
+                        f=mk(n, base), g=mk(n, base))
+        S, P, U = _lib.SRC_SAME, _lib.SRC_POOL2, _lib.SRC_UP2
+        # (layer, edge, src0, c0, mode0, src1, c1, mode1, dst)
+        plan = [('conv_2d_1', n, 'state', self.cp, S, 'forcing' if self.cf else None, self.cf, S, 'a'),
+                ('conv_2d_1_2', n, 'a', base, S, None, 0, S, 'x0'),
+                ('conv_2d_2', n // 2, 'x0', base, P, None, 0, S, 'b'),
+                ('conv_2d_2_2', n // 2, 'b', 2 * base, S, None, 0, S, 'x1'),
+                ('conv_2d_5_2', n // 4, 'x1', 2 * base, P, None, 0, S, 'c'),
+                ('conv_2d_5', n // 4, 'c', 4 * base, S, None, 0, S, 'x2'),
+                ('conv_2d_6_2', n // 2, 'x2', 2 * base, U, 'x1', 2 * base, S, 'd'),
+                ('conv_2d_6', n // 2, 'd', 2 * base, S, None, 0, S, 'e'),
+                ('conv_2d_7', n, 'e', base, U, 'x0', base, S, 'f'),
+                ('conv_2d_7_2', n, 'f', base, S, None, 0, S, 'g'),
+                ('conv_2d_8', n, 'g', base, S, None, 0, S, 'out')]
+        self.plan = []
+        for name, edge, s0, c0, m0, s1, c1, m1, dst in plan:
+            layer = getattr(model, name)
+            k = layer.kernel_size
+            fused = F_cs.resolve_activation(layer.activation)
+            d = _lib.make_desc(b, edge, c0 + c1, layer.filters, k, (1, 1), (1, 1), layer.fuse_padding, False,
+                               layer.flip_north_pole, layer.independent_north_pole, layer.use_bias, fused[0], fused[1],
+                               fused[2], dt, dt, c0, m0, c1, m1)
+            self.plan.append([name, d, s0, s1, dst, None])
+        self.graph = None
+        self.repack()
+
+    def repack(self):
+        """(Re)pack the layer weights into the kernels' layouts -- call after the model's parameters change."""
+        for item in self.plan:
+            layer = getattr(self.model, item[0])
+            item[5] = _lib.pack_weights(item[1], layer.equatorial_kernel, layer.polar_kernel, layer.north_pole_kernel,
+                                        layer.equatorial_bias, layer.polar_bias, layer.north_pole_bias)
+        self.graph = None
+
+    @property
+    def launches_per_step(self):
+        return len(self.plan)
+
+    def _src(self, key, t):
+        if key is None:
+            return None
+        if key == 'state':
+            return self.state if t == 0 else self.ring[t - 1]
+        if key == 'forcing':
+            return self.forcing[t] if self.per_step_forcing else self.forcing
+        return self.buf[key]
+
+    def _step(self, t):
+        for name, d, s0, s1, dst, packed in self.plan:
+            out = self.ring[t] if dst == 'out' else self.buf[dst]
+            _lib.conv2d_fwd(d, self._src(s0, t), self._src(s1, t), packed, out=out)
+
+    def _enqueue_all(self):
+        for t in range(self.steps):
+            self._step(t)
+
+    def _ensure_graph(self):
+        if self.graph is not None or not self.use_graph:
+            return
+        # warm the halo-table caches and kernel attributes outside the capture
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self._step(0)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._enqueue_all()
+        self.graph = g
+
+    def load_inputs(self, state, forcing=None, non_blocking=True):
+        """Copy initial conditions (host or device tensors, any float dtype) into the engine's resident buffers."""
+        self.state.copy_(state, non_blocking=non_blocking)
+        if self.cf:
+            if forcing is None:
+                raise ValueError('this engine was built with %d forcing channels' % self.cf)
+            self.forcing.copy_(forcing, non_blocking=non_blocking)
+
+    def launch(self):
+        """Enqueue the whole rollout on the current stream (graph replay when enabled); no host synchronisation."""
+        if self.use_graph:
+            self._ensure_graph()
+            self.graph.replay()
+        else:
+            self._enqueue_all()
+        return self.ring
+
+    def run(self, state, forcing=None):
+        self.load_inputs(state, forcing)
+        return self.launch()

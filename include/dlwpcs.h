@@ -1,0 +1,117 @@
+/*
+ * dlwpcs.h -- C ABI of the B200-native cubed-sphere convolution engine (libdlwpcs.so).
+ *
+ * The reference (jweyn/DLWP-CS) has no FFI: its "operator interface" for this path is two Keras layer classes in
+ * DLWP/custom.py.  Each entry point below names the reference code it replaces (file:line relative to the reference
+ * repository).  All tensors are channels_last, face-major:  (batch, 6, edge, edge, channels), faces 4/5 = south/north
+ * pole (custom.py:759-763).  Pointers are plain device pointers unless the function name ends in `_host`; `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  Nothing here allocates caller-visible memory; the
+ * library keeps small per-device caches (halo index tables).  Every function returns 0 on success, non-zero on error;
+ * dlwpcs_last_error() then returns a static, thread-local message.
+ */
+#ifndef DLWPCS_H_
+#define DLWPCS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLWPCS_VERSION 1
+
+enum { DLWPCS_F32 = 0, DLWPCS_BF16 = 1 };
+enum { DLWPCS_ACT_NONE = 0, DLWPCS_ACT_CAPPED_LEAKY_RELU = 1 };       /* keras ReLU(negative_slope, max_value) */
+/* how a fused input source is sampled relative to the convolution's own resolution (edge n):                          */
+enum { DLWPCS_SRC_SAME = 0,      /* source edge n                                                                      */
+       DLWPCS_SRC_POOL2 = 1,     /* source edge 2n, 2x2 mean   == AveragePooling3D((1,2,2))   Azure/train_cs.py:197     */
+       DLWPCS_SRC_UP2 = 2 };     /* source edge n/2, nearest   == UpSampling3D((1,2,2))       Azure/train_cs.py:198     */
+
+/* One CubeSphereConv2D call (custom.py:824-869 constructor arguments + 921-1002 call), optionally with the preceding
+ * CubeSpherePadding2D (custom.py:1082-1308) folded into the load stage (`halo` = p) and the U-Net's
+ * pool / upsample / concatenate (Azure/train_cs.py:282-299) folded into the input sampling.                          */
+typedef struct dlwpcs_conv_desc {
+  int32_t batch;
+  int32_t n;                 /* face edge of the tensor the layer pair sees BEFORE the halo exchange                   */
+  int32_t halo;              /* p of the fused CubeSpherePadding2D; 0 = input is used as is                            */
+  int32_t cin, cout;
+  int32_t kh, kw;            /* kernel_size                                                                             */
+  int32_t stride_h, stride_w;
+  int32_t dil_h, dil_w;      /* dilation_rate                                                                           */
+  int32_t same;              /* 0 = padding 'valid', 1 = 'same' (TensorFlow zero padding, extra on bottom/right)        */
+  int32_t flip_north_pole;   /* custom.py:965-996                                                                       */
+  int32_t independent_north_pole;
+  int32_t use_bias;
+  int32_t act;               /* DLWPCS_ACT_*; applied after bias (the ReLU layer the U-Net applies to every conv)       */
+  float act_slope, act_max;
+  int32_t x_dtype, y_dtype;  /* DLWPCS_F32 / DLWPCS_BF16 (bf16 activations select the tcgen05 tensor-core kernel)       */
+  int32_t c0, mode0;         /* first  input source: channels [0,c0)      and its DLWPCS_SRC_* sampling mode           */
+  int32_t c1, mode1;         /* second input source: channels [c0,c0+c1)  (c1 = 0: none); c0 + c1 == cin               */
+} dlwpcs_conv_desc;
+
+/* Weights in the reference's logical layout (custom.py:880-914): HWIO float32 kernels (kh,kw,cin,cout) and (cout,)
+ * biases.  w_np / b_np only with independent_north_pole; biases only with use_bias.                                  */
+typedef struct dlwpcs_conv_weights {
+  const float *w_eq, *w_pol, *w_np;
+  const float *b_eq, *b_pol, *b_np;
+} dlwpcs_conv_weights;
+
+int dlwpcs_version(void);
+const char *dlwpcs_last_error(void);
+
+/* Output face size of a conv: keras conv_output_length as used by compute_output_shape, custom.py:1004-1030.
+ * `edge_in` is the edge the conv sees (n + 2*halo).                                                                  */
+int dlwpcs_conv_out_edge(int edge_in, int k, int stride, int dilation, int same);
+
+/* Halo index table of CubeSpherePadding2D(p) (custom.py:1198-1308 two-stage composition): lut[f][r][c] = flat source
+ * index f'*n*n + i*n + j.  Host-only, no GPU needed.                                                                  */
+int dlwpcs_pad_lut_host(int n, int p, int32_t *lut /* [6][n+2p][n+2p] */);
+
+/* Standalone CubeSpherePadding2D.call (custom.py:1198-1308): x (B,6,n,n,c) -> y (B,6,n+2p,n+2p,c).                     */
+int dlwpcs_pad_fwd(const void *x, void *y, int batch, int n, int c, int p, int dtype, void *stream);
+/* Its adjoint (TF autodiff of the slices/concats): dx[src] = sum of dy over every padded position reading src.
+ * Deterministic gather over the inverse table (no float atomics).                                                     */
+int dlwpcs_pad_bwd(const void *dy, void *dx, int batch, int n, int c, int p, int dtype, void *stream);
+
+/* Weight packing: HWIO float32 -> the per-face-group layouts the kernels read.  `packed` must hold
+ * dlwpcs_packed_weight_bytes(desc, transposed) bytes.  transposed = 0: forward; 1: dgrad (taps rotated 180 degrees,
+ * cin/cout swapped).  Group 0 = equatorial, 1 = south pole, 2 = north pole (polar or independent kernel, rows flipped
+ * when flip_north_pole -- equivalent to custom.py:969/995 for every stride).                           */
+int64_t dlwpcs_packed_weight_bytes(const dlwpcs_conv_desc *d, int transposed);
+int dlwpcs_pack_weights(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, int transposed, void *packed,
+                        void *stream);
+
+/* CubeSphereConv2D.call (+ optional fused padding / sampling / bias / activation).
+ *   x0, x1 : the input source(s), dtype d->x_dtype;   y : (B,6,Hout,Wout,cout), dtype d->y_dtype.                     */
+int dlwpcs_conv2d_fwd(const dlwpcs_conv_desc *d, const void *x0, const void *x1, const void *packed_w, void *y,
+                      void *stream);
+
+/* Backward of the same (what TF autodiff derives from custom.py:921-1002 and 1198-1308), stride 1 only, float32:
+ *   dgrad: dy (B,6,Hout,Wout,cout) [, y: forward output, to apply the activation derivative] -> dx (B,6,n,n,cin),
+ *          including the halo scatter-add.  `workspace` holds dlwpcs_dgrad_workspace_bytes(d) bytes.
+ *   wgrad: x0 (B,6,n,n,cin), dy [, y] -> HWIO float32 gradients in the reference's parameter order, `workspace` holds
+ *          dlwpcs_wgrad_workspace_bytes(d) bytes.                                                                     */
+int64_t dlwpcs_dgrad_workspace_bytes(const dlwpcs_conv_desc *d);
+int dlwpcs_conv2d_dgrad(const dlwpcs_conv_desc *d, const void *dy, const void *y, const void *packed_w_t, void *dx,
+                        void *workspace, void *stream);
+int64_t dlwpcs_wgrad_workspace_bytes(const dlwpcs_conv_desc *d);
+typedef struct dlwpcs_conv_wgrads {
+  float *dw_eq, *dw_pol, *dw_np;
+  float *db_eq, *db_pol, *db_np;
+} dlwpcs_conv_wgrads;
+int dlwpcs_conv2d_wgrad(const dlwpcs_conv_desc *d, const void *x0, const void *dy, const void *y,
+                        const dlwpcs_conv_wgrads *g, void *workspace, void *stream);
+
+/* Elementwise / resampling steps either side of the conv (Azure/train_cs.py:197-199), standalone, float32 or bf16.   */
+int dlwpcs_act_fwd(const void *x, void *y, int64_t count, int act, float slope, float maxv, int dtype, void *stream);
+int dlwpcs_act_bwd(const void *dy, const void *y, void *dx, int64_t count, int act, float slope, float maxv,
+                   int dtype, void *stream);
+
+/* Host-buffer entry point: the call a reference-side binding makes with numpy arrays.  Copies x (and weights) to the
+ * device, runs pad(halo)+conv, copies y back; synchronous.                                                            */
+int dlwpcs_conv2d_fwd_host(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, const void *x_host, void *y_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLWPCS_H_ */

@@ -17,27 +17,11 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, '..', '..', 'oracle'))
+sys.path.insert(0, HERE)
 import tf_shim  # noqa: E402
+from cases import CONV_CASES, PAD_CASES  # noqa: E402
 
 ref = tf_shim.load_reference_custom()
-
-PAD_CASES = [(4, 1), (5, 2), (8, 3), (48, 1), (24, 1), (12, 1), (6, 2)]
-
-# (name, ctor kwargs, batch, H (already padded input edge), Cin)
-CONV_CASES = [
-    ('k3_valid_flip', dict(filters=5, kernel_size=3), 2, 8, 4),
-    ('k3_valid_noflip', dict(filters=5, kernel_size=3, flip_north_pole=False), 2, 8, 4),
-    ('k3_indep_north', dict(filters=3, kernel_size=3, independent_north_pole=True, flip_north_pole=False), 1, 7, 2),
-    ('k3_indep_north_flip', dict(filters=3, kernel_size=3, independent_north_pole=True, flip_north_pole=True), 1, 7, 2),
-    ('k1_output', dict(filters=6, kernel_size=1), 2, 6, 8),
-    ('k3_nobias', dict(filters=4, kernel_size=3, use_bias=False), 1, 6, 3),
-    ('k3_same', dict(filters=4, kernel_size=3, padding='same'), 1, 6, 3),
-    ('k3_same_stride2', dict(filters=4, kernel_size=3, padding='same', strides=2), 1, 7, 3),
-    ('k3_valid_stride2', dict(filters=4, kernel_size=3, strides=2), 1, 8, 3),
-    ('k3_dilation2', dict(filters=4, kernel_size=3, dilation_rate=2), 1, 9, 3),
-    ('k23_rect', dict(filters=3, kernel_size=(2, 3)), 1, 7, 2),
-    ('k5_valid', dict(filters=2, kernel_size=5), 1, 9, 2),
-]
 
 
 def reference_pad(x, p, data_format):

@@ -1,0 +1,105 @@
+"""CPU-only checks of the C-ABI library: it loads, exports every symbol include/dlwpcs.h declares, its host-side halo
+table equals the reference-generated golden tables, and the layer classes mirror the reference's constructor behaviour."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from dlwp_cs_b200 import build, _lib
+    build.build()
+    return _lib
+
+
+def test_exports_match_header(lib):
+    hdr = open(os.path.join(ROOT, 'include', 'dlwpcs.h')).read()
+    declared = set(re.findall(r'\b(dlwpcs_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(lib.EXPORTED)
+    cdll = ctypes.CDLL(lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(cdll, name), name
+    assert lib.load().dlwpcs_version() == 1
+
+
+def test_desc_struct_matches_header(lib):
+    hdr = open(os.path.join(ROOT, 'include', 'dlwpcs.h')).read()
+    body = hdr[hdr.index('typedef struct dlwpcs_conv_desc {'):hdr.index('} dlwpcs_conv_desc;')]
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    fields = []
+    for decl in re.findall(r'(?:int32_t|float)\s+([^;]+);', body):
+        fields += [f.strip() for f in decl.split(',')]
+    assert fields == [f[0] for f in lib.ConvDesc._fields_]
+
+
+@pytest.mark.parametrize('n,p', [(4, 1), (5, 2), (8, 3), (48, 1), (24, 1), (12, 1), (6, 2)])
+def test_pad_lut_vs_reference_golden(lib, n, p, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'pad_luts.npz'))
+    np.testing.assert_array_equal(lib.pad_lut(n, p), g['cl_n%d_p%d' % (n, p)])
+
+
+@pytest.mark.parametrize('n,p', [(96, 1), (48, 2), (7, 3), (3, 3), (2, 1)])
+def test_pad_lut_vs_oracle(lib, n, p):
+    import cs_oracle
+    np.testing.assert_array_equal(lib.pad_lut(n, p), cs_oracle.pad_lut(n, p))
+
+
+def test_out_edge_matches_oracle(lib):
+    import cs_oracle
+    for n in (5, 8, 9, 48):
+        for k in (1, 2, 3, 5):
+            for s in (1, 2, 3):
+                for d in (1, 2):
+                    for same in (False, True):
+                        if not same and n < (k - 1) * d + 1:
+                            continue
+                        assert lib.conv_out_edge(n, k, s, d, same) == \
+                            cs_oracle.conv_output_length(n, k, 'same' if same else 'valid', s, d)
+
+
+def test_errors_are_reported(lib):
+    with pytest.raises(lib.DlwpcsError):
+        lib.pad_lut(4, 9)
+    d = lib.make_desc(1, 4, 3, 3, c0=2, c1=0)
+    assert lib.load().dlwpcs_packed_weight_bytes(ctypes.byref(d), 0) == -1
+    assert b'c0 + c1' in lib.load().dlwpcs_last_error()
+
+
+def test_no_cpu_fallback(lib):
+    from dlwp_cs_b200 import CubeSpherePadding2D
+    with pytest.raises(lib.DlwpcsError):
+        CubeSpherePadding2D(1, data_format='channels_last')(torch.zeros(1, 6, 4, 4, 2))
+
+
+def test_layer_constructors_mirror_reference():
+    from dlwp_cs_b200 import CubeSphereConv2D, CubeSpherePadding2D
+    with pytest.raises(ValueError):          # the reference's declared default (1, 1) is rejected by keras too
+        CubeSpherePadding2D((1, 1))
+    pad = CubeSpherePadding2D(2, data_format='channels_last')
+    assert pad.padding == ((0, 0), (2, 2), (2, 2))
+    assert pad.compute_output_shape((None, 6, 48, 48, 7)) == (None, 6, 52, 52, 7)
+    assert CubeSpherePadding2D((5, 1, 1)).padding == ((0, 0), (1, 1), (1, 1))
+    conv = CubeSphereConv2D(32, 3, data_format='channels_last', independent_north_pole=True, in_channels=18)
+    names = [n for n, _ in conv.named_parameters()]
+    assert names == ['equatorial_kernel', 'polar_kernel', 'north_pole_kernel', 'equatorial_bias', 'polar_bias',
+                     'north_pole_bias']                      # custom.py:882-914 creation order
+    assert tuple(conv.equatorial_kernel.shape) == (3, 3, 18, 32)
+    limit = np.sqrt(6.0 / (9 * 18 + 9 * 32))
+    assert float(conv.equatorial_kernel.abs().max()) <= limit and float(conv.equatorial_bias.abs().max()) == 0.0
+    assert conv.compute_output_shape((4, 6, 50, 50, 18)) == (4, 6, 48, 48, 32)
+    cf = CubeSphereConv2D(8, (3, 3), strides=2, padding='SAME')
+    assert cf.data_format == 'channels_first' and cf.compute_output_shape((4, 5, 6, 9, 9)) == (4, 8, 6, 5, 5)
+    cfg = conv.get_config()
+    assert cfg['filters'] == 32 and cfg['kernel_size'] == (3, 3) and cfg['flip_north_pole'] is True
+    lazy = CubeSphereConv2D(4, 3, data_format='channels_last')
+    assert lazy.has_uninitialized_params()
+    with pytest.raises(ValueError):
+        CubeSphereConv2D(4, 3, padding='full')
+    with pytest.raises(TypeError):
+        CubeSphereConv2D(4, 3, bogus=1)

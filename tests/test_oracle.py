@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import cs_oracle as O
-from tests.golden.make_golden import CONV_CASES, PAD_CASES
+from tests.golden.cases import CONV_CASES, PAD_CASES
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
