@@ -268,3 +268,66 @@ def rollout(params, state, forcing, steps, exact=True, host_hop=False):
             p = torch.from_numpy(np.array(p.numpy(), copy=True))
         outs.append(p)
     return torch.stack(outs, dim=0)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Timed CPU baseline: the same arithmetic arranged the way a CPU likes it (one LUT gather for the halo exchange instead
+# of ~70 strided slices/concats, the four equatorial faces batched into one oneDNN convolution).  Checked against the
+# literal restatement above in tests/test_oracle.py; used only by bench.py's cpu_baseline / --impl reference legs.
+# ----------------------------------------------------------------------------------------------------------------------
+_LUT_CACHE = {}
+
+
+def cube_sphere_pad_fast(x, p):
+    b, _, n, _, c = x.shape
+    key = (n, p)
+    if key not in _LUT_CACHE:
+        _LUT_CACHE[key] = torch.from_numpy(pad_lut(n, p).reshape(-1))
+    h = n + 2 * p
+    return x.reshape(b, 6 * n * n, c).index_select(1, _LUT_CACHE[key]).reshape(b, 6, h, h, c)
+
+
+def _conv_nhwc(x, w):
+    # x (B',H,W,C) contiguous == NCHW tensor in channels_last memory format; w HWIO
+    y = F.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1))
+    return y.permute(0, 2, 3, 1)
+
+
+def cube_sphere_conv2d_fast(x, w_eq, w_pol, b_eq, b_pol):
+    """stride 1 / 'valid' / shared polar kernel / flip_north_pole=True only (the U-Net's configuration)."""
+    b, _, h, w, c = x.shape
+    y_eq = _conv_nhwc(x[:, :4].reshape(b * 4, h, w, c), w_eq) + b_eq
+    ho, wo, co = y_eq.shape[1:]
+    y4 = _conv_nhwc(x[:, 4], w_pol) + b_pol
+    y5 = (_conv_nhwc(x[:, 5].flip(1), w_pol) + b_pol).flip(1)
+    return torch.cat([y_eq.reshape(b, 4, ho, wo, co), y4.unsqueeze(1), y5.unsqueeze(1)], dim=1)
+
+
+def unet2_fast(params, x):
+    def cs(name, t, pad=1, act=True):
+        if pad:
+            t = cube_sphere_pad_fast(t, pad)
+        t = cube_sphere_conv2d_fast(t, params[name + '.equatorial_kernel'], params[name + '.polar_kernel'],
+                                    params[name + '.equatorial_bias'], params[name + '.polar_bias'])
+        return capped_leaky_relu(t) if act else t
+    x0 = cs('conv_2d_1_2', cs('conv_2d_1', x))
+    x1 = cs('conv_2d_2_2', cs('conv_2d_2', avg_pool_2x2(x0)))
+    x2 = cs('conv_2d_5', cs('conv_2d_5_2', avg_pool_2x2(x1)))
+    t = torch.cat([upsample_2x2(x2), x1], dim=-1)
+    t = cs('conv_2d_6', cs('conv_2d_6_2', t))
+    t = torch.cat([upsample_2x2(t), x0], dim=-1)
+    t = cs('conv_2d_7_2', cs('conv_2d_7', t))
+    return cs('conv_2d_8', t, pad=0, act=False)
+
+
+def rollout_fast(params, state, forcing, steps, host_hop=True):
+    """``rollout`` on the fast arrangement, with the numpy hop per step of keras ``Model.predict`` (models.py:446-454)."""
+    outs = []
+    p = state
+    for _ in range(steps):
+        xin = p if forcing is None else torch.cat([p, forcing], dim=-1)
+        p = unet2_fast(params, xin)
+        if host_hop:
+            p = torch.from_numpy(np.array(p.numpy(), copy=True))
+        outs.append(p)
+    return torch.stack(outs, dim=0)
