@@ -362,7 +362,7 @@ static int64_t fp32_packed_floats(const dlwpcs_conv_desc *d, int transposed) {
 int64_t dlwpcs_packed_weight_bytes(const dlwpcs_conv_desc *d, int transposed) {
   Geometry g;
   if (check_common(d, &g)) return -1;
-  if (d->x_dtype == DLWPCS_BF16 && !transposed) return tc_packed_weight_bytes(d, g);
+  if (d->x_dtype == DLWPCS_BF16) return tc_packed_weight_bytes(d, g, transposed);
   return fp32_packed_floats(d, transposed) * 4;
 }
 
@@ -374,7 +374,7 @@ int dlwpcs_pack_weights(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w,
   CS_CHECK(!d->independent_north_pole || w->w_np, "independent_north_pole needs w_np");
   CS_CHECK(transposed || !d->use_bias || (w->b_eq && w->b_pol && (!d->independent_north_pole || w->b_np)),
            "use_bias needs biases");
-  if (d->x_dtype == DLWPCS_BF16 && !transposed) return tc_pack_weights(d, g, w, packed, (cudaStream_t)stream);
+  if (d->x_dtype == DLWPCS_BF16) return tc_pack_weights(d, g, w, transposed, packed, (cudaStream_t)stream);
   return fp32_pack_weights(d, w, transposed, (float *)packed, (cudaStream_t)stream);
 }
 

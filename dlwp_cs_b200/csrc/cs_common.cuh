@@ -61,9 +61,9 @@ int fp32_conv_wgrad(const dlwpcs_conv_desc *d, const Geometry &g, const float *x
 int64_t fp32_wgrad_workspace_bytes(const dlwpcs_conv_desc *d, const Geometry &g);
 
 // tensor-core path (cs_tc.cu)
-int64_t tc_packed_weight_bytes(const dlwpcs_conv_desc *d, const Geometry &g);
-int tc_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, void *packed,
-                    cudaStream_t st);
+int64_t tc_packed_weight_bytes(const dlwpcs_conv_desc *d, const Geometry &g, int transposed);
+int tc_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, int transposed,
+                    void *packed, cudaStream_t st);
 int tc_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed,
                 void *y, cudaStream_t st);
 bool tc_supported(const dlwpcs_conv_desc *d, const Geometry &g, const char **why);
