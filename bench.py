@@ -235,7 +235,8 @@ def main():
 
     state, forcing = synth_inputs(args.batch, seed=rank)
     h_state, h_forcing = state.to(tdt).pin_memory(), forcing.to(tdt).pin_memory()
-    h_ring = torch.empty(eng.ring.shape, dtype=tdt).pin_memory()
+    h_ring = torch.empty(eng.forecast.shape, dtype=tdt).pin_memory()
+    d_out = torch.empty(eng.forecast.shape, dtype=tdt, device=dev)      # forecast without the engine's pad channels
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
     # ---------------- device-resident arm: inputs already in HBM
@@ -260,7 +261,8 @@ def main():
     # ---------------- end-to-end arm: pinned host inputs in, forecast ring out, every step
     for _ in range(2):
         eng.run(h_state, h_forcing)
-        h_ring.copy_(eng.ring, non_blocking=True)
+        d_out.copy_(eng.forecast)
+        h_ring.copy_(d_out, non_blocking=True)
     barrier()
     ev2 = []
     for _ in range(args.steps):
@@ -268,7 +270,8 @@ def main():
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         eng.run(h_state, h_forcing)
-        h_ring.copy_(eng.ring, non_blocking=True)
+        d_out.copy_(eng.forecast)
+        h_ring.copy_(d_out, non_blocking=True)
         e.record()
         ev2.append((s, e))
     barrier()

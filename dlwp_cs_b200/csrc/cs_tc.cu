@@ -1,4 +1,4 @@
-// tcgen05 (sm_100a) bf16 implicit-GEMM kernel of the cubed-sphere convolution.
+// tcgen05 (sm_100a) bf16 implicit-GEMM kernel of the cubed-sphere convolution: persistent, warp-specialised, pipelined.
 //
 // Reference semantics: DLWP/custom.py:921-1002 (CubeSphereConv2D.call) with the preceding CubeSpherePadding2D
 // (custom.py:1198-1308) and the U-Net's pool / upsample / concatenate (Azure/train_cs.py:197-199, 282-299) folded
@@ -10,53 +10,71 @@
 //         same shared-memory patch: the A operand descriptor of tap (u,v) is the patch base + (u*dh*Wv + v*dw) rows.
 //   A     the patch, K-major without swizzle: [channel slab of 8][patch pixel][8 bf16] -- core matrices of 8 pixels x
 //         16 bytes are contiguous (SBO = 128 B), slabs are LBO apart, and a row offset is a plain +16 B per pixel.
-//   W     packed once per layer in exactly the shared-memory image, streamed through an mbarrier ring by TMA bulk copy.
-//   D     fp32 in tensor memory: MB accumulators of 128 lanes x CoutP columns.
-// Warp roles (192 threads): warp 0 = TMA weight producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = patch loaders (halo gather through the index table, cp.async 16 B per pixel-slab; 2x2 mean or scalar
-// gathers go through registers) and then the epilogue (tcgen05.ld -> bias/activation -> global stores).
+//   W     packed once per layer in exactly the shared-memory image; TMA bulk copies through an mbarrier ring, kept
+//         resident across tiles of the same face group when the whole set fits.
+//   D     fp32 in tensor memory, double buffered: AS x MB accumulators of 128 lanes x CoutP columns.
+// A tile is MB consecutive 128-row blocks of one face; a CTA (one per SM) walks tiles blockIdx.x, +gridDim.x, ...
+// Warp roles (576 threads): warp 16 = TMA weight producer, warp 17 = TMEM allocator + MMA issuer, warps 8..15 = epilogue
+// (tcgen05.ld -> bias / activation -> global; two warps per TMEM lane quarter), warps 0..7 = patch loaders: the halo
+// exchange, pooling, upsampling and concatenation are one table lookup per patch row (physical source pixel or -1 =
+// zero) followed by 16-byte cp.async gathers; they run up to PS-1 tiles ahead of the MMA warp.
+// tcgen05.mma in SS mode is shared-memory-bandwidth paced (measured, tools/umma_probe.cu: M128 K16 costs
+// max(N/2, (4 KB + N*32 B) / 128 B) cycles: 41.7 / 48.8 / 65 / 130 for N = 32 / 64 / 128 / 256), so the issue loop is
+// kept free of divisions and table-driven: one LDS per (chunk, tap) unit, then MB x KC/16 back-to-back MMAs.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <map>
+#include <mutex>
+#include <vector>
 #include "cs_common.cuh"
 
 namespace dlwpcs {
 
 namespace {
 
-constexpr int TC_THREADS = 192;
-constexpr int TC_LOADERS = 128;
-constexpr int MAX_CHUNKS = 8;
-constexpr int MAX_STAGES = 8;
-constexpr int MAX_MB = 8;
+// warps 0-7 loaders, 8-15 epilogue, 16 TMA weight producer, 17 MMA issuer.  The scheduler favours the highest warp id of
+// a sub-partition (B300_MICROARCH.md), so the latency-critical MMA issuer gets the last warp.
+constexpr int TC_THREADS = 576;
+constexpr int TC_LOADERS = 256;
+constexpr int TC_EPI = 256;
+constexpr int LOAD_WARP0 = 0, EPI_WARP0 = 8, TMA_WARP = 16, MMA_WARP = 17;
+constexpr int MAX_UNITS = 256;     // (K chunk, tap) pairs of one layer
+constexpr int MAX_STAGES = 8;     // weight ring
+constexpr int MAX_PS = 4;         // patch stages
+constexpr int SMEM_CAP = 227 * 1024;
 
 struct TcPlan {
-  int CinP, CoutP, KC, nch, SPC;     // padded channels, channels per K chunk, chunks, 8-channel slabs per chunk
-  int taps, NU, UPS, NST, nstages;   // weight units (chunk,tap), units per ring stage, ring depth, total stage loads
-  int unitBytes, stageBytes;
+  int CinP, CoutP, KC, nch, SPC, S;  // padded channels, channels per weight K chunk, chunks, slabs per chunk, slabs
+  int taps, NU, UPS, NST, nstages;   // weight units (chunk,tap), units per ring stage, ring depth, stage loads per set
+  int unitBytes, stageBytes, resident;
   int Wv, Hv, Q, nmb, haloExt;       // virtual face, linear outputs per face, 128-row blocks per face, patch overhang
-  int MB, tiles, NPIXp, slabBytes;   // m-blocks per CTA, CTAs per face, patch rows (padded), bytes per slab
-  int tmemCols;
+  int MB, tpf, NPIXp, slabBytes;     // m-blocks per tile, tiles per face, patch rows (padded), bytes per slab
+  int patchBytes, PS, AS, tmemCols;  // bytes per patch stage, patch stages, accumulator stages
+  int G;                             // patch-table entries per face
   int smemBytes;
   int64_t groupBytes;                // packed weights per face group
-  int vec;                           // 16-byte gather path usable
+  int vec, logS;                     // 16-byte gather path usable; log2(S) or -1
 };
 
 struct TcP {
   const __nv_bfloat16 *x0, *x1;
-  const int32_t *lut;
+  const int32_t *tab0, *tab1;   // [6][G] physical source pixel within one batch element, -1 = zero
   const uint8_t *wpack;
-  const float *bias;        // [3][CoutP] fp32 (zeros when the layer has no bias)
+  const float *bias;            // [3][CoutP] fp32 (zeros when the layer has no bias)
   void *y;
-  const void *mask_y;       // dgrad: forward output whose activation derivative scales the gathered dy (nullptr: none)
+  const void *mask_y;           // dgrad: forward output whose activation derivative scales the gathered dy
   int y_f32, mask_f32;
-  int n, Hin, Win, Hout, Wout;
+  int batch, n, Hout, Wout;
   int cin, cout, c0, c1, mode0, mode1;
+  int ppb0, ppb1;               // pixels per batch element of each source tensor
   int kw, dh, dw;
-  int pt[3], pl;
   int act;
   float slope, maxv;
   int mask_act;
   float mask_slope, mask_max;
+  long long *dbg;               // optional phase timestamps (DLWPCS_TC_TIMING=1)
+  int dbg_notab;                // timing experiment only: skip the table lookups (wrong results)
   TcPlan pl_;
 };
 
@@ -92,23 +110,37 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// arrive on the mbarrier once all cp.async issued so far by this thread have landed (no increment of the pending count)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_dyn(int pending) {
   switch (pending) {
     case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
     case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
     case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-    case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
-    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
   }
+}
+__device__ __forceinline__ void st_shared16(uint32_t dst, const uint4 &o) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xFFFFFFFF;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
                : "memory");
@@ -117,6 +149,10 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem]: bf16 inputs, fp32 accumulation, M = 128; N and the operand majors come from idesc.
+// Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor), K-major without swizzle: low word = start address >> 4
+// | leading byte offset >> 4 (distance between the two 8-channel core matrices of a K = 16 step) << 16; high word =
+// stride byte offset >> 4 (distance between 8-row groups) | descriptor version 1 << 14.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
@@ -139,13 +175,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): start address, leading byte offset
-// (between the two 8-channel core matrices of one K=16 step), stride byte offset (between 8-row groups), version 1.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-
 __device__ __forceinline__ float act_apply(float v, int act, float slope, float maxv) {
   if (act == DLWPCS_ACT_CAPPED_LEAKY_RELU) v = v < 0.f ? slope * v : fminf(v, maxv);
   return v;
@@ -154,7 +183,6 @@ __device__ __forceinline__ float act_grad_from_y(float y, int act, float slope, 
   if (act == DLWPCS_ACT_CAPPED_LEAKY_RELU) return y < 0.f ? slope : (y < maxv ? 1.f : 0.f);
   return 1.f;
 }
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t *>(&t);
@@ -168,278 +196,393 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4 &v, float *f) {
   }
 }
 
-// physical pixel index (into a (B,6,e,e,C) tensor) of logical source pixel s = f*n*n + i*n + j for one input source
-__device__ __forceinline__ int phys_pixel(int s, int n, int mode, int b) {
-  if (mode == DLWPCS_SRC_SAME) return b * 6 * n * n + s;
-  const int nn = n * n;
-  const int f = s / nn, rem = s - f * nn, i = rem / n, j = rem - i * n;
-  if (mode == DLWPCS_SRC_UP2) {
-    const int h = n >> 1;
-    return ((b * 6 + f) * h + (i >> 1)) * h + (j >> 1);
+// debug timeline (DLWPCS_TC_TIMING=1): timestamps of the CTA in the middle of the grid at its DBG_K-th tile
+constexpr int DBG_K = 6;
+__device__ __forceinline__ void stamp(const TcP &P, int slot, int k, bool who) {
+  if (P.dbg && who && blockIdx.x == gridDim.x / 2 && (k == DBG_K || (slot == 11 && k == DBG_K + 1) || slot == 0))
+    P.dbg[slot] = clock64();
+}
+
+// tile id -> (batch, face, tile in face).  Tiles are enumerated face-group-major (equatorial faces of every sample, then
+// the south-pole faces, then the north-pole faces) so that a CTA changes weight set at most twice.
+struct TileInfo {
+  int b, f, grp, tf;
+};
+__device__ __forceinline__ TileInfo decode_tile(int id, int batch, int tpf) {
+  TileInfo t;
+  const int eq = 4 * batch * tpf, pol = batch * tpf;
+  if (id < eq) {
+    const int bf = id / tpf;
+    t.tf = id - bf * tpf;
+    t.b = bf >> 2;
+    t.f = bf & 3;
+    t.grp = 0;
+  } else {
+    int r = id - eq;
+    t.grp = 1;
+    if (r >= pol) { r -= pol; t.grp = 2; }
+    t.b = r / tpf;
+    t.tf = r - t.b * tpf;
+    t.f = 3 + t.grp;
   }
-  const int h = n * 2;  // POOL2: top-left pixel of the 2x2 block
-  return ((b * 6 + f) * h + 2 * i) * h + 2 * j;
+  return t;
+}
+
+// One 8-channel slab of one patch row through registers: 2x2 mean, activation-derivative mask, or plain copy.
+__device__ __forceinline__ uint4 gather_regs(const TcP &P, const __nv_bfloat16 *src, int C, int mode, size_t pix, int cc,
+                                             int w2) {
+  float a[8];
+  if (mode == DLWPCS_SRC_POOL2) {
+    float t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (pix + dy * w2 + dx) * C + cc));
+        unpack_bf16x8(v, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += t[k];
+      }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] *= 0.25f;
+  } else {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + pix * C + cc));
+    unpack_bf16x8(v, a);
+  }
+  if (P.mask_y) {
+    float m[8];
+    if (P.mask_f32) {
+      const float4 *mp = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(P.mask_y) + pix * C + cc);
+      const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+      m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w; m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
+    } else {
+      unpack_bf16x8(
+          __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(P.mask_y) + pix * C + cc)), m);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] *= act_grad_from_y(m[k], P.mask_act, P.mask_slope, P.mask_max);
+  }
+  return make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ TcP P) {
+template <int MBT, int KC16T>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcP P) {
   extern __shared__ uint8_t smem_raw[];
   const TcPlan &L = P.pl_;
-  // carve: [barriers 256 B][patch][weight ring][pixel tables]
+  // carve: [barriers + tmem slot: 512 B][unit table 2 KB][bias 3*CoutP fp32][patch stages][weight ring]
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar_wfull = base, bar_wempty = base + 8 * MAX_STAGES, bar_pfull = base + 16 * MAX_STAGES,
-                 bar_acc = base + 16 * MAX_STAGES + 8 * MAX_CHUNKS, tmem_slot = bar_acc + 8;
-  const uint32_t patch = base + 256;
-  const uint32_t wring = patch + (uint32_t)(L.CinP / 8) * L.slabBytes;
-  int *s_pix0 = reinterpret_cast<int *>(gen + 256 + (size_t)(L.CinP / 8) * L.slabBytes + (size_t)L.NST * L.stageBytes);
-  int *s_pix1 = s_pix0 + L.NPIXp;
+  const uint32_t bar_wfull = base, bar_wempty = base + 64, bar_pfull = base + 128, bar_pempty = base + 160,
+                 bar_afull = base + 192, bar_aempty = base + 208, tmem_slot = base + 224;
+  uint2 *s_unit = reinterpret_cast<uint2 *>(gen + 512);
+  float *s_bias = reinterpret_cast<float *>(gen + 512 + MAX_UNITS * 8);
+  const uint32_t patch0 = base + 512 + MAX_UNITS * 8 + (uint32_t)(3 * L.CoutP * 4);
+  const uint32_t wring = patch0 + (uint32_t)L.PS * L.patchBytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x, bf = blockIdx.y, f = bf % 6, b = bf / 6;
-  const int grp = f < 4 ? 0 : f - 3;
-  const int mb0 = tile * L.MB;
-  const int MBc = min(L.MB, L.nmb - mb0);
-  const int q0 = mb0 * 128;
-  const int npix = MBc * 128 + L.haloExt;
+  const int ntiles = 6 * P.batch * L.tpf;
 
   if (tid == 0) {
     for (int i = 0; i < L.NST; ++i) {
       mbar_init(bar_wfull + 8 * i, 1);
       mbar_init(bar_wempty + 8 * i, 1);
     }
-    for (int i = 0; i < L.nch; ++i) mbar_init(bar_pfull + 8 * i, TC_LOADERS);
-    mbar_init(bar_acc, 1);
+    for (int i = 0; i < L.PS; ++i) {
+      mbar_init(bar_pfull + 8 * i, TC_LOADERS);
+      mbar_init(bar_pempty + 8 * i, 1);
+    }
+    for (int i = 0; i < L.AS; ++i) {
+      mbar_init(bar_afull + 8 * i, 1);
+      mbar_init(bar_aempty + 8 * i, TC_EPI);
+    }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)L.tmemCols);
+  for (int i = tid; i < 3 * L.CoutP; i += TC_THREADS) s_bias[i] = P.bias[i];
+  // per (chunk, tap) unit: A descriptor offset (>>4) inside a patch stage; B ring offset (>>4) | wait / release flags
+  for (int un = tid; un < L.NU; un += TC_THREADS) {
+    const int kc = un / L.taps, tap = un - kc * L.taps, u = tap / P.kw, v = tap - u * P.kw;
+    const int uis = un % L.UPS, sidx = un / L.UPS;
+    const uint32_t a_off = ((uint32_t)(kc * L.SPC) * L.slabBytes + (uint32_t)(u * P.dh * L.Wv + v * P.dw) * 16u) >> 4;
+    const uint32_t b_off = ((uint32_t)uis * L.unitBytes) >> 4;
+    const uint32_t flags = (uis == 0 ? 1u : 0u) | ((uis == L.UPS - 1 || un == L.NU - 1) ? 2u : 0u);
+    s_unit[un] = make_uint2(a_off, b_off | (flags << 28) | ((uint32_t)sidx << 20));
+  }
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, (uint32_t)L.tmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(gen + (tmem_slot - base));
+  stamp(P, 0, 0, tid == 0);
 
-  if (warp == 0) {
-    // ===== weight producer: TMA bulk copies of whole ring stages =====
+  if (warp == TMA_WARP) {
+    // ===== weight producer: TMA bulk copies of whole ring stages, skipped while the resident set stays valid =====
     if (lane == 0) {
-      const uint8_t *wg = P.wpack + (size_t)grp * L.groupBytes;
-      for (int s = 0; s < L.nstages; ++s) {
-        const int st = s % L.NST, ph = (s / L.NST) & 1;
-        mbar_wait(bar_wempty + 8 * st, ph ^ 1);
-        const int units = min(L.UPS, L.NU - s * L.UPS);
-        const uint32_t bytes = (uint32_t)units * L.unitBytes;
-        mbar_expect_tx(bar_wfull + 8 * st, bytes);
-        tma_bulk_g2s(wring + st * L.stageBytes, wg + (size_t)s * L.stageBytes, bytes, bar_wfull + 8 * st);
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L.CoutP >> 3) << 17) | (8u << 24);
-      int unit = 0, st = 0, ph = 0;
-      for (int kc = 0; kc < L.nch; ++kc) {
-        mbar_wait(bar_pfull + 8 * kc, 0);
-        tc_fence_after();
-        for (int tap = 0; tap < L.taps; ++tap) {
-          const int uis = unit % L.UPS;
-          if (uis == 0) {
-            mbar_wait(bar_wfull + 8 * st, ph);
-            tc_fence_after();
-          }
-          const int u = tap / P.kw, v = tap - u * P.kw;
-          const uint32_t a0 = patch + (uint32_t)(kc * L.SPC) * L.slabBytes + (uint32_t)(u * P.dh * L.Wv + v * P.dw) * 16u;
-          const uint32_t b0 = wring + st * L.stageBytes + uis * L.unitBytes;
-          for (int mb = 0; mb < MBc; ++mb) {
-            for (int j = 0; j < L.KC / 16; ++j) {
-              const uint64_t ad = make_desc(a0 + (uint32_t)(2 * j) * L.slabBytes + (uint32_t)mb * 2048u, L.slabBytes, 128);
-              const uint64_t bd = make_desc(b0 + (uint32_t)(2 * j) * L.CoutP * 16u, (uint32_t)L.CoutP * 16u, 128);
-              umma_bf16(tmem_base + (uint32_t)(mb * L.CoutP), ad, bd, idesc, (unit > 0 || j > 0) ? 1u : 0u);
-            }
-          }
-          ++unit;
-          if (unit % L.UPS == 0 || unit == L.NU) {
-            umma_commit(bar_wempty + 8 * st);
-            if (++st == L.NST) { st = 0; ph ^= 1; }
-          }
+      int st = 0, ph = 0, prev_grp = -1;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int grp = decode_tile(tile, P.batch, L.tpf).grp;
+        if (L.resident && grp == prev_grp) continue;
+        prev_grp = grp;
+        const uint8_t *wg = P.wpack + (size_t)grp * L.groupBytes;
+        for (int s = 0; s < L.nstages; ++s) {
+          mbar_wait(bar_wempty + 8 * st, ph ^ 1);
+          const int units = min(L.UPS, L.NU - s * L.UPS);
+          const uint32_t bytes = (uint32_t)units * L.unitBytes;
+          mbar_expect_tx(bar_wfull + 8 * st, bytes);
+          tma_bulk_g2s(wring + st * L.stageBytes, wg + (size_t)s * L.stageBytes, bytes, bar_wfull + 8 * st);
+          if (++st == L.NST) { st = 0; ph ^= 1; }
         }
       }
-      umma_commit(bar_acc);
     }
-  } else {
-    // ===== patch loaders, then epilogue =====
-    const int lt = tid - 64;
-    // phase 1: logical source pixel of every patch row, mapped to the physical pixel of each input source
-    for (int i = lt; i < npix; i += TC_LOADERS) {
-      const int g = q0 + i;
-      const int rv = g / L.Wv, cv = g - rv * L.Wv;
-      const int r = rv - P.pt[grp], c = cv - P.pl;
-      int p0 = -1, p1 = -1;
-      if (r >= 0 && r < P.Hin && c >= 0 && c < P.Win) {
-        const int s = P.lut ? __ldg(P.lut + (f * P.Hin + r) * P.Win + c) : (f * P.Hin + r) * P.Win + c;
-        p0 = phys_pixel(s, P.n, P.mode0, b);
-        if (P.c1 > 0) p1 = phys_pixel(s, P.n, P.mode1, b);
-      }
-      s_pix0[i] = p0;
-      s_pix1[i] = p1;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(TC_LOADERS) : "memory");   // the tables are read by other loader threads
-    // phase 2: gather, one cp.async group per K chunk
-    const int items = npix * L.SPC;
-    for (int kc = 0; kc < L.nch; ++kc) {
-      for (int it = lt; it < items; it += TC_LOADERS) {
-        const int i = it / L.SPC, sl = it - i * L.SPC;
-        const int slab = kc * L.SPC + sl;
-        const int c = slab * 8;
-        const uint32_t dst = patch + (uint32_t)slab * L.slabBytes + (uint32_t)i * 16u;
-        if (L.vec) {
-          const bool first = c < P.c0;
-          const __nv_bfloat16 *src = first ? P.x0 : P.x1;
-          const int C = first ? P.c0 : P.c1, cc = first ? c : c - P.c0, mode = first ? P.mode0 : P.mode1;
-          const int px = first ? s_pix0[i] : s_pix1[i];
-          const bool valid = px >= 0 && c < P.cin;
-          if (mode != DLWPCS_SRC_POOL2 && !P.mask_y) {
-            const __nv_bfloat16 *g = valid ? src + (size_t)px * C + cc : P.x0;
-            cp_async16(dst, g, valid ? 16u : 0u);
-          } else {
-            uint4 o = make_uint4(0, 0, 0, 0);
-            if (valid) {
-              float a[8];
-              if (mode == DLWPCS_SRC_POOL2) {
-                const int w2 = P.n * 2;
-                float t[8];
+  } else if (warp == MMA_WARP) {
+    // ===== MMA issuer: the whole warp walks the loop (uniform control flow), one elected lane issues =====
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L.CoutP >> 3) << 17) | (8u << 24);
+    const uint64_t desc_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;    // SBO = 128 B, descriptor version 1
+    const uint64_t a_fix = desc_hi | ((uint64_t)((uint32_t)(L.slabBytes >> 4) & 0x3FFFu) << 16);   // LBO: next slab
+    const uint64_t b_fix = desc_hi | ((uint64_t)((uint32_t)L.CoutP & 0x3FFFu) << 16);              // LBO: CoutP*16 B
+    const uint32_t a_jstep = (uint32_t)(2 * L.slabBytes) >> 4, b_jstep = (uint32_t)(2 * L.CoutP * 16) >> 4;
+    const uint32_t stage16 = (uint32_t)L.stageBytes >> 4, coutp = (uint32_t)L.CoutP;
+    int st = 0, ph = 0, sp = 0, pp = 0, sa = 0, pa = 0, prev_grp = -1, k = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+      const TileInfo T = decode_tile(tile, P.batch, L.tpf);
+      const int MBc = min(L.MB, L.nmb - T.tf * L.MB);
+      const bool load_ev = !(L.resident && T.grp == prev_grp);
+      prev_grp = T.grp;
+      const int next = tile + gridDim.x;
+      const bool release_w = !L.resident || next >= ntiles || decode_tile(next, P.batch, L.tpf).grp != T.grp;
+      stamp(P, 5, k, lane == 0);
+      mbar_wait(bar_aempty + 8 * sa, pa ^ 1);
+      mbar_wait(bar_pfull + 8 * sp, pp);
+      tc_fence_after();
+      stamp(P, 6, k, lane == 0);
+      stamp(P, 11, k, lane == 0);
+      const uint64_t a_stage = a_fix | ((patch0 + (uint32_t)sp * L.patchBytes) >> 4);
+      const uint64_t b_ring = b_fix | (wring >> 4);
+      const uint32_t d_stage = tmem_base + (uint32_t)(sa * L.MB) * coutp;
+      for (int unit = 0; unit < L.NU; ++unit) {
+        const uint2 e = s_unit[unit];
+        const uint32_t flags = e.y >> 28;
+        const int stage = load_ev ? st : (int)((e.y >> 20) & 0xFFu);
+        if (load_ev && (flags & 1u)) {
+          mbar_wait(bar_wfull + 8 * st, ph);
+          tc_fence_after();
+        }
+        const uint64_t a_unit = a_stage + e.x;
+        const uint64_t b_unit = b_ring + ((uint32_t)stage * stage16 + (e.y & 0xFFFFFu));
+        if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) a[k] = 0.f;
+          for (int mb = 0; mb < MBT; ++mb) {
+            if (mb < MBc) {
 #pragma unroll
-                for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                  for (int dx = 0; dx < 2; ++dx) {
-                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)(px + dy * w2 + dx) * C + cc));
-                    unpack_bf16x8(v, t);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) a[k] += t[k];
-                  }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) a[k] *= 0.25f;
-              } else {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)px * C + cc));
-                unpack_bf16x8(v, a);
-              }
-              if (P.mask_y) {  // dgrad: scale dy by the activation derivative taken from the forward output
-                float m[8];
-                if (P.mask_f32) {
-                  const float *mp = reinterpret_cast<const float *>(P.mask_y) + (size_t)px * C + cc;
-                  const float4 m0 = __ldg(reinterpret_cast<const float4 *>(mp));
-                  const float4 m1 = __ldg(reinterpret_cast<const float4 *>(mp) + 1);
-                  m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w; m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
-                } else {
-                  const uint4 mv = __ldg(reinterpret_cast<const uint4 *>(
-                      reinterpret_cast<const __nv_bfloat16 *>(P.mask_y) + (size_t)px * C + cc));
-                  unpack_bf16x8(mv, m);
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) a[k] *= act_grad_from_y(m[k], P.mask_act, P.mask_slope, P.mask_max);
-              }
-              o = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]),
-                             pack_bf16x2(a[6], a[7]));
+              for (int j = 0; j < KC16T; ++j)
+                umma_bf16(d_stage + (uint32_t)mb * coutp, a_unit + (uint32_t)(mb * 128) + (uint32_t)j * a_jstep,
+                          b_unit + (uint32_t)j * b_jstep, idesc, (unit > 0 || j > 0) ? 1u : 0u);
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
-                         : "memory");
           }
-        } else {
-          // scalar gather: channel counts that are not multiples of 8 (the 18-channel network input)
-          float a[8];
-          const int px0 = s_pix0[i], px1 = s_pix1[i];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int ch = c + k;
-            float v = 0.f;
-            if (ch < P.cin) {
-              const bool first = ch < P.c0;
-              const __nv_bfloat16 *src = first ? P.x0 : P.x1;
-              const int C = first ? P.c0 : P.c1, cc = first ? ch : ch - P.c0, mode = first ? P.mode0 : P.mode1;
-              const int px = first ? px0 : px1;
-              if (px >= 0) {
-                if (mode == DLWPCS_SRC_POOL2) {
-                  const int w2 = P.n * 2;
-                  v = 0.25f * (__bfloat162float(src[(size_t)px * C + cc]) + __bfloat162float(src[(size_t)(px + 1) * C + cc]) +
-                               __bfloat162float(src[(size_t)(px + w2) * C + cc]) +
-                               __bfloat162float(src[(size_t)(px + w2 + 1) * C + cc]));
-                } else {
-                  v = __bfloat162float(src[(size_t)px * C + cc]);
-                }
-                if (P.mask_y) {
-                  const float m = P.mask_f32 ? reinterpret_cast<const float *>(P.mask_y)[(size_t)px * C + cc]
-                                             : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(P.mask_y)[(size_t)px * C + cc]);
-                  v *= act_grad_from_y(m, P.mask_act, P.mask_slope, P.mask_max);
-                }
-              }
-            }
-            a[k] = v;
-          }
-          const uint4 o = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]),
-                                     pack_bf16x2(a[6], a[7]));
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
-                       : "memory");
+        }
+        __syncwarp();
+        if (flags & 2u) {
+          if (release_w && elect_one()) umma_commit(bar_wempty + 8 * stage);
+          __syncwarp();
+          if (load_ev && ++st == L.NST) { st = 0; ph ^= 1; }
         }
       }
-      cp_async_commit();
+      if (elect_one()) {
+        umma_commit(bar_pempty + 8 * sp);     // patch stage may be refilled once these MMAs have read it
+        umma_commit(bar_afull + 8 * sa);      // accumulators complete
+      }
+      __syncwarp();
+      stamp(P, 7, k, lane == 0);
+      if (++sp == L.PS) { sp = 0; pp ^= 1; }
+      if (++sa == L.AS) { sa = 0; pa ^= 1; }
     }
-    for (int kc = 0; kc < L.nch; ++kc) {
-      cp_async_wait_dyn(L.nch - 1 - kc);
-      fence_proxy_async();
-      mbar_arrive(bar_pfull + 8 * kc);
-    }
-
-    // ===== epilogue: TMEM -> registers -> bias / activation -> global =====
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    const int quarter = warp & 3;                  // TMEM lanes this warp may read: 32*quarter .. +31
-    const float *bias = P.bias + grp * L.CoutP;
-    const size_t face_px = (size_t)(b * 6 + f) * P.Hout * P.Wout;
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 8) {
+    // ===== epilogue: TMEM -> registers -> bias / activation -> global.  Warp w reads TMEM lanes 32*(w%4)..+31; the two
+    // warps of a lane quarter take alternate m-blocks. =====
+    const int quarter = warp & 3, half = (warp - EPI_WARP0) >> 2;
     const bool vec_out = P.y_f32 ? (P.cout % 4 == 0) : (P.cout % 8 == 0);
-    for (int mb = 0; mb < MBc; ++mb) {
-      const int q = q0 + mb * 128 + quarter * 32 + lane;
-      const int r = q / L.Wv, c = q - r * L.Wv;
-      const bool ok = q < L.Q && c < P.Wout;
-      const size_t opix = face_px + (size_t)r * P.Wout + c;
-      for (int n0 = 0; n0 < L.CoutP; n0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * L.CoutP + n0), v);
-        tmem_ld_wait();
-        if (!ok) continue;
-        float o[16];
+    int sa = 0, pa = 0, k = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+      const TileInfo T = decode_tile(tile, P.batch, L.tpf);
+      const int MBc = min(L.MB, L.nmb - T.tf * L.MB);
+      const float *bias = s_bias + T.grp * L.CoutP;
+      const size_t face_px = (size_t)(T.b * 6 + T.f) * P.Hout * P.Wout;
+      stamp(P, 8, k, tid == EPI_WARP0 * 32);
+      mbar_wait(bar_afull + 8 * sa, pa);
+      tc_fence_after();
+      stamp(P, 9, k, tid == EPI_WARP0 * 32);
+      for (int mb = half; mb < MBc; mb += 2) {
+        const int q = (T.tf * L.MB + mb) * 128 + quarter * 32 + lane;
+        const int r = q / L.Wv, c = q - r * L.Wv;
+        const bool ok = q < L.Q && c < P.Wout;
+        const size_t opix = face_px + (size_t)r * P.Wout + c;
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((sa * L.MB + mb) * L.CoutP);
+        for (int n0 = 0; n0 < L.CoutP; n0 += 32) {
+          uint32_t v[32];
+          const bool two = n0 + 16 < L.CoutP;
+          tmem_ld16(trow + (uint32_t)n0, v);
+          if (two) tmem_ld16(trow + (uint32_t)n0 + 16u, v + 16);
+          tmem_ld_wait();
+          if (!ok) continue;
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-          o[k] = act_apply(__uint_as_float(v[k]) + __ldg(bias + n0 + k), P.act, P.slope, P.maxv);
-        if (P.y_f32) {
-          float *yp = reinterpret_cast<float *>(P.y) + opix * P.cout + n0;
-          if (vec_out && n0 + 16 <= P.cout) {
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !two) break;
+            const int nb = n0 + 16 * h;
+            float o[16];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              reinterpret_cast<float4 *>(yp)[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
-          } else {
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const float4 bv = *reinterpret_cast<const float4 *>(bias + nb + 4 * k4);
+              o[4 * k4 + 0] = act_apply(__uint_as_float(v[16 * h + 4 * k4 + 0]) + bv.x, P.act, P.slope, P.maxv);
+              o[4 * k4 + 1] = act_apply(__uint_as_float(v[16 * h + 4 * k4 + 1]) + bv.y, P.act, P.slope, P.maxv);
+              o[4 * k4 + 2] = act_apply(__uint_as_float(v[16 * h + 4 * k4 + 2]) + bv.z, P.act, P.slope, P.maxv);
+              o[4 * k4 + 3] = act_apply(__uint_as_float(v[16 * h + 4 * k4 + 3]) + bv.w, P.act, P.slope, P.maxv);
+            }
+            if (P.y_f32) {
+              float *yp = reinterpret_cast<float *>(P.y) + opix * P.cout + nb;
+              if (vec_out && nb + 16 <= P.cout) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-              if (n0 + k < P.cout) yp[k] = o[k];
-          }
-        } else {
-          __nv_bfloat16 *yp = reinterpret_cast<__nv_bfloat16 *>(P.y) + opix * P.cout + n0;
-          if (vec_out && n0 + 16 <= P.cout) {
-            reinterpret_cast<uint4 *>(yp)[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                          pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-            reinterpret_cast<uint4 *>(yp)[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]),
-                                                          pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
-          } else {
+                for (int k = 0; k < 4; ++k)
+                  reinterpret_cast<float4 *>(yp)[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+              } else {
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-              if (n0 + k < P.cout) yp[k] = __float2bfloat16_rn(o[k]);
+                for (int k = 0; k < 16; ++k)
+                  if (nb + k < P.cout) yp[k] = o[k];
+              }
+            } else {
+              __nv_bfloat16 *yp = reinterpret_cast<__nv_bfloat16 *>(P.y) + opix * P.cout + nb;
+              if (vec_out && nb + 16 <= P.cout) {
+                reinterpret_cast<uint4 *>(yp)[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                              pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                reinterpret_cast<uint4 *>(yp)[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]),
+                                                              pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+              } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                  if (nb + k < P.cout) yp[k] = __float2bfloat16_rn(o[k]);
+              }
+            }
           }
         }
       }
+      tc_fence_before();
+      mbar_arrive(bar_aempty + 8 * sa);
+      stamp(P, 10, k, tid == EPI_WARP0 * 32);
+      if (++sa == L.AS) { sa = 0; pa ^= 1; }
+    }
+  } else if (warp < LOAD_WARP0 + 8) {
+    // ===== patch loaders =====
+    const int lt = tid - LOAD_WARP0 * 32;
+    int si = 0, pi = 0, k = 0;
+    const int w2_0 = P.n * 2;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+      const TileInfo T = decode_tile(tile, P.batch, L.tpf);
+      const int MBc = min(L.MB, L.nmb - T.tf * L.MB);
+      const int q0 = T.tf * L.MB * 128;
+      const int npix = MBc * 128 + L.haloExt;
+      stamp(P, 1, k, lt == 0);
+      mbar_wait(bar_pempty + 8 * si, pi ^ 1);
+      stamp(P, 2, k, lt == 0);
+      const uint32_t stage = patch0 + (uint32_t)si * L.patchBytes;
+      const int32_t *t0 = P.tab0 + (size_t)T.f * L.G + q0;
+      const int32_t *t1 = P.tab1 + (size_t)T.f * L.G + q0;
+      const size_t b0 = (size_t)T.b * P.ppb0, b1 = (size_t)T.b * P.ppb1;
+      if (L.vec && L.logS >= 0) {
+        // each thread owns one slab (fixed source / channel offset) of every (256 >> logS)-th patch row
+        const int slab = lt & (L.S - 1), c = slab * 8;
+        const bool first = c < P.c0;
+        const __nv_bfloat16 *src = first ? P.x0 : P.x1;
+        const int C = first ? P.c0 : P.c1, cc = first ? c : c - P.c0, mode = first ? P.mode0 : P.mode1;
+        const int32_t *tab = first ? t0 : t1;
+        const size_t boff = first ? b0 : b1;
+        const bool chan_ok = c < P.cin;
+        const int pstep = TC_LOADERS >> L.logS;
+        const uint32_t dst0 = stage + (uint32_t)slab * L.slabBytes;
+        const bool direct = mode != DLWPCS_SRC_POOL2 && !P.mask_y;
+        for (int i0 = lt >> L.logS; i0 < npix; i0 += 8 * pstep) {
+          int px[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int i = i0 + e * pstep;
+            px[e] = (i < npix && chan_ok) ? (P.dbg_notab ? (q0 + i) % P.ppb0 : __ldg(tab + i)) : -1;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int i = i0 + e * pstep;
+            if (i >= npix) continue;
+            const uint32_t dst = dst0 + (uint32_t)i * 16u;
+            if (direct) {
+              const __nv_bfloat16 *g = px[e] >= 0 ? src + (boff + px[e]) * C + cc : P.x0;
+              cp_async16(dst, g, px[e] >= 0 ? 16u : 0u);
+            } else {
+              uint4 o = make_uint4(0, 0, 0, 0);
+              if (px[e] >= 0) o = gather_regs(P, src, C, mode, boff + px[e], cc, w2_0);
+              st_shared16(dst, o);
+            }
+          }
+        }
+      } else {
+        // generic gather: any slab count / channel counts that are not multiples of 8 (element-wise loads)
+        const int items = npix * L.S;
+        for (int it = lt; it < items; it += TC_LOADERS) {
+          const int i = it / L.S, slab = it - i * L.S, c = slab * 8;
+          const uint32_t dst = stage + (uint32_t)slab * L.slabBytes + (uint32_t)i * 16u;
+          const int p0 = __ldg(t0 + i), p1 = P.c1 > 0 ? __ldg(t1 + i) : -1;
+          if (L.vec) {
+            const bool first = c < P.c0;
+            const __nv_bfloat16 *src = first ? P.x0 : P.x1;
+            const int C = first ? P.c0 : P.c1, cc = first ? c : c - P.c0, mode = first ? P.mode0 : P.mode1;
+            const int px = first ? p0 : p1;
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (px >= 0 && c < P.cin) o = gather_regs(P, src, C, mode, (first ? b0 : b1) + px, cc, w2_0);
+            st_shared16(dst, o);
+          } else {
+            float a[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ch = c + e;
+              float val = 0.f;
+              if (ch < P.cin) {
+                const bool first = ch < P.c0;
+                const __nv_bfloat16 *src = first ? P.x0 : P.x1;
+                const int C = first ? P.c0 : P.c1, cc = first ? ch : ch - P.c0, mode = first ? P.mode0 : P.mode1;
+                const int px = first ? p0 : p1;
+                if (px >= 0) {
+                  const size_t pix = (first ? b0 : b1) + px;
+                  if (mode == DLWPCS_SRC_POOL2) {
+                    val = 0.25f * (__bfloat162float(src[pix * C + cc]) + __bfloat162float(src[(pix + 1) * C + cc]) +
+                                   __bfloat162float(src[(pix + w2_0) * C + cc]) +
+                                   __bfloat162float(src[(pix + w2_0 + 1) * C + cc]));
+                  } else {
+                    val = __bfloat162float(src[pix * C + cc]);
+                  }
+                  if (P.mask_y) {
+                    const float m = P.mask_f32
+                                        ? reinterpret_cast<const float *>(P.mask_y)[pix * C + cc]
+                                        : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(P.mask_y)[pix * C + cc]);
+                    val *= act_grad_from_y(m, P.mask_act, P.mask_slope, P.mask_max);
+                  }
+                }
+              }
+              a[e] = val;
+            }
+            st_shared16(dst, make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]),
+                                        pack_bf16x2(a[6], a[7])));
+          }
+        }
+      }
+      // the stage is published when this thread's copies have landed (register-path stores are already visible; the
+      // proxy fence orders them before the tensor core's reads) -- no blocking, so the loaders run ahead of the MMA warp
+      fence_proxy_async();
+      cp_async_mbar_arrive(bar_pfull + 8 * si);
+      stamp(P, 3, k, lt == 0);
+      if (++si == L.PS) { si = 0; pi ^= 1; }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)L.tmemCols);
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)L.tmemCols);
 }
 
 // ---- weight packing -----------------------------------------------------------------------------------------------
@@ -495,8 +638,11 @@ const char *make_plan(const dlwpcs_conv_desc *d, const Geometry &g, int gemm_cin
   for (int kc : {64, 48, 32, 16})
     if (L->CinP % kc == 0) { L->KC = kc; break; }
   L->nch = L->CinP / L->KC;
-  if (L->nch > MAX_CHUNKS) return "too many input channels";
   L->SPC = L->KC / 8;
+  L->S = L->CinP / 8;
+  L->logS = -1;
+  for (int l = 0; l <= 5; ++l)
+    if ((1 << l) == L->S) L->logS = l;
   L->taps = d->kh * d->kw;
   L->NU = L->nch * L->taps;
   L->unitBytes = L->KC * L->CoutP * 2;
@@ -505,49 +651,160 @@ const char *make_plan(const dlwpcs_conv_desc *d, const Geometry &g, int gemm_cin
   if (L->UPS > L->NU) L->UPS = L->NU;
   L->stageBytes = L->UPS * L->unitBytes;
   L->nstages = (L->NU + L->UPS - 1) / L->UPS;
-  L->NST = L->nstages < 4 ? L->nstages : 4;
   L->groupBytes = (int64_t)L->NU * L->unitBytes;
+  L->resident = (L->nstages <= MAX_STAGES && (int64_t)L->nstages * L->stageBytes <= 96 * 1024) ? 1 : 0;
+  L->NST = L->resident ? L->nstages : 4;
   L->Wv = g.Wout + (d->kw - 1) * d->dil_w;
   L->Hv = g.Hout + (d->kh - 1) * d->dil_h;
   L->Q = (g.Hout - 1) * L->Wv + g.Wout;
   L->nmb = (L->Q + 127) / 128;
   L->haloExt = (d->kh - 1) * d->dil_h * L->Wv + (d->kw - 1) * d->dil_w;
-  const int smem_cap = 225 * 1024, smem_pair = 110 * 1024;
-  auto smem_for = [&](int MB, int *npixp, int *slab) {
+  L->G = L->nmb * 128 + L->haloExt;
+  if (L->NU > MAX_UNITS) return "kernel window x input channels too large";
+  const int fixed = 128 + 512 + MAX_UNITS * 8 + 3 * L->CoutP * 4 + L->NST * L->stageBytes;
+  auto patch_for = [&](int MB, int *npixp) {
     const int np = ((MB * 128 + L->haloExt + 7) / 8) * 8 + 1;     // odd multiple of 16 B: slab-strided stores spread
     *npixp = np;
-    *slab = np * 16;
-    return 128 + 256 + (L->CinP / 8) * np * 16 + L->NST * L->stageBytes + 2 * np * 4 + 64;
+    return L->S * np * 16;
   };
   int mbmax = 512 / L->CoutP;
-  if (mbmax > MAX_MB) mbmax = MAX_MB;
+  if (mbmax > 4) mbmax = 4;
   if (mbmax > L->nmb) mbmax = L->nmb;
-  int best = 0, np = 0, sb = 0;
+  int best = 0, np = 0;
   const int forced = env_int("DLWPCS_TC_MB", 0);
-  if (forced > 0) {
-    best = forced < mbmax ? forced : mbmax;
-    if (smem_for(best, &np, &sb) > smem_cap) return "forced DLWPCS_TC_MB does not fit shared memory";
-  } else {
-    for (int MB = mbmax; MB >= 1; --MB)          // largest tile that still lets two CTAs share an SM ...
-      if (smem_for(MB, &np, &sb) <= smem_pair && MB * L->CoutP <= 256) { best = MB; break; }
-    if (!best)
-      for (int MB = mbmax; MB >= 1; --MB)        // ... else the largest that fits at all
-        if (smem_for(MB, &np, &sb) <= smem_cap) { best = MB; break; }
-    if (!best) return "input patch does not fit shared memory (too many input channels for this face width)";
-    const int tiles = (L->nmb + best - 1) / best;
-    best = (L->nmb + tiles - 1) / tiles;           // even out the tiles of a face
+  for (int MB = (forced > 0 && forced < mbmax) ? forced : mbmax; MB >= 1; --MB)
+    if (fixed + 2 * patch_for(MB, &np) <= SMEM_CAP) { best = MB; break; }
+  if (!best) {
+    best = 1;                                      // single-buffered patch as the last resort
+    if (fixed + patch_for(1, &np) > SMEM_CAP) return "input patch does not fit shared memory (too many input channels)";
   }
+  const int tiles = (L->nmb + best - 1) / best;
+  best = (L->nmb + tiles - 1) / tiles;             // even out the tiles of a face
   L->MB = best;
-  L->tiles = (L->nmb + best - 1) / best;
-  L->smemBytes = smem_for(best, &L->NPIXp, &L->slabBytes);
+  L->tpf = (L->nmb + best - 1) / best;
+  L->patchBytes = patch_for(best, &L->NPIXp);
+  L->slabBytes = L->NPIXp * 16;
+  L->PS = (SMEM_CAP - fixed) / L->patchBytes;
+  int ps_max = env_int("DLWPCS_TC_PS", 3);
+  if (ps_max > MAX_PS) ps_max = MAX_PS;
+  if (L->PS > ps_max) L->PS = ps_max;
+  if (L->PS < 1) return "input patch does not fit shared memory";
+  L->AS = (2 * best * L->CoutP <= 512) ? 2 : 1;
   int cols = 32;
-  while (cols < best * L->CoutP) cols *= 2;
+  while (cols < L->AS * best * L->CoutP) cols *= 2;
   L->tmemCols = cols;
+  L->smemBytes = fixed + L->PS * L->patchBytes;
   if (L->slabBytes >= (1 << 18)) return "patch too large";
   return nullptr;
 }
 
+// ---- patch tables: for every position of the linearised virtual face, the physical source pixel (within one batch
+// element of the source tensor, in its own resolution) or -1 for zero fill.  One table per (geometry, sampling mode).
+struct TabKey {
+  int dev, n, halo, Hin, Win, Wv, G, pt0, pt1, pt2, pl, mode;
+  bool operator<(const TabKey &o) const { return memcmp(this, &o, sizeof(TabKey)) < 0; }
+};
+std::mutex g_tab_mu;
+std::map<TabKey, int32_t *> g_tabs;
+
+const int32_t *get_patch_table(const Geometry &g, const TcPlan &L, int n, int halo, int mode) {
+  TabKey key;
+  memset(&key, 0, sizeof(key));
+  if (cudaGetDevice(&key.dev) != cudaSuccess) {
+    set_error("cudaGetDevice failed");
+    return nullptr;
+  }
+  key.n = n; key.halo = halo; key.Hin = g.Hin; key.Win = g.Win; key.Wv = L.Wv; key.G = L.G;
+  key.pt0 = g.pt[0]; key.pt1 = g.pt[1]; key.pt2 = g.pt[2]; key.pl = g.pl; key.mode = mode;
+  std::lock_guard<std::mutex> lk(g_tab_mu);
+  auto it = g_tabs.find(key);
+  if (it != g_tabs.end()) return it->second;
+  std::vector<int32_t> lut;
+  if (halo > 0) build_pad_lut(n, halo, lut);
+  std::vector<int32_t> tab((size_t)6 * L.G);
+  for (int f = 0; f < 6; ++f) {
+    const int pt = g.pt[face_group_host(f)];
+    for (int q = 0; q < L.G; ++q) {
+      const int rv = q / L.Wv, cv = q % L.Wv, r = rv - pt, c = cv - g.pl;
+      int32_t val = -1;
+      if (r >= 0 && r < g.Hin && c >= 0 && c < g.Win) {
+        const int s = halo > 0 ? lut[((size_t)f * g.Hin + r) * g.Win + c] : (f * g.Hin + r) * g.Win + c;
+        const int sf = s / (n * n), si = (s % (n * n)) / n, sj = s % n;
+        if (mode == DLWPCS_SRC_SAME) val = s;
+        else if (mode == DLWPCS_SRC_UP2) val = (sf * (n / 2) + si / 2) * (n / 2) + sj / 2;
+        else val = (sf * 2 * n + 2 * si) * 2 * n + 2 * sj;
+      }
+      tab[(size_t)f * L.G + q] = val;
+    }
+  }
+  int32_t *dev = nullptr;
+  // plain cudaMalloc + synchronous copy: never inside a stream capture -- callers warm the cache first
+  cudaError_t e = cudaMalloc(&dev, tab.size() * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemcpy(dev, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("patch table upload failed: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
+  g_tabs[key] = dev;
+  return dev;
+}
+
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+int launch_tc(TcP &P, cudaStream_t st) {
+  const TcPlan &L = P.pl_;
+  typedef void (*kern_t)(const TcP);
+  static const kern_t kerns[4][4] = {
+      {conv_tc_kernel<1, 1>, conv_tc_kernel<1, 2>, conv_tc_kernel<1, 3>, conv_tc_kernel<1, 4>},
+      {conv_tc_kernel<2, 1>, conv_tc_kernel<2, 2>, conv_tc_kernel<2, 3>, conv_tc_kernel<2, 4>},
+      {conv_tc_kernel<3, 1>, conv_tc_kernel<3, 2>, conv_tc_kernel<3, 3>, conv_tc_kernel<3, 4>},
+      {conv_tc_kernel<4, 1>, conv_tc_kernel<4, 2>, conv_tc_kernel<4, 3>, conv_tc_kernel<4, 4>}};
+  static bool attr_set[4][4] = {};
+  CS_CHECK(L.MB >= 1 && L.MB <= 4 && L.KC % 16 == 0 && L.KC <= 64, "internal: bad tile plan");
+  const int ki = L.MB - 1, kj = L.KC / 16 - 1;
+  const kern_t kern = kerns[ki][kj];
+  if (!attr_set[ki][kj]) {
+    CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
+    attr_set[ki][kj] = true;
+  }
+  const long long ntiles = 6LL * P.batch * L.tpf;
+  CS_CHECK(ntiles < (1LL << 30), "batch too large");
+  int grid = num_sms();
+  if (grid > ntiles) grid = (int)ntiles;
+  static const int timing = env_int("DLWPCS_TC_TIMING", 0);
+  P.dbg_notab = env_int("DLWPCS_TC_DEBUG_NOTAB", 0);
+  static long long *dbg = nullptr;
+  if (timing) {
+    if (!dbg) CS_CUDA(cudaMalloc(&dbg, 16 * sizeof(long long)));
+    CS_CUDA(cudaMemset(dbg, 0, 16 * sizeof(long long)));
+    P.dbg = dbg;
+  }
+  kern<<<grid, TC_THREADS, L.smemBytes, st>>>(P);
+  CS_CUDA(cudaGetLastError());
+  if (timing) {
+    long long h[16];
+    CS_CUDA(cudaDeviceSynchronize());
+    CS_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr,
+            "[tc timing] cin=%d cout=%d n=%d MB=%d tpf=%d PS=%d AS=%d res=%d smem=%d tiles/cta=%.1f | tile %d of the mid "
+            "CTA, cycles since kernel start: loader wait %lld got %lld issued %lld | mma wait %lld "
+            "start %lld issued %lld (next start %lld) | epi wait %lld ready %lld end %lld\n",
+            P.cin, P.cout, P.n, L.MB, L.tpf, L.PS, L.AS, L.resident, L.smemBytes, (double)ntiles / grid, DBG_K,
+            h[1] - h[0], h[2] - h[0], h[3] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[11] - h[0],
+            h[8] - h[0], h[9] - h[0], h[10] - h[0]);
+  }
+  return 0;
+}
 
 }  // namespace
 
@@ -591,20 +848,6 @@ int tc_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_c
   return 0;
 }
 
-static int launch_tc(TcP &P, int batch, cudaStream_t st) {
-  const TcPlan &L = P.pl_;
-  static int cur_max = 48 * 1024;
-  if (L.smemBytes > cur_max) {
-    CS_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    cur_max = 227 * 1024;
-  }
-  CS_CHECK((long long)batch * 6 <= 65535, "batch too large for one launch (B*6 = %lld > 65535)", (long long)batch * 6);
-  dim3 grid(L.tiles, batch * 6);
-  conv_tc_kernel<<<grid, TC_THREADS, L.smemBytes, st>>>(P);
-  CS_CUDA(cudaGetLastError());
-  return 0;
-}
-
 int tc_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed,
                 void *y, cudaStream_t st) {
   TcP P;
@@ -614,24 +857,30 @@ int tc_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, co
   TcPlan &L = P.pl_;
   P.x0 = (const __nv_bfloat16 *)x0;
   P.x1 = (const __nv_bfloat16 *)x1;
-  P.lut = nullptr;
-  if (d->halo > 0) {
-    const HaloTables *t = get_halo_tables(d->n, d->halo);
-    if (!t) return 3;
-    P.lut = t->lut;
+  P.tab0 = get_patch_table(g, L, d->n, d->halo, d->mode0);
+  if (!P.tab0) return 3;
+  P.tab1 = P.tab0;
+  if (d->c1 > 0) {
+    P.tab1 = get_patch_table(g, L, d->n, d->halo, d->mode1);
+    if (!P.tab1) return 3;
   }
+  auto ppb = [&](int mode) {
+    const int e = mode == DLWPCS_SRC_SAME ? d->n : (mode == DLWPCS_SRC_UP2 ? d->n / 2 : d->n * 2);
+    return 6 * e * e;
+  };
+  P.ppb0 = ppb(d->mode0);
+  P.ppb1 = ppb(d->mode1);
   P.wpack = (const uint8_t *)packed;
   P.bias = reinterpret_cast<const float *>(P.wpack + 3 * L.groupBytes);
   P.y = y;
   P.y_f32 = d->y_dtype == DLWPCS_F32;
   P.mask_y = nullptr;
-  P.n = d->n; P.Hin = g.Hin; P.Win = g.Win; P.Hout = g.Hout; P.Wout = g.Wout;
+  P.batch = d->batch; P.n = d->n; P.Hout = g.Hout; P.Wout = g.Wout;
   P.cin = d->cin; P.cout = d->cout; P.c0 = d->c0; P.c1 = d->c1; P.mode0 = d->mode0; P.mode1 = d->mode1;
   P.kw = d->kw; P.dh = d->dil_h; P.dw = d->dil_w;
-  P.pt[0] = g.pt[0]; P.pt[1] = g.pt[1]; P.pt[2] = g.pt[2]; P.pl = g.pl;
   P.act = d->act; P.slope = d->act_slope; P.maxv = d->act_max;
   L.vec = (d->c0 % 8 == 0) && (d->c1 % 8 == 0) && aligned16(x0) && (d->c1 == 0 || aligned16(x1));
-  return launch_tc(P, d->batch, st);
+  return launch_tc(P, st);
 }
 
 }  // namespace dlwpcs

@@ -11,6 +11,7 @@ host<->device copies per step).
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _lib
 from .custom import CubeSphereConv2D
@@ -96,6 +97,10 @@ class RolloutEngine(object):
             raise ValueError('prognostic (%d) + forcing (%d) channels != model input channels (%d)'
                              % (self.cp, self.cf, model.in_channels))
         self.dtype = dtype
+        # channel counts padded to multiples of 8 so that every gather is a 16-byte copy: the pad channels carry zero
+        # weights on the way in and are written as exact zeros by the output layer
+        self.cp_pad = -(-self.cp // 8) * 8
+        self.cf_pad = -(-self.cf // 8) * 8 if self.cf else 0
         self.device = device or next(model.parameters()).device
         if self.device.type != 'cuda':
             raise _lib.DlwpcsError('RolloutEngine needs the model on a CUDA device')
@@ -104,16 +109,16 @@ class RolloutEngine(object):
         dt = _lib.dtype_code(dtype)
         b, base = batch, model.base
         mk = lambda edge, c: torch.empty((b, 6, edge, edge, c), dtype=dtype, device=self.device)
-        self.state = mk(n, self.cp)
-        fshape = ((steps,) if per_step_forcing else ()) + (b, 6, n, n, max(self.cf, 1))
+        self.state = torch.zeros((b, 6, n, n, self.cp_pad), dtype=dtype, device=self.device)
+        fshape = ((steps,) if per_step_forcing else ()) + (b, 6, n, n, max(self.cf_pad, 8))
         self.forcing = torch.zeros(fshape, dtype=dtype, device=self.device)
-        self.ring = torch.empty((steps, b, 6, n, n, self.cp), dtype=dtype, device=self.device)
+        self.ring = torch.empty((steps, b, 6, n, n, self.cp_pad), dtype=dtype, device=self.device)
         self.buf = dict(a=mk(n, base), x0=mk(n, base), b=mk(n // 2, 2 * base), x1=mk(n // 2, 2 * base),
                         c=mk(n // 4, 4 * base), x2=mk(n // 4, 2 * base), d=mk(n // 2, 2 * base), e=mk(n // 2, base),
                         f=mk(n, base), g=mk(n, base))
         S, P, U = _lib.SRC_SAME, _lib.SRC_POOL2, _lib.SRC_UP2
         # (layer, edge, src0, c0, mode0, src1, c1, mode1, dst)
-        plan = [('conv_2d_1', n, 'state', self.cp, S, 'forcing' if self.cf else None, self.cf, S, 'a'),
+        plan = [('conv_2d_1', n, 'state', self.cp_pad, S, 'forcing' if self.cf else None, self.cf_pad, S, 'a'),
                 ('conv_2d_1_2', n, 'a', base, S, None, 0, S, 'x0'),
                 ('conv_2d_2', n // 2, 'x0', base, P, None, 0, S, 'b'),
                 ('conv_2d_2_2', n // 2, 'b', 2 * base, S, None, 0, S, 'x1'),
@@ -129,7 +134,8 @@ class RolloutEngine(object):
             layer = getattr(model, name)
             k = layer.kernel_size
             fused = F_cs.resolve_activation(layer.activation)
-            d = _lib.make_desc(b, edge, c0 + c1, layer.filters, k, (1, 1), (1, 1), layer.fuse_padding, False,
+            cout = self.cp_pad if dst == 'out' else layer.filters
+            d = _lib.make_desc(b, edge, c0 + c1, cout, k, (1, 1), (1, 1), layer.fuse_padding, False,
                                layer.flip_north_pole, layer.independent_north_pole, layer.use_bias, fused[0], fused[1],
                                fused[2], dt, dt, c0, m0, c1, m1)
             self.plan.append([name, d, s0, s1, dst, None])
@@ -140,9 +146,23 @@ class RolloutEngine(object):
         """(Re)pack the layer weights into the kernels' layouts -- call after the model's parameters change."""
         for item in self.plan:
             layer = getattr(self.model, item[0])
-            item[5] = _lib.pack_weights(item[1], layer.equatorial_kernel, layer.polar_kernel, layer.north_pole_kernel,
-                                        layer.equatorial_bias, layer.polar_bias, layer.north_pole_bias)
+            ws = [layer.equatorial_kernel, layer.polar_kernel, layer.north_pole_kernel]
+            bs = [layer.equatorial_bias, layer.polar_bias, layer.north_pole_bias]
+            if item[0] == 'conv_2d_1':          # input channels: [prognostic | pad | forcing | pad]
+                ws = [None if w is None else self._pad_in(w.detach()) for w in ws]
+            if item[4] == 'out':                # output channels: [prognostic | pad]
+                ws = [None if w is None else F.pad(w.detach(), (0, self.cp_pad - self.cp)) for w in ws]
+                bs = [None if v is None else F.pad(v.detach(), (0, self.cp_pad - self.cp)) for v in bs]
+            item[5] = _lib.pack_weights(item[1], ws[0], ws[1], ws[2], bs[0], bs[1], bs[2])
         self.graph = None
+
+    def _pad_in(self, w):
+        kh, kw, _, co = w.shape
+        out = w.new_zeros((kh, kw, self.cp_pad + self.cf_pad, co))
+        out[:, :, :self.cp] = w[:, :, :self.cp]
+        if self.cf:
+            out[:, :, self.cp_pad:self.cp_pad + self.cf] = w[:, :, self.cp:]
+        return out
 
     @property
     def launches_per_step(self):
@@ -183,11 +203,11 @@ class RolloutEngine(object):
 
     def load_inputs(self, state, forcing=None, non_blocking=True):
         """Copy initial conditions (host or device tensors, any float dtype) into the engine's resident buffers."""
-        self.state.copy_(state, non_blocking=non_blocking)
+        self.state[..., :self.cp].copy_(state, non_blocking=non_blocking)
         if self.cf:
             if forcing is None:
                 raise ValueError('this engine was built with %d forcing channels' % self.cf)
-            self.forcing.copy_(forcing, non_blocking=non_blocking)
+            self.forcing[..., :self.cf].copy_(forcing, non_blocking=non_blocking)
 
     def launch(self):
         """Enqueue the whole rollout on the current stream (graph replay when enabled); no host synchronisation."""
@@ -196,7 +216,12 @@ class RolloutEngine(object):
             self.graph.replay()
         else:
             self._enqueue_all()
-        return self.ring
+        return self.forecast
+
+    @property
+    def forecast(self):
+        """(steps, B, 6, N, N, Cout) view of the resident forecast ring without the pad channels."""
+        return self.ring[..., :self.cp]
 
     def run(self, state, forcing=None):
         self.load_inputs(state, forcing)
