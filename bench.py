@@ -179,10 +179,13 @@ def main():
     ap.add_argument('--batch', type=int, default=64, help='ensemble members (initial conditions) per GPU')
     ap.add_argument('--rollout-steps', type=int, default=100)
     ap.add_argument('--dtype', default='auto', choices=['auto', 'bf16', 'fp32'])
-    ap.add_argument('--ref-batch', type=int, default=8)
-    ap.add_argument('--ref-steps', type=int, default=20)
+    ap.add_argument('--ref-batch', type=int, default=16)
+    ap.add_argument('--ref-steps', type=int, default=100)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-train', action='store_true')
+    ap.add_argument('--train-batch', type=int, default=32, help='training samples per GPU per step')
+    ap.add_argument('--train-steps', type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -316,6 +319,40 @@ def main():
                      'share_of_step': top['share'],
                      'whole_step_frac_of_roof': round(sum(r['frac_of_roof'] * r['ms'] for r in layers) / tot, 3)})
 
+    # ---------------- training step (BASELINE.json configs[2]/[3]): batch-sharded DP, one flat NCCL all-reduce per step
+    train = None
+    rollout_launches = args.steps * args.rollout_steps * eng.launches_per_step * 2
+    if not args.no_train:
+        del eng, flush, d_out
+        torch.cuda.empty_cache()
+        from dlwp_cs_b200.train import DataParallelTrainer
+        tmodel = CubeSphereUNet2(C_PROG + C_FORC, C_PROG, base=BASE).to(dev)
+        tmodel.load_oracle_params(params)
+        trainer = DataParallelTrainer(tmodel, lr=1e-3)
+        g = torch.Generator().manual_seed(100 + rank)
+        tb = args.train_batch
+        xs = torch.randn(tb, 6, N_FACE, N_FACE, C_PROG + C_FORC, generator=g).to(dev)
+        ts = torch.randn(tb, 6, N_FACE, N_FACE, C_PROG, generator=g).to(dev)
+        for _ in range(2):
+            trainer.step(xs, ts)
+        barrier()
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record()
+        for _ in range(args.train_steps):
+            loss = trainer.step(xs, ts)
+        e_ev.record()
+        barrier()
+        tt = torch.tensor([s_ev.elapsed_time(e_ev)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tms = float(tt.item()) / args.train_steps
+        train = {'metric': 'train samples/sec, unet2 C48 fwd+bwd+Adam', 'value': tb * world / (tms * 1e-3),
+                 'unit': 'samples/s', 'ms_per_step': tms, 'global_batch': tb * world, 'batch_per_gpu': tb,
+                 'dtype': 'f32', 'parallelism': 'dp%d, one flat all-reduce of %d float32 gradients per step'
+                                                % (world, trainer.flat.count),
+                 'loss': float(loss.item()),
+                 'note': 'float32 CUDA-core backward kernels this round; the bf16 tensor-core backward is the next row'}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -340,8 +377,8 @@ def main():
                            'cuda_graph': not args.no_graph, 'parallelism': 'replicas x%d' % world},
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': e2e_ms / args.steps},
-                'gpu_launches': args.steps * args.rollout_steps * eng.launches_per_step * 2,
-                'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'layers': layers}
+                'gpu_launches': rollout_launches,
+                'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'train': train, 'layers': layers}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -63,6 +63,8 @@ def load():
         'dlwpcs_act_fwd': (i32, [vp, vp, i64, i32, f32, f32, i32, vp]),
         'dlwpcs_act_bwd': (i32, [vp, vp, vp, i64, i32, f32, f32, i32, vp]),
         'dlwpcs_conv2d_fwd_host': (i32, [dp, wp, vp, vp]),
+        'dlwpcs_mse_loss_grad': (i32, [vp, vp, vp, vp, i64, f32, i32, vp]),
+        'dlwpcs_adam_step': (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)          # AttributeError here == header and library out of sync
@@ -76,7 +78,8 @@ def load():
 EXPORTED = ('dlwpcs_version', 'dlwpcs_last_error', 'dlwpcs_conv_out_edge', 'dlwpcs_pad_lut_host', 'dlwpcs_pad_fwd',
             'dlwpcs_pad_bwd', 'dlwpcs_packed_weight_bytes', 'dlwpcs_pack_weights', 'dlwpcs_conv2d_fwd',
             'dlwpcs_dgrad_workspace_bytes', 'dlwpcs_conv2d_dgrad', 'dlwpcs_wgrad_workspace_bytes',
-            'dlwpcs_conv2d_wgrad', 'dlwpcs_act_fwd', 'dlwpcs_act_bwd', 'dlwpcs_conv2d_fwd_host')
+            'dlwpcs_conv2d_wgrad', 'dlwpcs_act_fwd', 'dlwpcs_act_bwd', 'dlwpcs_conv2d_fwd_host',
+            'dlwpcs_mse_loss_grad', 'dlwpcs_adam_step')
 
 
 class DlwpcsError(RuntimeError):
@@ -252,3 +255,24 @@ def conv2d_fwd_host(d, x, w_eq, w_pol, w_np=None, b_eq=None, b_pol=None, b_np=No
     check(lib.dlwpcs_conv2d_fwd_host(ctypes.byref(d), ctypes.byref(cw), x.ctypes.data_as(ctypes.c_void_p),
                                      y.ctypes.data_as(ctypes.c_void_p)))
     return y
+
+
+def mse_loss_grad(y, t, loss_accum):
+    """keras 'mse': adds mean((y-t)^2) to the 1-element float32 device tensor loss_accum, returns dL/dy."""
+    require_cuda(y, t, loss_accum)
+    y, t = y.contiguous(), t.contiguous()
+    dy = torch.empty_like(y)
+    n = y.numel()
+    check(load().dlwpcs_mse_loss_grad(ptr(y), ptr(t), ptr(dy), ptr(loss_accum), n, 1.0 / max(n, 1), dtype_code(y.dtype),
+                                      stream_ptr()))
+    return dy
+
+
+def adam_step(param, grad, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    """In-place Keras-Adam update of a flat float32 parameter buffer."""
+    require_cuda(param, grad, m, v)
+    for t in (param, grad, m, v):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise DlwpcsError('adam_step needs contiguous float32 buffers')
+    check(load().dlwpcs_adam_step(ptr(param), ptr(grad), ptr(m), ptr(v), param.numel(), lr, beta1, beta2, eps, int(step),
+                                  grad_scale, stream_ptr()))

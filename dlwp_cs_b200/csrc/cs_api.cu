@@ -1,5 +1,6 @@
 // libdlwpcs C ABI: error reporting, halo tables, geometry, standalone padding / activation kernels and the dispatch of
 // the convolution entry points onto the fp32 (cs_fp32.cu) and tcgen05 bf16 (cs_tc.cu) kernels.
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -238,6 +239,42 @@ __global__ void act_bwd_kernel(const T *__restrict__ dy, const T *__restrict__ y
   for (; i < n; i += stride) dx[i] = from_f<T>(to_f<T>(dy[i]) * act_grad_from_y(to_f<T>(y[i]), act, slope, maxv));
 }
 
+template <typename T>
+__global__ void mse_kernel(const T *__restrict__ y, const T *__restrict__ t, T *__restrict__ dy, float *loss, long long n,
+                           float inv) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float acc = 0.f;
+  for (; i < n; i += stride) {
+    const float d = to_f<T>(y[i]) - to_f<T>(t[i]);
+    acc = fmaf(d, d, acc);
+    dy[i] = from_f<T>(2.f * d * inv);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += part[w];
+    atomicAdd(loss, s * inv);
+  }
+}
+
+__global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                            float *__restrict__ v, long long n, float lr_t, float b1, float b2, float eps, float gscale) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
 static int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -344,6 +381,32 @@ int dlwpcs_act_bwd(const void *dy, const void *y, void *dx, int64_t count, int a
   else
     act_bwd_kernel<__nv_bfloat16><<<grid_for(count, 256), 256, 0, st>>>(
         (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)y, (__nv_bfloat16 *)dx, count, act, slope, maxv);
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dlwpcs_mse_loss_grad(const void *y, const void *t, void *dy, float *loss_accum, int64_t count, float inv_count,
+                         int dtype, void *stream) {
+  CS_CHECK(elem_size(dtype) != 0 && y && t && dy && loss_accum && count >= 0, "bad arguments to dlwpcs_mse_loss_grad");
+  if (count == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DLWPCS_F32)
+    mse_kernel<float><<<grid_for(count, 256), 256, 0, st>>>((const float *)y, (const float *)t, (float *)dy, loss_accum,
+                                                             count, inv_count);
+  else
+    mse_kernel<__nv_bfloat16><<<grid_for(count, 256), 256, 0, st>>>(
+        (const __nv_bfloat16 *)y, (const __nv_bfloat16 *)t, (__nv_bfloat16 *)dy, loss_accum, count, inv_count);
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dlwpcs_adam_step(float *param, const float *grad, float *m, float *v, int64_t count, float lr, float beta1,
+                     float beta2, float eps, int step, float grad_scale, void *stream) {
+  CS_CHECK(param && grad && m && v && count >= 0 && step >= 1, "bad arguments to dlwpcs_adam_step");
+  if (count == 0) return 0;
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+  adam_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, count, (float)lr_t, beta1, beta2,
+                                                                       eps, grad_scale);
   CS_CUDA(cudaGetLastError());
   return 0;
 }

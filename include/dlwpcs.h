@@ -107,6 +107,18 @@ int dlwpcs_act_fwd(const void *x, void *y, int64_t count, int act, float slope, 
 int dlwpcs_act_bwd(const void *dy, const void *y, void *dx, int64_t count, int act, float slope, float maxv,
                    int dtype, void *stream);
 
+/* Training-step helpers on flat float32 buffers (the engine keeps all parameters / gradients of a model in one buffer so
+ * that data-parallel training needs a single all-reduce).
+ *   dlwpcs_mse_loss_grad: keras 'mse' (Azure/train_cs.py:424): adds sum((y-t)^2) * inv_count to *loss_accum (device
+ *     float, caller zeroes it) and writes dy = 2 (y-t) * inv_count.  y / t / dy float32 or bfloat16 (dtype), same shape.
+ *   dlwpcs_adam_step: Keras Adam (DLWPFunctional.build_model, DLWP/model/models.py:353-377) with the gradient scaled by
+ *     grad_scale first (1/world_size after the all-reduce):  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *     p -= lr sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps),  t = step (1-based).                                         */
+int dlwpcs_mse_loss_grad(const void *y, const void *t, void *dy, float *loss_accum, int64_t count, float inv_count,
+                         int dtype, void *stream);
+int dlwpcs_adam_step(float *param, const float *grad, float *m, float *v, int64_t count, float lr, float beta1,
+                     float beta2, float eps, int step, float grad_scale, void *stream);
+
 /* Host-buffer entry point: the call a reference-side binding makes with numpy arrays.  Copies x (and weights) to the
  * device, runs pad(halo)+conv, copies y back; synchronous.                                                            */
 int dlwpcs_conv2d_fwd_host(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, const void *x_host, void *y_host);

@@ -1,0 +1,84 @@
+"""GPU tests of the training-step kernels and the data-parallel trainer (single rank here; the all-reduce logic is
+covered on CPU with gloo in tests/test_train_cpu.py and on 2+ GPUs by bench.py --gpus N)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import cs_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from dlwp_cs_b200 import _lib
+    _lib.load()
+    return _lib
+
+
+def keras_adam(p, g, m, v, lr, b1, b2, eps, t):
+    """numpy restatement of keras.optimizers.Adam (the optimizer of Azure/train_cs.py:424)."""
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    lr_t = lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+    return p - lr_t * m / (np.sqrt(v) + eps), m, v
+
+
+def test_adam_step_matches_keras_formula(lib):
+    rng = np.random.default_rng(0)
+    n = 100003
+    p, g = rng.standard_normal(n), rng.standard_normal(n) * 0.1
+    m, v = np.zeros(n), np.zeros(n)
+    dp, dm, dv = [torch.tensor(a, dtype=torch.float32).cuda() for a in (p, m, v)]
+    for t in range(1, 4):
+        gt = g * t
+        dg = torch.tensor(gt * 4.0, dtype=torch.float32).cuda()          # summed over 4 "ranks"
+        lib.adam_step(dp, dg, dm, dv, 1e-3, 0.9, 0.999, 1e-7, t, grad_scale=0.25)
+        p, m, v = keras_adam(p, gt, m, v, 1e-3, 0.9, 0.999, 1e-7, t)
+        # the hyper-parameters cross the C ABI as float32: 1 - 0.999f differs from 0.001 by 1.3e-5 relative
+        np.testing.assert_allclose(dp.cpu().numpy(), p, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(dv.cpu().numpy(), v, rtol=5e-5, atol=1e-12)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_mse_loss_grad(lib, dtype):
+    g = torch.Generator().manual_seed(2)
+    y = torch.randn(3, 6, 8, 8, 5, generator=g).to(dtype)
+    t = torch.randn(3, 6, 8, 8, 5, generator=g).to(dtype)
+    loss = torch.zeros(1, device='cuda')
+    dy = lib.mse_loss_grad(y.cuda(), t.cuda(), loss)
+    d = y.double() - t.double()
+    assert abs(float(loss) - float((d * d).mean())) < 1e-5 * float((d * d).mean())
+    ref = 2 * d / d.numel()
+    tol = 1e-6 if dtype == torch.float32 else 2.0 ** -8
+    np.testing.assert_allclose(dy.double().cpu().numpy(), ref.numpy(), rtol=tol, atol=tol * float(ref.abs().max()))
+
+
+def test_trainer_step_matches_oracle_autograd_and_keras_adam(lib):
+    """One optimizer step of the fp32 U-Net through the engine == oracle autograd (float64) + the Keras Adam formula."""
+    from dlwp_cs_b200.unet import CubeSphereUNet2
+    from dlwp_cs_b200.train import DataParallelTrainer
+    n, b, cin, cout, base = 8, 2, 5, 3, 8
+    params = O.make_unet2_params(cin, cout, base=base, seed=4)
+    model = CubeSphereUNet2(cin, cout, base=base).cuda()
+    model.load_oracle_params(params)
+    names = [k for k, _ in model.named_parameters()]
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(b, 6, n, n, cin, generator=g)
+    t = torch.randn(b, 6, n, n, cout, generator=g)
+    # oracle
+    pd = {k: params[k].double().requires_grad_(True) for k in names}
+    loss_ref = (O.unet2(pd, x.double()) - t.double()).pow(2).mean()
+    loss_ref.backward()
+    trainer = DataParallelTrainer(model, lr=1e-3)
+    loss = trainer.step(x.cuda(), t.cuda())
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) < 1e-5 * float(loss_ref.detach())
+    for k, p in model.named_parameters():
+        gref = pd[k].grad.numpy()
+        # gradient parity (the flat buffer still holds this step's gradients)
+        np.testing.assert_allclose(p.grad.double().cpu().numpy(), gref, rtol=1e-4,
+                                   atol=1e-5 * max(float(np.abs(gref).max()), 1e-30))
+        pref, _, _ = keras_adam(params[k].double().numpy(), gref, 0.0, 0.0, 1e-3, 0.9, 0.999, 1e-7, 1)
+        # the first Adam step moves every weight by ~lr * sign(g); tiny gradients make the direction itself ill-conditioned
+        big = np.abs(gref) > 1e-4 * np.abs(gref).max()
+        np.testing.assert_allclose(p.detach().double().cpu().numpy()[big], pref[big], rtol=0, atol=2e-5)
