@@ -315,7 +315,13 @@ def main():
         else:
             roof = {'bound': 'hbm', 'achieved': top['gbs'], 'peak': pk['hbm'], 'unit': 'GB/s',
                     'frac': round(top['gbs'] / pk['hbm'], 4)}
-        roof.update({'traffic': None, 'kernel': 'cs_conv (%s: %s)' % (dtype, top['layer']), 'peak_source': pk['src'],
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+        if dtype == 'bf16' and os.path.exists(tpath):            # DRAM bytes of that launch from the ncu --set full capture
+            tj = json.load(open(tpath))
+            if top['layer'] in tj['dram_bytes_per_launch']:
+                traffic = tj['dram_bytes_per_launch'][top['layer']] * args.batch / tj['batch']
+        roof.update({'traffic': traffic, 'kernel': 'cs_conv (%s: %s)' % (dtype, top['layer']), 'peak_source': pk['src'],
                      'share_of_step': top['share'],
                      'whole_step_frac_of_roof': round(sum(r['frac_of_roof'] * r['ms'] for r in layers) / tot, 3)})
 

@@ -59,6 +59,7 @@ struct TcPlan {
   int patchBytes, PS, AS, tmemCols;  // bytes per patch stage, patch stages, accumulator stages
   int G;                             // patch-table entries per face (multiple of 4)
   int TS, tabBytes, twoTabs;         // table ring slots, bytes per slot (one or two tables of NPIXp entries)
+  int stgBytes, stgBufs;             // output staging per epilogue warp (32 rows x cout bf16; 0: direct stores)
   int smemBytes;
   int64_t groupBytes;                // packed weights per face group
   int vec, logS;                     // 16-byte gather path usable; log2(S) or -1
@@ -132,6 +133,14 @@ __device__ __forceinline__ void cp_async_wait_dyn(int pending) {
 __device__ __forceinline__ void st_shared16(uint32_t dst, const uint4 &o) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
 }
+// TMA bulk store shared -> global (bypasses the L1 / LSU pipeline entirely) and its completion groups
+__device__ __forceinline__ void tma_bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -346,6 +355,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t tabring = misc + 512 + MAX_UNITS * 8 + (uint32_t)(3 * L.CoutP * 4);          // TS slots of tabBytes
   const int32_t *s_tab = reinterpret_cast<const int32_t *>(gen + (tabring - base));
   const uint32_t bar_tfull = misc + 256, bar_tempty = misc + 288;
+  const uint32_t stg0 = (tabring + (uint32_t)(L.TS * L.tabBytes) + 127u) & ~127u;      // 8 warps x stgBufs x stgBytes
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = 6 * P.batch * L.tpf;
@@ -492,6 +502,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // warps of a lane quarter take alternate m-blocks. =====
     const int quarter = warp & 3, half = (warp - EPI_WARP0) >> 2;
     const bool fast_out = !P.y_f32 && P.cout % 8 == 0;
+    // bf16 rows of 16-byte multiples: every warp compacts its 32 rows of an m-block in shared memory -- they are one
+    // contiguous run in HBM once the discarded columns are dropped -- and writes the run back with fully coalesced
+    // 512-byte stores (the per-thread 32-byte stores of the direct path cost 8x the L1 sector operations and starve
+    // the loaders' cp.async of the same pipeline)
+    const bool staged = L.stgBytes > 0;
+    const uint32_t stg = stg0 + (uint32_t)(warp - EPI_WARP0) * L.stgBytes;
+    const uint32_t rowB = (uint32_t)P.cout * 2u;
+    const bool act_fast = P.act == DLWPCS_ACT_CAPPED_LEAKY_RELU && P.slope >= 0.f && P.slope <= 1.f;
+    const uint32_t cpr = rowB >> 4;                                             // 16-byte chunks per output row
+    const int cprLog = (cpr & (cpr - 1)) == 0 ? 31 - __clz(cpr) : -1;          // rows of 2^k chunks: shifts instead of divisions
+    const uint32_t smask = (cpr & (cpr - 1)) == 0 ? min(cpr, 8u) - 1u : 0u;    // XOR swizzle of the chunk index by row
     int sa = 0, pa = 0, k = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
       const TileInfo T = decode_tile(tile, P.batch, L.tpf);
@@ -507,6 +528,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int r = q / L.Wv, c = q - r * L.Wv;
         const bool ok = q < L.Q && c < P.Wout;
         const size_t opix = face_px + (size_t)r * P.Wout + c;
+        const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+        const int nvalid = __popc(okmask);
+        const size_t opix0 = __shfl_sync(0xffffffffu, opix, okmask ? __ffs(okmask) - 1 : 0);   // first valid row of the warp
+        const uint32_t prow = (uint32_t)(opix - opix0);                          // compacted row of this lane
+        const uint32_t srow = stg + prow * rowB;
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((sa * L.MB + mb) * L.CoutP);
         for (int n0 = 0; n0 < L.CoutP; n0 += 32) {
           uint32_t v[32];
@@ -523,12 +549,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               const float4 bv = *reinterpret_cast<const float4 *>(bias + nb + 4 * k4);
-              o[4 * k4 + 0] = act_apply(__uint_as_float(v[16 * h + 4 * k4 + 0]) + bv.x, P.act, P.slope, P.maxv);
-              o[4 * k4 + 1] = act_apply(__uint_as_float(v[16 * h + 4 * k4 + 1]) + bv.y, P.act, P.slope, P.maxv);
-              o[4 * k4 + 2] = act_apply(__uint_as_float(v[16 * h + 4 * k4 + 2]) + bv.z, P.act, P.slope, P.maxv);
-              o[4 * k4 + 3] = act_apply(__uint_as_float(v[16 * h + 4 * k4 + 3]) + bv.w, P.act, P.slope, P.maxv);
+              o[4 * k4 + 0] = __uint_as_float(v[16 * h + 4 * k4 + 0]) + bv.x;
+              o[4 * k4 + 1] = __uint_as_float(v[16 * h + 4 * k4 + 1]) + bv.y;
+              o[4 * k4 + 2] = __uint_as_float(v[16 * h + 4 * k4 + 2]) + bv.z;
+              o[4 * k4 + 3] = __uint_as_float(v[16 * h + 4 * k4 + 3]) + bv.w;
             }
-            if (fast_out && nb + 16 <= P.cout) {
+            if (act_fast) {            // capped leaky ReLU with 0 <= slope <= 1: min(max(v, slope v), cap)
+#pragma unroll
+              for (int e = 0; e < 16; ++e) o[e] = fminf(fmaxf(o[e], P.slope * o[e]), P.maxv);
+            } else if (P.act != DLWPCS_ACT_NONE) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) o[e] = act_apply(o[e], P.act, P.slope, P.maxv);
+            }
+            if (staged) {
+              if (nb + 8 <= P.cout)
+                st_shared16(srow + ((((uint32_t)nb >> 3) ^ (prow & smask)) << 4), make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                                  pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
+              if (nb + 16 <= P.cout)
+                st_shared16(srow + (((((uint32_t)nb >> 3) + 1u) ^ (prow & smask)) << 4), make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]),
+                                                                        pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15])));
+            } else if (fast_out && nb + 16 <= P.cout) {
               __nv_bfloat16 *yp = reinterpret_cast<__nv_bfloat16 *>(P.y) + opix * P.cout + nb;
               reinterpret_cast<uint4 *>(yp)[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
                                                             pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
@@ -552,6 +592,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 if (nb + k < P.cout) yp[k] = __float2bfloat16_rn(o[k]);
             }
           }
+        }
+        if (staged) {
+          __syncwarp();
+          uint8_t *gdst = reinterpret_cast<uint8_t *>(P.y) + opix0 * rowB;
+          const uint32_t total = (uint32_t)nvalid * rowB;
+          for (uint32_t off = (uint32_t)lane * 16u; off < total; off += 512u) {
+            uint32_t row, ch;
+            if (cprLog >= 0) { row = off >> (4 + cprLog); ch = (off >> 4) & (cpr - 1u); }
+            else { row = off / rowB; ch = (off - row * rowB) >> 4; }
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(stg + row * rowB + ((ch ^ (row & smask)) << 4)));
+            *reinterpret_cast<uint4 *>(gdst + off) = v;
+          }
+          __syncwarp();                                 // the buffer is rewritten by the next m-block
         }
       }
       tc_fence_before();
@@ -605,6 +660,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const uint32_t row = dst0 + (uint32_t)i * L.RB;
                 const __nv_bfloat16 *g = px[e] >= 0 ? src + (boff + px[e]) * C + cc : P.x0;
                 cp_async16(row + ((cw ^ ((row >> 7) & (uint32_t)L.swzMask)) << 4), g, px[e] >= 0 ? 16u : 0u);
+              }
+            }
+          }
+        } else if (mode == DLWPCS_SRC_POOL2 && !P.mask_y) {
+          // 2x2 mean (AveragePooling3D((1,2,2)), train_cs.py:197) through registers: two patch rows = eight 16-byte
+          // loads in flight per thread; the mean is rounded to bf16 once, like a stored pooled tensor would be
+          for (int i0 = lt >> L.logS; i0 < npix; i0 += 2 * pstep) {
+            uint4 v[2][4];
+            int px[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = i0 + e * pstep;
+              px[e] = (i < npix && chan_ok) ? tab[i] : -1;
+              if (px[e] >= 0) {
+                const __nv_bfloat16 *g = src + (boff + px[e]) * C + cc;
+                v[e][0] = __ldg(reinterpret_cast<const uint4 *>(g));
+                v[e][1] = __ldg(reinterpret_cast<const uint4 *>(g + C));
+                v[e][2] = __ldg(reinterpret_cast<const uint4 *>(g + (size_t)w2_0 * C));
+                v[e][3] = __ldg(reinterpret_cast<const uint4 *>(g + (size_t)(w2_0 + 1) * C));
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = i0 + e * pstep;
+              if (i < npix) {
+                uint4 o = make_uint4(0, 0, 0, 0);
+                if (px[e] >= 0) {
+                  float a[8], t[8];
+                  unpack_bf16x8(v[e][0], a);
+#pragma unroll
+                  for (int q = 1; q < 4; ++q) {
+                    unpack_bf16x8(v[e][q], t);
+#pragma unroll
+                    for (int k2 = 0; k2 < 8; ++k2) a[k2] += t[k2];
+                  }
+                  o = make_uint4(pack_bf16x2(0.25f * a[0], 0.25f * a[1]), pack_bf16x2(0.25f * a[2], 0.25f * a[3]),
+                                 pack_bf16x2(0.25f * a[4], 0.25f * a[5]), pack_bf16x2(0.25f * a[6], 0.25f * a[7]));
+                }
+                const uint32_t row = dst0 + (uint32_t)i * L.RB;
+                st_shared16(row + ((cw ^ ((row >> 7) & (uint32_t)L.swzMask)) << 4), o);
               }
             }
           }
@@ -706,39 +801,58 @@ const char *make_plan(const dlwpcs_conv_desc *d, const Geometry &g, int gemm_cin
   L->nstages = (L->NU + L->UPS - 1) / L->UPS;
   L->groupBytes = (int64_t)L->NU * L->unitBytes;
   L->resident = (L->nstages <= MAX_STAGES && (int64_t)L->nstages * L->stageBytes <= 96 * 1024) ? 1 : 0;
-  L->NST = L->resident ? L->nstages : 4;
+  L->NST = L->resident ? L->nstages : 3;
   L->Wv = g.Wout + (d->kw - 1) * d->dil_w;
   L->Hv = g.Hout + (d->kh - 1) * d->dil_h;
   L->Q = (g.Hout - 1) * L->Wv + g.Wout;
   L->nmb = (L->Q + 127) / 128;
   L->haloExt = (d->kh - 1) * d->dil_h * L->Wv + (d->kw - 1) * d->dil_w;
   L->G = (L->nmb * 128 + L->haloExt + 3) / 4 * 4;
-  L->TS = 3;
+  L->TS = 2;
   L->twoTabs = (d->c1 > 0 && d->mode1 != d->mode0) ? 1 : 0;
   if (L->NU > MAX_UNITS) return "kernel window x input channels too large";
-  const int tab_max = L->TS * (1 + L->twoTabs) * ((4 * 128 + L->haloExt + 8) * 4);      // table ring, sized for MB = 4
-  const int fixed = 1024 + 512 + MAX_UNITS * 8 + 3 * L->CoutP * 4 + L->NST * L->stageBytes + tab_max;
+  // bf16 outputs with 16-byte rows are compacted in shared memory and written with TMA bulk stores
+  L->stgBytes = (d->y_dtype == DLWPCS_BF16 && gemm_cout % 8 == 0 && !env_int("DLWPCS_TC_NOSTAGE", 0)) ? 32 * gemm_cout * 2 : 0;
+  L->stgBufs = L->stgBytes ? 1 : 0;
+  int fixed0 = 1024 + 512 + MAX_UNITS * 8 + 3 * L->CoutP * 4 + L->NST * L->stageBytes + 8 * L->stgBufs * L->stgBytes + 128;
   auto patch_for = [&](int MB, int *npixp) {
     const int np = ((MB * 128 + L->haloExt + 7) / 8) * 8;
     *npixp = np;
     return (L->nch * np * L->RB + 1023) / 1024 * 1024;            // stages stay 1024-byte aligned (swizzle period)
   };
+  auto tabs_for = [&](int MB) { return L->TS * (1 + L->twoTabs) * (((MB * 128 + L->haloExt + 7) / 8) * 8) * 4; };
   int mbmax = 512 / L->CoutP;
   if (mbmax > 4) mbmax = 4;
   if (mbmax > L->nmb) mbmax = L->nmb;
   int best = 0, np = 0;
   const int forced = env_int("DLWPCS_TC_MB", 0);
-  for (int MB = (forced > 0 && forced < mbmax) ? forced : mbmax; MB >= 1; --MB)
-    if (fixed + 2 * patch_for(MB, &np) <= SMEM_CAP) { best = MB; break; }
+  const int stg_unit = 8 * L->stgBytes;           // one staging buffer for each of the 8 epilogue warps
+  fixed0 -= L->stgBufs * stg_unit;                // staging is decided together with the tile size below
+  const int bufs_max = L->stgBufs;
+  for (int MB = (forced > 0 && forced < mbmax) ? forced : mbmax; MB >= 1 && !best; --MB)
+    for (int bufs = bufs_max; bufs >= 0; --bufs)
+      if (fixed0 + bufs * stg_unit + tabs_for(MB) + 2 * patch_for(MB, &np) <= SMEM_CAP) {
+        best = MB;
+        L->stgBufs = bufs;
+        break;
+      }
+  if (best) {
+    if (L->stgBufs == 0) L->stgBytes = 0;
+    fixed0 += L->stgBufs * stg_unit;
+  } else {
+    L->stgBufs = 0;
+    L->stgBytes = 0;
+  }
   if (!best) {
     best = 1;                                      // single-buffered patch as the last resort
-    if (fixed + patch_for(1, &np) > SMEM_CAP) return "input patch does not fit shared memory (too many input channels)";
+    if (fixed0 + tabs_for(1) + patch_for(1, &np) > SMEM_CAP) return "input patch does not fit shared memory (too many input channels)";
   }
   const int tiles = (L->nmb + best - 1) / best;
   best = (L->nmb + tiles - 1) / tiles;             // even out the tiles of a face
   L->MB = best;
   L->tpf = (L->nmb + best - 1) / best;
   L->patchBytes = patch_for(best, &L->NPIXp);
+  const int fixed = fixed0 + tabs_for(best);
   L->blockBytes = L->NPIXp * L->RB;
   L->tabBytes = (1 + L->twoTabs) * L->NPIXp * 4;
   L->PS = (SMEM_CAP - fixed) / L->patchBytes;
