@@ -186,6 +186,7 @@ def main():
     ap.add_argument('--no-train', action='store_true')
     ap.add_argument('--train-batch', type=int, default=32, help='training samples per GPU per step')
     ap.add_argument('--train-steps', type=int, default=5)
+    ap.add_argument('--train-dtype', default='bf16', choices=['bf16', 'f32'])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -337,8 +338,9 @@ def main():
         trainer = DataParallelTrainer(tmodel, lr=1e-3)
         g = torch.Generator().manual_seed(100 + rank)
         tb = args.train_batch
-        xs = torch.randn(tb, 6, N_FACE, N_FACE, C_PROG + C_FORC, generator=g).to(dev)
-        ts = torch.randn(tb, 6, N_FACE, N_FACE, C_PROG, generator=g).to(dev)
+        ttd = torch.bfloat16 if args.train_dtype == 'bf16' else torch.float32
+        xs = torch.randn(tb, 6, N_FACE, N_FACE, C_PROG + C_FORC, generator=g).to(dev).to(ttd)
+        ts = torch.randn(tb, 6, N_FACE, N_FACE, C_PROG, generator=g).to(dev).to(ttd)
         for _ in range(2):
             trainer.step(xs, ts)
         barrier()
@@ -354,10 +356,12 @@ def main():
         tms = float(tt.item()) / args.train_steps
         train = {'metric': 'train samples/sec, unet2 C48 fwd+bwd+Adam', 'value': tb * world / (tms * 1e-3),
                  'unit': 'samples/s', 'ms_per_step': tms, 'global_batch': tb * world, 'batch_per_gpu': tb,
-                 'dtype': 'f32', 'parallelism': 'dp%d, one flat all-reduce of %d float32 gradients per step'
+                 'dtype': args.train_dtype, 'parallelism': 'dp%d, one flat all-reduce of %d float32 gradients per step'
                                                 % (world, trainer.flat.count),
                  'loss': float(loss.item()),
-                 'note': 'float32 CUDA-core backward kernels this round; the bf16 tensor-core backward is the next row'}
+                 'note': ('bf16 activations: forward and dgrad on the tcgen05 kernel, wgrad on CUDA cores with float32 '
+                          'accumulation (tensor-core wgrad is the next row); float32 master weights, fused Adam')
+                 if args.train_dtype == 'bf16' else 'float32 CUDA-core kernels (1e-5 parity path)'}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

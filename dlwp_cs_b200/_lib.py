@@ -185,7 +185,8 @@ def conv2d_dgrad(d, dy, y, packed_t):
     if nbytes < 0:
         check(1)
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dy.device)
-    dx = torch.empty((d.batch, 6, d.n, d.n, d.cin), dtype=torch.float32, device=dy.device)
+    dx = torch.empty((d.batch, 6, d.n, d.n, d.cin), dtype=torch.float32 if d.x_dtype == F32 else torch.bfloat16,
+                     device=dy.device)
     check(lib.dlwpcs_conv2d_dgrad(ctypes.byref(d), ptr(dy), ptr(y), ptr(packed_t), ptr(dx), ptr(ws), stream_ptr()))
     return dx
 

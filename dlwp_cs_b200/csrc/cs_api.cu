@@ -459,7 +459,7 @@ int dlwpcs_conv2d_fwd(const dlwpcs_conv_desc *d, const void *x0, const void *x1,
 
 static int check_bwd(const dlwpcs_conv_desc *d, Geometry *g) {
   if (int rc = check_common(d, g)) return rc;
-  CS_CHECK(d->x_dtype == DLWPCS_F32 && d->y_dtype == DLWPCS_F32, "backward kernels are float32");
+  CS_CHECK(d->x_dtype == d->y_dtype, "backward needs activations and outputs of one dtype (float32 or bfloat16)");
   CS_CHECK(d->stride_h == 1 && d->stride_w == 1, "backward is implemented for strides == 1 only (all cubed-sphere "
            "models in the reference use stride 1: Azure/train_cs.py:200-207)");
   CS_CHECK(d->c1 == 0 && d->mode0 == DLWPCS_SRC_SAME, "backward takes a single un-resampled input source");
@@ -469,7 +469,7 @@ static int check_bwd(const dlwpcs_conv_desc *d, Geometry *g) {
 int64_t dlwpcs_dgrad_workspace_bytes(const dlwpcs_conv_desc *d) {
   Geometry g;
   if (check_bwd(d, &g)) return -1;
-  return d->halo > 0 ? (int64_t)d->batch * 6 * g.Hin * g.Win * d->cin * 4 : 0;
+  return d->halo > 0 ? (int64_t)d->batch * 6 * g.Hin * g.Win * d->cin * elem_size(d->x_dtype) : 0;
 }
 
 int dlwpcs_conv2d_dgrad(const dlwpcs_conv_desc *d, const void *dy, const void *y, const void *packed_w_t, void *dx,
@@ -479,6 +479,7 @@ int dlwpcs_conv2d_dgrad(const dlwpcs_conv_desc *d, const void *dy, const void *y
   CS_CHECK(dy && packed_w_t && dx && (d->halo == 0 || workspace), "null pointer");
   CS_CHECK(d->act == DLWPCS_ACT_NONE || y, "activation derivative needs the forward output y");
   if (d->batch == 0) return 0;
+  if (d->x_dtype == DLWPCS_BF16) return tc_conv_dgrad(d, g, dy, y, packed_w_t, dx, workspace, (cudaStream_t)stream);
   return fp32_conv_dgrad(d, g, (const float *)dy, (const float *)y, (const float *)packed_w_t, (float *)dx, workspace,
                          (cudaStream_t)stream);
 }
@@ -499,7 +500,7 @@ int dlwpcs_conv2d_wgrad(const dlwpcs_conv_desc *d, const void *x0, const void *d
            "use_bias needs bias gradient buffers");
   CS_CHECK(d->act == DLWPCS_ACT_NONE || y, "activation derivative needs the forward output y");
   CS_CHECK(d->batch > 0, "wgrad needs a non-empty batch");
-  return fp32_conv_wgrad(d, g, (const float *)x0, (const float *)dy, (const float *)y, out, workspace,
+  return fp32_conv_wgrad(d, g, x0, dy, y, out, workspace,
                          (cudaStream_t)stream);
 }
 

@@ -56,7 +56,7 @@ int fp32_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const float *x0,
                   float *y, cudaStream_t st);
 int fp32_conv_dgrad(const dlwpcs_conv_desc *d, const Geometry &g, const float *dy, const float *y,
                     const float *packed_t, float *dx, void *workspace, cudaStream_t st);
-int fp32_conv_wgrad(const dlwpcs_conv_desc *d, const Geometry &g, const float *x0, const float *dy, const float *y,
+int fp32_conv_wgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *dy, const void *y,
                     const dlwpcs_conv_wgrads *out, void *workspace, cudaStream_t st);
 int64_t fp32_wgrad_workspace_bytes(const dlwpcs_conv_desc *d, const Geometry &g);
 
@@ -67,5 +67,7 @@ int tc_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_c
 int tc_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed,
                 void *y, cudaStream_t st);
 bool tc_supported(const dlwpcs_conv_desc *d, const Geometry &g, const char **why);
+int tc_conv_dgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *dy, const void *y, const void *packed_t,
+                  void *dx, void *workspace, cudaStream_t st);
 
 }  // namespace dlwpcs

@@ -372,7 +372,8 @@ constexpr int WCO = 32;    // output channels per CTA
 constexpr int WTAPS = 9;   // taps accumulated per CTA pass
 
 struct WgradP {
-  const float *x, *dy, *mask_y;
+  const void *x, *dy, *mask_y;   // float32 or bfloat16 (in_bf16)
+  int in_bf16;
   const int32_t *lut;
   float *ws;       // [6*strips][taps][cin][cout]
   float *ws_b;     // [6*strips][cout]
@@ -381,6 +382,10 @@ struct WgradP {
   int act;
   float slope, maxv;
 };
+
+__device__ __forceinline__ float ld_in(const void *p, long long i, int bf16) {
+  return bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(p)[i]) : __ldg(reinterpret_cast<const float *>(p) + i);
+}
 
 // grid: (cin_chunks*tap_blocks, ceil(cout/WCO), 6*strips); block 256 = (8 input channels) x (32 output channels)
 __global__ void __launch_bounds__(256) wgrad_fp32_kernel(const __grid_constant__ WgradP P) {
@@ -425,7 +430,7 @@ __global__ void __launch_bounds__(256) wgrad_fp32_kernel(const __grid_constant__
       const int q = idx / WCK, k = idx - q * WCK;
       const int code = s_src[q];
       float v = 0.f;
-      if (code >= 0 && cc0 + k < P.cin) v = __ldg(P.x + ((long long)b * src_px + code) * P.cin + cc0 + k);
+      if (code >= 0 && cc0 + k < P.cin) v = ld_in(P.x, ((long long)b * src_px + code) * P.cin + cc0 + k, P.in_bf16);
       s_patch[idx] = v;
     }
     for (int idx = tid; idx < P.TH * P.TW * WCO; idx += 256) {
@@ -434,8 +439,8 @@ __global__ void __launch_bounds__(256) wgrad_fp32_kernel(const __grid_constant__
       float v = 0.f;
       if (oy < P.Ho && ox < P.Wo && co0 + k < P.cout) {
         const long long off = ((((long long)b * 6 + f) * P.Ho + oy) * P.Wo + ox) * P.cout + co0 + k;
-        v = __ldg(P.dy + off);
-        if (P.mask_y) v *= act_grad_from_y(__ldg(P.mask_y + off), P.act, P.slope, P.maxv);
+        v = ld_in(P.dy, off, P.in_bf16);
+        if (P.mask_y) v *= act_grad_from_y(ld_in(P.mask_y, off, P.in_bf16), P.act, P.slope, P.maxv);
       }
       s_dy[idx] = v;
     }
@@ -526,11 +531,12 @@ int64_t fp32_wgrad_workspace_bytes(const dlwpcs_conv_desc *d, const Geometry &g)
   return 6 * strips * ((int64_t)g.taps * d->cin * d->cout + d->cout) * 4;
 }
 
-int fp32_conv_wgrad(const dlwpcs_conv_desc *d, const Geometry &g, const float *x0, const float *dy, const float *y,
+int fp32_conv_wgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *dy, const void *y,
                     const dlwpcs_conv_wgrads *out, void *workspace, cudaStream_t st) {
   WgradP P;
   memset(&P, 0, sizeof(P));
   P.x = x0; P.dy = dy;
+  P.in_bf16 = d->x_dtype == DLWPCS_BF16;
   P.mask_y = d->act != DLWPCS_ACT_NONE ? y : nullptr;
   P.act = d->act; P.slope = d->act_slope; P.maxv = d->act_max;
   P.lut = nullptr;

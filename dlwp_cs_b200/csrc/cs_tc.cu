@@ -1053,4 +1053,49 @@ int tc_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, co
   return launch_tc(P, st);
 }
 
+// dgrad on the same kernel: dx_ext[r,c,ci] = sum_{u,v,o} dy[r + pt - u*dh, c + pl - v*dw, o] * W[u,v,ci,o] is a convolution
+// over dy (scaled by the activation derivative taken from the forward output) with the taps rotated 180 degrees and the
+// channels swapped (weights packed with transposed = 1), zero fill outside dy, followed by the adjoint of the halo gather.
+int tc_conv_dgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *dy, const void *y, const void *packed_t,
+                  void *dx, void *workspace, cudaStream_t st) {
+  dlwpcs_conv_desc dd = *d;
+  dd.cin = d->cout; dd.cout = d->cin; dd.c0 = d->cout; dd.c1 = 0;
+  dd.mode0 = dd.mode1 = DLWPCS_SRC_SAME;
+  dd.halo = 0; dd.n = g.Hout;
+  dd.x_dtype = dd.y_dtype = DLWPCS_BF16;
+  dd.act = DLWPCS_ACT_NONE; dd.use_bias = 0;
+  Geometry gg;
+  gg.Hin = g.Hout; gg.Win = g.Wout; gg.Hout = g.Hin; gg.Wout = g.Win;
+  for (int k = 0; k < 3; ++k) gg.pt[k] = (d->kh - 1) * d->dil_h - g.pt[k];
+  gg.pl = (d->kw - 1) * d->dil_w - g.pl;
+  gg.taps = g.taps;
+  TcP P;
+  memset(&P, 0, sizeof(P));
+  const char *r = make_plan(&dd, gg, d->cout, d->cin, &P.pl_);
+  CS_CHECK(r == nullptr, "bf16 tensor-core dgrad does not support this configuration: %s", r);
+  TcPlan &L = P.pl_;
+  P.x0 = (const __nv_bfloat16 *)dy;
+  P.x1 = nullptr;
+  P.tab0 = get_patch_table(gg, L, g.Hout, 0, DLWPCS_SRC_SAME);
+  if (!P.tab0) return 3;
+  P.tab1 = P.tab0;
+  P.ppb0 = P.ppb1 = 6 * g.Hout * g.Wout;
+  P.wpack = (const uint8_t *)packed_t;
+  P.bias = reinterpret_cast<const float *>(P.wpack + 3 * L.groupBytes);      // zeros in a transposed pack
+  P.y = d->halo > 0 ? workspace : dx;
+  P.y_f32 = 0;
+  P.mask_y = d->act != DLWPCS_ACT_NONE ? y : nullptr;
+  P.mask_f32 = 0;
+  P.mask_act = d->act; P.mask_slope = d->act_slope; P.mask_max = d->act_max;
+  P.batch = d->batch; P.n = g.Hout; P.Hout = gg.Hout; P.Wout = gg.Wout;
+  P.cin = d->cout; P.cout = d->cin; P.c0 = d->cout; P.c1 = 0;
+  P.mode0 = P.mode1 = DLWPCS_SRC_SAME;
+  P.kw = d->kw; P.dh = d->dil_h; P.dw = d->dil_w;
+  P.act = DLWPCS_ACT_NONE;
+  L.vec = (d->cout % 8 == 0) && aligned16(dy) && (!P.mask_y || aligned16(y));
+  if (int rc = launch_tc(P, st)) return rc;
+  if (d->halo > 0) return dlwpcs_pad_bwd(workspace, dx, d->batch, d->n, d->cin, d->halo, DLWPCS_BF16, st);
+  return 0;
+}
+
 }  // namespace dlwpcs

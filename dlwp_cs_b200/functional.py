@@ -73,8 +73,8 @@ class _CubeSphereConv(torch.autograd.Function):
     def backward(ctx, dy):
         x, y, w_eq, w_pol, w_np = ctx.saved_tensors
         d = ctx.d
-        if d.x_dtype != _lib.F32:
-            raise _lib.DlwpcsError('backward is float32 in this build')
+        if d.x_dtype != d.y_dtype:
+            raise _lib.DlwpcsError('backward needs the output dtype to equal the input dtype')
         dy = dy.contiguous()
         dx = None
         if ctx.needs_input_grad[0]:
