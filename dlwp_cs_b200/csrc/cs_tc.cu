@@ -82,6 +82,7 @@ struct TcP {
   int mask_act;
   float mask_slope, mask_max;
   long long *dbg;               // optional phase timestamps (DLWPCS_TC_TIMING=1)
+  int knock;                    // bottleneck analysis (DLWPCS_TC_KNOCK): 1 no gathers, 2 no MMAs, 4 no epilogue math/stores, 8 no global stores
   TcPlan pl_;
 };
 
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         const uint64_t a_unit = a_stage + e.x;
         const uint64_t b_unit = b_ring + ((uint32_t)stage * stage16 + (e.y & 0xFFFFFu));
-        if (elect_one()) {
+        if (!(P.knock & 2) && elect_one()) {
 #pragma unroll
           for (int mi = 0; mi < (MBT + NUM_MMA_WARPS - 1) / NUM_MMA_WARPS; ++mi) {
             const int mb = mw + NUM_MMA_WARPS * mi;
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           tmem_ld16(trow + (uint32_t)n0, v);
           if (two) tmem_ld16(trow + (uint32_t)n0 + 16u, v + 16);
           tmem_ld_wait();
-          if (!ok) continue;
+          if (!ok || (P.knock & 4)) continue;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (h == 1 && !two) break;
@@ -593,7 +594,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
           }
         }
-        if (staged) {
+        if (staged && !(P.knock & 12)) {
           __syncwarp();
           uint8_t *gdst = reinterpret_cast<uint8_t *>(P.y) + opix0 * rowB;
           const uint32_t total = (uint32_t)nvalid * rowB;
@@ -632,7 +633,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int32_t *t0 = s_tab + (size_t)ts * (L.tabBytes / 4);
       const int32_t *t1 = L.twoTabs ? t0 + L.NPIXp : t0;
       const size_t b0 = (size_t)T.b * P.ppb0, b1 = (size_t)T.b * P.ppb1;
-      if (L.vec && L.logS >= 0) {
+      if (P.knock & 1) {
+      } else if (L.vec && L.logS >= 0) {
         // each thread owns one 16-byte chunk (fixed source / channel offset) of every (256 >> logS)-th patch row
         const int chunk = lt & (L.S - 1), c = chunk * 8;
         const bool first = c < P.c0;
@@ -953,6 +955,8 @@ int launch_tc(TcP &P, cudaStream_t st) {
   int grid = num_sms();
   if (grid > ntiles) grid = (int)ntiles;
   static const int timing = env_int("DLWPCS_TC_TIMING", 0);
+  static const int knock = env_int("DLWPCS_TC_KNOCK", 0);
+  P.knock = knock;
   static long long *dbg = nullptr;
   if (timing) {
     if (!dbg) CS_CUDA(cudaMalloc(&dbg, 16 * sizeof(long long)));

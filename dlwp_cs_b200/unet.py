@@ -140,6 +140,9 @@ class RolloutEngine(object):
                                fused[2], dt, dt, c0, m0, c1, m1)
             self.plan.append([name, d, s0, s1, dst, None])
         self.graph = None
+        self.graph_host = None
+        self.host_ring = None
+        self.host_chunk = 0
         self.repack()
 
     def repack(self):
@@ -155,6 +158,7 @@ class RolloutEngine(object):
                 bs = [None if v is None else F.pad(v.detach(), (0, self.cp_pad - self.cp)) for v in bs]
             item[5] = _lib.pack_weights(item[1], ws[0], ws[1], ws[2], bs[0], bs[1], bs[2])
         self.graph = None
+        self.graph_host = None
 
     def _pad_in(self, w):
         kh, kw, _, co = w.shape
@@ -226,3 +230,45 @@ class RolloutEngine(object):
     def run(self, state, forcing=None):
         self.load_inputs(state, forcing)
         return self.launch()
+
+    # ---- forecast delivered to the host while the rollout is still running ------------------------------------------
+    def _enqueue_all_to_host(self):
+        """The rollout with the forecast ring streamed to pinned host memory in chunks of `host_chunk` model steps on a
+        second stream: the PCIe transfer of steps [t0, t1) overlaps the computation of the following steps (the
+        reference copies every step's result to the host before it starts the next one, models.py:446-454)."""
+        main = torch.cuda.current_stream(self.device)
+        side = self._side
+        for t0 in range(0, self.steps, self.host_chunk):
+            t1 = min(self.steps, t0 + self.host_chunk)
+            for t in range(t0, t1):
+                self._step(t)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                stage = self._stage[(t0 // self.host_chunk) % 2]
+                stage[:t1 - t0].copy_(self.ring[t0:t1, ..., :self.cp])            # strip the pad channels on the device
+                self.host_ring[t0:t1].copy_(stage[:t1 - t0], non_blocking=True)
+        main.wait_stream(side)
+
+    def run_to_host(self, state, forcing=None, chunk=5):
+        """Initial conditions from (pinned) host tensors in, whole forecast (steps,B,6,N,N,Cout) out in pinned host memory
+        owned by the engine.  Everything is enqueued on the current stream; synchronise before reading the result."""
+        if self.host_ring is None or self.host_chunk != chunk:
+            self.host_chunk = chunk
+            shape = (self.steps, self.batch, 6, self.n, self.n, self.cp)
+            self.host_ring = torch.empty(shape, dtype=self.dtype).pin_memory()
+            self._stage = [torch.empty((chunk,) + shape[1:], dtype=self.dtype, device=self.device) for _ in range(2)]
+            self._side = torch.cuda.Stream(device=self.device)
+            self.graph_host = None
+        self.load_inputs(state, forcing)
+        if not self.use_graph:
+            self._enqueue_all_to_host()
+            return self.host_ring
+        if self.graph_host is None:
+            self._ensure_graph()                      # warms tables / attributes
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue_all_to_host()
+            self.graph_host = g
+        self.graph_host.replay()
+        return self.host_ring

@@ -139,6 +139,12 @@ def test_tc_rollout_vs_oracle(lib):
     torch.cuda.synchronize()
     err = (out.double().cpu() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 3e-2, err
+    # the host-streaming variant (forecast chunks copied to pinned memory while later steps run) delivers the same bits
+    for chunk in (1, 2):
+        host = eng.run_to_host(state.pin_memory(), forcing.pin_memory(), chunk=chunk)
+        torch.cuda.synchronize()
+        assert not host.is_cuda and host.is_pinned()
+        assert torch.equal(host, out.cpu())
 
 
 BWD_TC_CASES = [
