@@ -354,8 +354,8 @@ def main():
                  'dtype': args.train_dtype, 'parallelism': 'dp%d, one flat all-reduce of %d float32 gradients per step'
                                                 % (world, trainer.flat.count),
                  'loss': float(loss.item()),
-                 'note': ('bf16 activations: forward and dgrad on the tcgen05 kernel, wgrad on CUDA cores with float32 '
-                          'accumulation (tensor-core wgrad is the next row); float32 master weights, fused Adam')
+                 'note': ('bf16 activations: forward, dgrad and wgrad on tcgen05 kernels (fp32 accumulation in tensor '
+                          'memory); float32 master weights, fused Adam')
                  if args.train_dtype == 'bf16' else 'float32 CUDA-core kernels (1e-5 parity path)'}
 
     cpu = None

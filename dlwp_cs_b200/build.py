@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libdlwpcs.so')
-SOURCES = ['cs_api.cu', 'cs_fp32.cu', 'cs_tc.cu']
+SOURCES = ['cs_api.cu', 'cs_fp32.cu', 'cs_tc.cu', 'cs_wgrad_tc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O3', '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
 # --use_fast_math only affects transcendental / division intrinsics; the kernels use fmaf and fminf only.

@@ -487,6 +487,7 @@ int dlwpcs_conv2d_dgrad(const dlwpcs_conv_desc *d, const void *dy, const void *y
 int64_t dlwpcs_wgrad_workspace_bytes(const dlwpcs_conv_desc *d) {
   Geometry g;
   if (check_bwd(d, &g)) return -1;
+  if (d->x_dtype == DLWPCS_BF16 && tc_wgrad_supported(d, g)) return tc_wgrad_workspace_bytes(d, g);
   return fp32_wgrad_workspace_bytes(d, g);
 }
 
@@ -500,6 +501,9 @@ int dlwpcs_conv2d_wgrad(const dlwpcs_conv_desc *d, const void *x0, const void *d
            "use_bias needs bias gradient buffers");
   CS_CHECK(d->act == DLWPCS_ACT_NONE || y, "activation derivative needs the forward output y");
   CS_CHECK(d->batch > 0, "wgrad needs a non-empty batch");
+  // bf16 activations: tcgen05 kernel (cs_wgrad_tc.cu); float32 (and shapes outside its reach): CUDA-core kernel
+  if (d->x_dtype == DLWPCS_BF16 && tc_wgrad_supported(d, g))
+    return tc_conv_wgrad(d, g, x0, dy, y, out, workspace, (cudaStream_t)stream);
   return fp32_conv_wgrad(d, g, x0, dy, y, out, workspace,
                          (cudaStream_t)stream);
 }

@@ -70,4 +70,13 @@ bool tc_supported(const dlwpcs_conv_desc *d, const Geometry &g, const char **why
 int tc_conv_dgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *dy, const void *y, const void *packed_t,
                   void *dx, void *workspace, cudaStream_t st);
 
+// patch table of a linearised virtual face (width Wv, G entries per face): physical source pixel or -1; cached per device
+const int32_t *get_patch_table(const Geometry &g, int Wv, int G, int n, int halo, int mode);
+
+// tensor-core wgrad (cs_wgrad_tc.cu)
+bool tc_wgrad_supported(const dlwpcs_conv_desc *d, const Geometry &g);
+int64_t tc_wgrad_workspace_bytes(const dlwpcs_conv_desc *d, const Geometry &g);
+int tc_conv_wgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *dy, const void *y,
+                  const dlwpcs_conv_wgrads *out, void *workspace, cudaStream_t st);
+
 }  // namespace dlwpcs

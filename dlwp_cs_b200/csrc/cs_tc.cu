@@ -31,6 +31,7 @@
 #include <mutex>
 #include <vector>
 #include "cs_common.cuh"
+#include "cs_ptx.cuh"
 
 namespace dlwpcs {
 
@@ -85,132 +86,6 @@ struct TcP {
   int knock;                    // bottleneck analysis (DLWPCS_TC_KNOCK): 1 no gathers, 2 no MMAs, 4 no epilogue math/stores, 8 no global stores
   TcPlan pl_;
 };
-
-// ---- PTX wrappers -------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-// arrive on the mbarrier once all cp.async issued so far by this thread have landed (no increment of the pending count)
-__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_dyn(int pending) {
-  switch (pending) {
-    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-  }
-}
-__device__ __forceinline__ void st_shared16(uint32_t dst, const uint4 &o) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
-}
-// TMA bulk store shared -> global (bypasses the L1 / LSU pipeline entirely) and its completion groups
-__device__ __forceinline__ void tma_bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "elect.sync _|P1, 0xFFFFFFFF;\n\t"
-      "selp.b32 %0, 1, 0, P1;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]: bf16 inputs, fp32 accumulation, M = 128; N and the operand majors come from idesc.
-// Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor), K-major without swizzle: low word = start address >> 4
-// | leading byte offset >> 4 (distance between the two 8-channel core matrices of a K = 16 step) << 16; high word =
-// stride byte offset >> 4 (distance between 8-row groups) | descriptor version 1 << 14.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float act_apply(float v, int act, float slope, float maxv) {
-  if (act == DLWPCS_ACT_CAPPED_LEAKY_RELU) v = v < 0.f ? slope * v : fminf(v, maxv);
-  return v;
-}
-__device__ __forceinline__ float act_grad_from_y(float y, int act, float slope, float maxv) {
-  if (act == DLWPCS_ACT_CAPPED_LEAKY_RELU) return y < 0.f ? slope : (y < maxv ? 1.f : 0.f);
-  return 1.f;
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t *>(&t);
-}
-__device__ __forceinline__ void unpack_bf16x8(const uint4 &v, float *f) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    f[2 * k] = __uint_as_float(w[k] << 16);
-    f[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
-  }
-}
 
 // debug timeline (DLWPCS_TC_TIMING=1): timestamps of the CTA in the middle of the grid at its DBG_K-th tile
 constexpr int DBG_K = 6;
@@ -880,25 +755,27 @@ struct TabKey {
 std::mutex g_tab_mu;
 std::map<TabKey, int32_t *> g_tabs;
 
-const int32_t *get_patch_table(const Geometry &g, const TcPlan &L, int n, int halo, int mode) {
+}  // namespace
+
+const int32_t *get_patch_table(const Geometry &g, int Wv, int G, int n, int halo, int mode) {
   TabKey key;
   memset(&key, 0, sizeof(key));
   if (cudaGetDevice(&key.dev) != cudaSuccess) {
     set_error("cudaGetDevice failed");
     return nullptr;
   }
-  key.n = n; key.halo = halo; key.Hin = g.Hin; key.Win = g.Win; key.Wv = L.Wv; key.G = L.G;
+  key.n = n; key.halo = halo; key.Hin = g.Hin; key.Win = g.Win; key.Wv = Wv; key.G = G;
   key.pt0 = g.pt[0]; key.pt1 = g.pt[1]; key.pt2 = g.pt[2]; key.pl = g.pl; key.mode = mode;
   std::lock_guard<std::mutex> lk(g_tab_mu);
   auto it = g_tabs.find(key);
   if (it != g_tabs.end()) return it->second;
   std::vector<int32_t> lut;
   if (halo > 0) build_pad_lut(n, halo, lut);
-  std::vector<int32_t> tab((size_t)6 * L.G);
+  std::vector<int32_t> tab((size_t)6 * G);
   for (int f = 0; f < 6; ++f) {
     const int pt = g.pt[face_group_host(f)];
-    for (int q = 0; q < L.G; ++q) {
-      const int rv = q / L.Wv, cv = q % L.Wv, r = rv - pt, c = cv - g.pl;
+    for (int q = 0; q < G; ++q) {
+      const int rv = q / Wv, cv = q % Wv, r = rv - pt, c = cv - g.pl;
       int32_t val = -1;
       if (r >= 0 && r < g.Hin && c >= 0 && c < g.Win) {
         const int s = halo > 0 ? lut[((size_t)f * g.Hin + r) * g.Win + c] : (f * g.Hin + r) * g.Win + c;
@@ -907,7 +784,7 @@ const int32_t *get_patch_table(const Geometry &g, const TcPlan &L, int n, int ha
         else if (mode == DLWPCS_SRC_UP2) val = (sf * (n / 2) + si / 2) * (n / 2) + sj / 2;
         else val = (sf * 2 * n + 2 * si) * 2 * n + 2 * sj;
       }
-      tab[(size_t)f * L.G + q] = val;
+      tab[(size_t)f * G + q] = val;
     }
   }
   int32_t *dev = nullptr;
@@ -921,6 +798,8 @@ const int32_t *get_patch_table(const Geometry &g, const TcPlan &L, int n, int ha
   g_tabs[key] = dev;
   return dev;
 }
+
+namespace {
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -1031,11 +910,11 @@ int tc_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, co
   TcPlan &L = P.pl_;
   P.x0 = (const __nv_bfloat16 *)x0;
   P.x1 = (const __nv_bfloat16 *)x1;
-  P.tab0 = get_patch_table(g, L, d->n, d->halo, d->mode0);
+  P.tab0 = get_patch_table(g, L.Wv, L.G, d->n, d->halo, d->mode0);
   if (!P.tab0) return 3;
   P.tab1 = P.tab0;
   if (d->c1 > 0) {
-    P.tab1 = get_patch_table(g, L, d->n, d->halo, d->mode1);
+    P.tab1 = get_patch_table(g, L.Wv, L.G, d->n, d->halo, d->mode1);
     if (!P.tab1) return 3;
   }
   auto ppb = [&](int mode) {
@@ -1080,7 +959,7 @@ int tc_conv_dgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *dy, 
   TcPlan &L = P.pl_;
   P.x0 = (const __nv_bfloat16 *)dy;
   P.x1 = nullptr;
-  P.tab0 = get_patch_table(gg, L, g.Hout, 0, DLWPCS_SRC_SAME);
+  P.tab0 = get_patch_table(gg, L.Wv, L.G, g.Hout, 0, DLWPCS_SRC_SAME);
   if (!P.tab0) return 3;
   P.tab1 = P.tab0;
   P.ppb0 = P.ppb1 = 6 * g.Hout * g.Wout;

@@ -155,6 +155,15 @@ BWD_TC_CASES = [
     dict(n=16, cin=32, cout=16, k=1, halo=0, act=False),
     dict(n=9, cin=16, cout=8, k=3, halo=0, act=True, same=True),
     dict(n=48, cin=24, cout=32, k=3, halo=1, act=True, batch=1),
+    # shapes that exercise the tcgen05 wgrad's job splits: two 64-channel input blocks, two output-channel groups,
+    # channel counts that are not multiples of 8 (element-wise loads), the 1x1 head, a 5x5 window, 3 images
+    dict(n=24, cin=128, cout=64, k=3, halo=1, act=True),
+    dict(n=12, cin=64, cout=128, k=3, halo=1, act=True),
+    dict(n=24, cin=64, cout=64, k=3, halo=1, act=True, batch=3),
+    dict(n=16, cin=18, cout=32, k=3, halo=1, act=True),
+    dict(n=16, cin=32, cout=14, k=1, halo=0, act=False),
+    dict(n=12, cin=16, cout=16, k=5, halo=2, act=True),
+    dict(n=48, cin=32, cout=32, k=3, halo=1, act=True, batch=3),
 ]
 
 
