@@ -226,14 +226,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t misc = wring + (uint32_t)L.NST * L.stageBytes;
   const uint32_t bar_wfull = misc, bar_wempty = misc + 64, bar_pfull = misc + 128, bar_pempty = misc + 160,
                  bar_afull = misc + 192, bar_aempty = misc + 208, tmem_slot = misc + 224;
-  uint2 *s_unit = reinterpret_cast<uint2 *>(gen + (misc - base) + 512);
   float *s_bias = reinterpret_cast<float *>(gen + (misc - base) + 512 + MAX_UNITS * 8);
   const uint32_t tabring = misc + 512 + MAX_UNITS * 8 + (uint32_t)(3 * L.CoutP * 4);          // TS slots of tabBytes
   const int32_t *s_tab = reinterpret_cast<const int32_t *>(gen + (tabring - base));
   const uint32_t bar_tfull = misc + 256, bar_tempty = misc + 288;
   const uint32_t stg0 = (tabring + (uint32_t)(L.TS * L.tabBytes) + 127u) & ~127u;      // 8 warps x stgBufs x stgBytes
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index broadcast from lane 0 (cutlass::canonical_warp_idx_sync): the role branches become provably warp-uniform,
+  // which lets the compiler keep the MMA descriptors in uniform registers
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int ntiles = 6 * P.batch * L.tpf;
 
   if (tid == 0) {
@@ -256,15 +257,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     fence_mbar_init();
   }
   for (int i = tid; i < 3 * L.CoutP; i += TC_THREADS) s_bias[i] = P.bias[i];
-  // per (chunk, tap) unit: A descriptor offset (>>4) inside a patch stage; B ring offset (>>4) | wait / release flags
-  for (int un = tid; un < L.NU; un += TC_THREADS) {
-    const int kc = un / L.taps, tap = un - kc * L.taps, u = tap / P.kw, v = tap - u * P.kw;
-    const int uis = un % L.UPS, sidx = un / L.UPS;
-    const uint32_t a_off = ((uint32_t)kc * L.blockBytes + (uint32_t)(u * P.dh * L.Wv + v * P.dw) * L.RB) >> 4;
-    const uint32_t b_off = ((uint32_t)uis * L.unitBytes) >> 4;
-    const uint32_t flags = (uis == 0 ? 1u : 0u) | ((uis == L.UPS - 1 || un == L.NU - 1) ? 2u : 0u);
-    s_unit[un] = make_uint2(a_off, b_off | (flags << 28) | ((uint32_t)sidx << 20));
-  }
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, (uint32_t)L.tmemCols);
   tc_fence_before();
   __syncthreads();
@@ -317,7 +309,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const uint64_t b_fix = ((uint64_t)((128u >> 4) | (1u << 14)) << 32) | ((uint64_t)((uint32_t)L.CoutP & 0x3FFFu) << 16);
     const uint32_t a_jstep = 32u >> 4, b_jstep = (uint32_t)(2 * L.CoutP * 16) >> 4;     // one K = 16 step
     const uint32_t a_mbstep = (uint32_t)(128 * L.RB) >> 4;
-    const uint32_t stage16 = (uint32_t)L.stageBytes >> 4, coutp = (uint32_t)L.CoutP;
+    const uint32_t stage16 = (uint32_t)L.stageBytes >> 4, coutp = (uint32_t)L.CoutP, unit16 = (uint32_t)L.unitBytes >> 4;
+    const int kh = L.taps / P.kw;
+    const uint32_t blk16 = (uint32_t)L.blockBytes >> 4, urow16 = ((uint32_t)(P.dh * L.Wv) * L.RB) >> 4,
+                   vcol16 = ((uint32_t)P.dw * L.RB) >> 4;
     int st = 0, ph = 0, sp = 0, pp = 0, sa = 0, pa = 0, prev_grp = -1, k = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
       const TileInfo T = decode_tile(tile, P.batch, L.tpf);
@@ -335,40 +330,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint64_t a_stage = a_fix | ((patch0 + (uint32_t)sp * L.patchBytes) >> 4);
       const uint64_t b_ring = b_fix | (wring >> 4);
       const uint32_t d_stage = tmem_base + (uint32_t)(sa * L.MB) * coutp;
-      for (int unit = 0; unit < L.NU; ++unit) {
-        const uint2 e = s_unit[unit];
-        const uint32_t flags = e.y >> 28;
-        const int stage = load_ev ? st : (int)((e.y >> 20) & 0xFFu);
-        if (load_ev && (flags & 1u)) {
-          mbar_wait(bar_wfull + 8 * st, ph);
-          tc_fence_after();
-        }
-        const uint64_t a_unit = a_stage + e.x;
-        const uint64_t b_unit = b_ring + ((uint32_t)stage * stage16 + (e.y & 0xFFFFFu));
-        if (!(P.knock & 2) && elect_one()) {
-#pragma unroll
-          for (int mi = 0; mi < (MBT + NUM_MMA_WARPS - 1) / NUM_MMA_WARPS; ++mi) {
-            const int mb = mw + NUM_MMA_WARPS * mi;
-            if (mb < MBc) {
-#pragma unroll
-              for (int j = 0; j < KC16T; ++j)
-                umma_bf16(d_stage + (uint32_t)mb * coutp, a_unit + (uint32_t)mb * a_mbstep + (uint32_t)j * a_jstep,
-                          b_unit + (uint32_t)j * b_jstep, idesc, (unit > 0 || j > 0) ? 1u : 0u);
+      // whole-warp loops over (K chunk, kernel row, kernel column); one elected lane per instruction (umma_*_elect)
+      int uis = 0, sidx = 0, unit = 0;
+      uint32_t a_kc = 0;
+#pragma unroll 1
+      for (int kc = 0; kc < L.nch; ++kc, a_kc += blk16) {
+        uint32_t a_u = a_kc;
+#pragma unroll 1
+        for (int u = 0; u < kh; ++u, a_u += urow16) {
+          uint32_t a_off = a_u;
+#pragma unroll 1
+          for (int v = 0; v < P.kw; ++v, a_off += vcol16) {
+            const int stage = load_ev ? st : sidx;
+            if (load_ev && uis == 0) {
+              mbar_wait(bar_wfull + 8 * st, ph);
+              tc_fence_after();
             }
+            const uint64_t a_unit = a_stage + a_off;
+            const uint64_t b_unit = b_ring + ((uint32_t)stage * stage16 + (uint32_t)uis * unit16);
+            if (!(P.knock & 2)) {
+#pragma unroll
+              for (int mi = 0; mi < (MBT + NUM_MMA_WARPS - 1) / NUM_MMA_WARPS; ++mi) {
+                const int mb = mw + NUM_MMA_WARPS * mi;
+                if (mb < MBc) {
+#pragma unroll
+                  for (int j = 0; j < KC16T; ++j)
+                    umma_bf16_elect(d_stage + (uint32_t)mb * coutp, a_unit + (uint32_t)mb * a_mbstep + (uint32_t)j * a_jstep,
+                                    b_unit + (uint32_t)j * b_jstep, idesc, (unit > 0 || j > 0) ? 1u : 0u);
+                }
+              }
+            }
+            if (uis == L.UPS - 1 || unit == L.NU - 1) {
+              if (release_w) umma_commit_elect(bar_wempty + 8 * stage);
+              if (load_ev && ++st == L.NST) { st = 0; ph ^= 1; }
+            }
+            ++unit;
+            if (++uis == L.UPS) { uis = 0; ++sidx; }
           }
         }
-        __syncwarp();
-        if (flags & 2u) {
-          if (release_w && elect_one()) umma_commit(bar_wempty + 8 * stage);
-          __syncwarp();
-          if (load_ev && ++st == L.NST) { st = 0; ph ^= 1; }
-        }
       }
-      if (elect_one()) {
-        umma_commit(bar_pempty + 8 * sp);     // patch stage may be refilled once these MMAs have read it
-        umma_commit(bar_afull + 8 * sa);      // accumulators complete
-      }
-      __syncwarp();
+      umma_commit_elect(bar_pempty + 8 * sp);     // patch stage may be refilled once these MMAs have read it
+      umma_commit_elect(bar_afull + 8 * sa);      // accumulators complete
       stamp(P, 7, k, lane == 0 && mw == 0);
       if (++sp == L.PS) { sp = 0; pp ^= 1; }
       if (++sa == L.AS) { sa = 0; pa ^= 1; }

@@ -97,10 +97,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const uint32_t stage0 = base;
   const uint32_t misc = stage0 + (uint32_t)L.PS * L.stageBytes;
   const uint32_t bar_full = misc, bar_empty = misc + 32, bar_done = misc + 64, tmem_slot = misc + 72;
-  uint4 *s_unit = reinterpret_cast<uint4 *>(gen + (misc - base) + 128);
   float *s_bsum = reinterpret_cast<float *>(gen + (misc - base) + 128 + WG_MAX_UNITS * 16);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index broadcast from lane 0: tells the compiler the role branches are warp-uniform (uniform datapath usable)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
 
   // ---- which job / face group / tiles this CTA owns
   const int job = blockIdx.x / L.nc, ic = blockIdx.x - job * L.nc;
@@ -119,13 +119,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     mbar_init(bar_done, 1);
     fence_mbar_init();
   }
-  // MMA units (kernel row u, M block, dy channel block): A / B descriptor offsets (>> 4) and the accumulator column
-  for (int un = tid; un < L.NU; un += WG_THREADS) {
-    const int nbj = un % L.NBJ, r = un / L.NBJ, mbu = r % L.MBu, u = r / L.MBu;
-    const uint32_t a_off = ((uint32_t)(u * L.dh * L.Wv + mbu * L.SPB) * L.RBx) >> 4;
-    const uint32_t b_off = ((uint32_t)nbj * L.yBlockBytes) >> 4;
-    s_unit[un] = make_uint4(a_off, b_off, (uint32_t)((u * L.MBu + mbu) * L.NJ + nbj * L.NBlk), 0u);
-  }
   if (warp == WG_MMA_WARP) tmem_alloc(tmem_slot, (uint32_t)L.tmemCols);
   tc_fence_before();
   __syncthreads();
@@ -141,27 +134,34 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const uint32_t a_lbo = ((uint32_t)L.RBx >> 4) << 16, b_lbo = 1u << 16;
     const uint32_t a_kstep = ((uint32_t)(16 * L.RBx)) >> 4, b_kstep = ((uint32_t)(16 * L.RBy)) >> 4;
     const int ksteps = L.TP / 16;
+    const uint32_t a_ustep = ((uint32_t)(L.dh * L.Wv) * L.RBx) >> 4, a_mstep = ((uint32_t)L.SPB * L.RBx) >> 4;
+    const uint32_t b_nstep = (uint32_t)L.yBlockBytes >> 4;
     int s = 0, ph = 0;
     for (int k = 0; k < my_tiles; ++k) {
       mbar_wait(bar_full + 8 * s, ph);
       tc_fence_after();
       const uint32_t st_addr = stage0 + (uint32_t)s * L.stageBytes;
       const uint32_t a_stage = a_lbo | (st_addr >> 4), b_stage = b_lbo | ((st_addr + (uint32_t)L.xBytes) >> 4);
-      if (elect_one()) {
+      // whole-warp loops, one elected lane per instruction: every descriptor stays in uniform registers
 #pragma unroll 1
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t a_ks = a_stage + (uint32_t)ks * a_kstep, b_ks = b_stage + (uint32_t)ks * b_kstep;
-          const uint32_t acc = (k > 0 || ks > 0) ? 1u : 0u;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t a_ks = a_stage + (uint32_t)ks * a_kstep, b_ks = b_stage + (uint32_t)ks * b_kstep;
+        const uint32_t acc = (k > 0 || ks > 0) ? 1u : 0u;
+        uint32_t a_u = a_ks, dcol = tmem_base;
 #pragma unroll 1
-          for (int un = 0; un < L.NU; ++un) {
-            const uint4 e = s_unit[un];
-            umma_bf16(tmem_base + e.z, a_hi | (uint64_t)(a_ks + e.x), b_hi | (uint64_t)(b_ks + e.y), idesc, acc);
+        for (int u = 0; u < L.kh; ++u, a_u += a_ustep) {
+          uint32_t a_m = a_u;
+#pragma unroll 1
+          for (int mbu = 0; mbu < L.MBu; ++mbu, a_m += a_mstep) {
+            uint32_t b_n = b_ks;
+#pragma unroll 1
+            for (int nbj = 0; nbj < L.NBJ; ++nbj, b_n += b_nstep, dcol += (uint32_t)L.NBlk)
+              umma_bf16_elect(dcol, a_hi | (uint64_t)a_m, b_hi | (uint64_t)b_n, idesc, acc);
           }
         }
-        umma_commit(bar_empty + 8 * s);          // the stage may be refilled once these MMAs have read it
-        if (k == my_tiles - 1) umma_commit(bar_done);
       }
-      __syncwarp();
+      umma_commit_elect(bar_empty + 8 * s);        // the stage may be refilled once these MMAs have read it
+      if (k == my_tiles - 1) umma_commit_elect(bar_done);
       if (++s == L.PS) { s = 0; ph ^= 1; }
     }
   } else {
