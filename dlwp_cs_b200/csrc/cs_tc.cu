@@ -256,13 +256,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     fence_mbar_init();
   }
-  for (int i = tid; i < 3 * L.CoutP; i += TC_THREADS) s_bias[i] = P.bias[i];
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, (uint32_t)L.tmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(gen + (tmem_slot - base));
   stamp(P, 0, 0, tid == 0);
+  // programmatic dependent launch: the next kernel of the stream may start its prologue (barriers, tensor-memory
+  // allocation, patch-table TMA) on every SM this grid has left.  Whatever may have been written by the previous kernel
+  // -- activations (loaders), packed weights (TMA lane 0), bias (epilogue) -- is read behind griddepcontrol.wait; the
+  // patch tables are library-owned and static; every global store is data-dependent on such a read
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == TMA_WARP) {
     // ===== producers (one thread each): lane 0 streams weights through the ring with TMA bulk copies, skipped while the
@@ -270,6 +274,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // the loaders' lookups do not queue behind their own DRAM gathers in the L1 pipeline =====
     if (lane == 0) {
       int st = 0, ph = 0, prev_grp = -1;
+      asm volatile("griddepcontrol.wait;" ::: "memory");      // the packed weights may come from the previous kernel
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int grp = decode_tile(tile, P.batch, L.tpf).grp;
         if (L.resident && grp == prev_grp) continue;
@@ -392,6 +397,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int cprLog = (cpr & (cpr - 1)) == 0 ? 31 - __clz(cpr) : -1;          // rows of 2^k chunks: shifts instead of divisions
     const uint32_t smask = (cpr & (cpr - 1)) == 0 ? min(cpr, 8u) - 1u : 0u;    // XOR swizzle of the chunk index by row
     int sa = 0, pa = 0, k = 0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");        // the bias sits behind the packed weights
+    for (int i = tid - EPI_WARP0 * 32; i < 3 * L.CoutP; i += TC_EPI) s_bias[i] = P.bias[i];
+    asm volatile("bar.sync 2, %0;" ::"n"(TC_EPI) : "memory");
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
       const TileInfo T = decode_tile(tile, P.batch, L.tpf);
       const int MBc = min(L.MB, L.nmb - T.tf * L.MB);
@@ -497,6 +505,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int lt = tid - LOAD_WARP0 * 32;
     int si = 0, pi = 0, k = 0, ts = 0, tp = 0;
     const int w2_0 = P.n * 2;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
       const TileInfo T = decode_tile(tile, P.batch, L.tpf);
       const int MBc = min(L.MB, L.nmb - T.tf * L.MB);
@@ -844,8 +853,19 @@ int launch_tc(TcP &P, cudaStream_t st) {
     CS_CUDA(cudaMemset(dbg, 0, 16 * sizeof(long long)));
     P.dbg = dbg;
   }
-  kern<<<grid, TC_THREADS, L.smemBytes, st>>>(P);
-  CS_CUDA(cudaGetLastError());
+  static const int pdl = env_int("DLWPCS_TC_PDL", 1);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = (size_t)L.smemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  CS_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
   if (timing) {
     long long h[16];
     CS_CUDA(cudaDeviceSynchronize());
