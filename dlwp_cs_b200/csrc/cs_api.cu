@@ -214,6 +214,42 @@ __global__ void pad_bwd_kernel(const T *__restrict__ dy, T *__restrict__ dx, con
   }
 }
 
+// 16-byte version (channel count a multiple of 8 bf16 / 4 fp32): one thread sums one 16-byte chunk of a source pixel over
+// the padded positions that read it (1 interior, 2 edge, 3-5 corner: SURVEY.md appendix A), in the table's fixed order
+template <typename T>
+__global__ void pad_bwd_vec_kernel(const uint4 *__restrict__ dy, uint4 *__restrict__ dx,
+                                   const int32_t *__restrict__ inv_start, const int32_t *__restrict__ inv_items, int npad,
+                                   int nsrc, int vpp, long long total) {
+  constexpr int E = 16 / sizeof(T);
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int v = (int)(i % vpp);
+    const long long s = i / vpp;
+    const int sp = (int)(s % nsrc);
+    const long long b = s / nsrc;
+    const int k0 = __ldg(inv_start + sp), k1 = __ldg(inv_start + sp + 1);
+    if (k1 - k0 == 1) {                     // interior pixel: plain copy
+      dx[i] = __ldg(dy + (b * npad + __ldg(inv_items + k0)) * vpp + v);
+      continue;
+    }
+    float acc[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = 0.f;
+    for (int k = k0; k < k1; ++k) {
+      const uint4 q = __ldg(dy + (b * npad + __ldg(inv_items + k)) * vpp + v);
+      const T *t = reinterpret_cast<const T *>(&q);
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[e] += to_f<T>(t[e]);
+    }
+    uint4 o;
+    T *t = reinterpret_cast<T *>(&o);
+#pragma unroll
+    for (int e = 0; e < E; ++e) t[e] = from_f<T>(acc[e]);
+    dx[i] = o;
+  }
+}
+
 __device__ __forceinline__ float act_apply(float v, int act, float slope, float maxv) {
   if (act == DLWPCS_ACT_CAPPED_LEAKY_RELU) v = v < 0.f ? slope * v : fminf(v, maxv);
   return v;
@@ -347,6 +383,19 @@ int dlwpcs_pad_bwd(const void *dy, void *dx, int batch, int n, int c, int p, int
   cudaStream_t st = (cudaStream_t)stream;
   const int H = n + 2 * p, npad = 6 * H * H, nsrc = 6 * n * n;
   const long long total = (long long)batch * nsrc * c;
+  const int epv = 16 / (int)elem_size(dtype);       // elements per 16-byte chunk
+  if (c % epv == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
+    const int vpp = c / epv;
+    const long long tv = total / epv;
+    if (dtype == DLWPCS_F32)
+      pad_bwd_vec_kernel<float><<<grid_for(tv, 256), 256, 0, st>>>((const uint4 *)dy, (uint4 *)dx, t->inv_start,
+                                                                     t->inv_items, npad, nsrc, vpp, tv);
+    else
+      pad_bwd_vec_kernel<__nv_bfloat16><<<grid_for(tv, 256), 256, 0, st>>>((const uint4 *)dy, (uint4 *)dx, t->inv_start,
+                                                                             t->inv_items, npad, nsrc, vpp, tv);
+    CS_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (dtype == DLWPCS_F32)
     pad_bwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float *)dy, (float *)dx, t->inv_start,
                                                                   t->inv_items, npad, nsrc, c, total);

@@ -335,45 +335,92 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint64_t a_stage = a_fix | ((patch0 + (uint32_t)sp * L.patchBytes) >> 4);
       const uint64_t b_ring = b_fix | (wring >> 4);
       const uint32_t d_stage = tmem_base + (uint32_t)(sa * L.MB) * coutp;
-      // whole-warp loops over (K chunk, kernel row, kernel column); one elected lane per instruction (umma_*_elect)
-      int uis = 0, sidx = 0, unit = 0;
-      uint32_t a_kc = 0;
-#pragma unroll 1
-      for (int kc = 0; kc < L.nch; ++kc, a_kc += blk16) {
-        uint32_t a_u = a_kc;
-#pragma unroll 1
-        for (int u = 0; u < kh; ++u, a_u += urow16) {
-          uint32_t a_off = a_u;
-#pragma unroll 1
-          for (int v = 0; v < P.kw; ++v, a_off += vcol16) {
+      // whole-warp loops over (K chunk, kernel row, kernel column); one elected lane per instruction (umma_*_elect).
+      // The loop bodies are unrolled over the window (the uniform-datapath address chains of one iteration are long:
+      // tools/umma_mn_rate.cu measures ~110 cycles of loop overhead per un-unrolled iteration next to ~40 per MMA).
+#define TC_ISSUE_UNIT(A_OFF, B_UNIT, FIRST)                                                                              \
+  do {                                                                                                                   \
+    const uint64_t a_unit_ = a_stage + (A_OFF);                                                                          \
+    _Pragma("unroll") for (int mi = 0; mi < (MBT + NUM_MMA_WARPS - 1) / NUM_MMA_WARPS; ++mi) {                            \
+      const int mb = mw + NUM_MMA_WARPS * mi;                                                                            \
+      if (mb < MBc) {                                                                                                    \
+        _Pragma("unroll") for (int j = 0; j < KC16T; ++j)                                                                \
+            umma_bf16_elect(d_stage + (uint32_t)mb * coutp, a_unit_ + (uint32_t)mb * a_mbstep + (uint32_t)j * a_jstep,   \
+                            (B_UNIT) + (uint32_t)j * b_jstep, idesc, (!(FIRST) || j > 0) ? 1u : 0u);                     \
+      }                                                                                                                  \
+    }                                                                                                                    \
+  } while (0)
+      const bool win3 = kh == 3 && P.kw == 3;
+      if (P.knock & 2) {
+        // bottleneck analysis: no MMAs; the weight ring is still cycled below through the generic path's bookkeeping
+        if (load_ev || release_w) {
+          int uis = 0, sidx = 0;
+          for (int unit = 0; unit < L.NU; ++unit) {
             const int stage = load_ev ? st : sidx;
-            if (load_ev && uis == 0) {
-              mbar_wait(bar_wfull + 8 * st, ph);
-              tc_fence_after();
-            }
-            const uint64_t a_unit = a_stage + a_off;
-            const uint64_t b_unit = b_ring + ((uint32_t)stage * stage16 + (uint32_t)uis * unit16);
-            if (!(P.knock & 2)) {
-#pragma unroll
-              for (int mi = 0; mi < (MBT + NUM_MMA_WARPS - 1) / NUM_MMA_WARPS; ++mi) {
-                const int mb = mw + NUM_MMA_WARPS * mi;
-                if (mb < MBc) {
-#pragma unroll
-                  for (int j = 0; j < KC16T; ++j)
-                    umma_bf16_elect(d_stage + (uint32_t)mb * coutp, a_unit + (uint32_t)mb * a_mbstep + (uint32_t)j * a_jstep,
-                                    b_unit + (uint32_t)j * b_jstep, idesc, (unit > 0 || j > 0) ? 1u : 0u);
-                }
-              }
-            }
+            if (load_ev && uis == 0) { mbar_wait(bar_wfull + 8 * st, ph); tc_fence_after(); }
             if (uis == L.UPS - 1 || unit == L.NU - 1) {
               if (release_w) umma_commit_elect(bar_wempty + 8 * stage);
               if (load_ev && ++st == L.NST) { st = 0; ph ^= 1; }
             }
-            ++unit;
             if (++uis == L.UPS) { uis = 0; ++sidx; }
           }
         }
+      } else if (L.resident && !load_ev && !release_w) {
+        // steady state of a resident weight set: units are contiguous in the ring, nothing to wait for or release
+        uint64_t b_unit = b_ring;
+        uint32_t a_kc = 0;
+        if (win3) {
+#pragma unroll 1
+          for (int kc = 0; kc < L.nch; ++kc, a_kc += blk16) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              TC_ISSUE_UNIT(a_kc + (uint32_t)(t / 3) * urow16 + (uint32_t)(t % 3) * vcol16, b_unit + (uint32_t)t * unit16,
+                            kc == 0 && t == 0);
+            }
+            b_unit += 9u * unit16;
+          }
+        } else {
+          int unit = 0;
+#pragma unroll 1
+          for (int kc = 0; kc < L.nch; ++kc, a_kc += blk16) {
+            uint32_t a_u = a_kc;
+#pragma unroll 1
+            for (int u = 0; u < kh; ++u, a_u += urow16) {
+              uint32_t a_off = a_u;
+#pragma unroll 1
+              for (int v = 0; v < P.kw; ++v, a_off += vcol16, ++unit, b_unit += unit16) TC_ISSUE_UNIT(a_off, b_unit, unit == 0);
+            }
+          }
+        }
+      } else {
+        int uis = 0, sidx = 0, unit = 0;
+        uint32_t a_kc = 0;
+#pragma unroll 1
+        for (int kc = 0; kc < L.nch; ++kc, a_kc += blk16) {
+          uint32_t a_u = a_kc;
+#pragma unroll 1
+          for (int u = 0; u < kh; ++u, a_u += urow16) {
+            uint32_t a_off = a_u;
+#pragma unroll 1
+            for (int v = 0; v < P.kw; ++v, a_off += vcol16) {
+              const int stage = load_ev ? st : sidx;
+              if (load_ev && uis == 0) {
+                mbar_wait(bar_wfull + 8 * st, ph);
+                tc_fence_after();
+              }
+              const uint64_t b_unit = b_ring + ((uint32_t)stage * stage16 + (uint32_t)uis * unit16);
+              TC_ISSUE_UNIT(a_off, b_unit, unit == 0);
+              if (uis == L.UPS - 1 || unit == L.NU - 1) {
+                if (release_w) umma_commit_elect(bar_wempty + 8 * stage);
+                if (load_ev && ++st == L.NST) { st = 0; ph ^= 1; }
+              }
+              ++unit;
+              if (++uis == L.UPS) { uis = 0; ++sidx; }
+            }
+          }
+        }
       }
+#undef TC_ISSUE_UNIT
       umma_commit_elect(bar_pempty + 8 * sp);     // patch stage may be refilled once these MMAs have read it
       umma_commit_elect(bar_afull + 8 * sa);      // accumulators complete
       stamp(P, 7, k, lane == 0 && mw == 0);

@@ -36,13 +36,15 @@ namespace dlwpcs {
 
 namespace {
 
-constexpr int WG_THREADS = 288;
-constexpr int WG_LOADERS = 256;
-constexpr int WG_MMA_WARP = 8;
+constexpr int WG_THREADS = 320;      // warps 0-3 x loaders, 4-7 dy loaders, 8 MMA issuer, 9 patch-table TMA producer
+constexpr int WG_XL = 128, WG_YL = 128;
+constexpr int WG_LOADERS = WG_XL + WG_YL;
+constexpr int WG_MMA_WARP = 8, WG_TAB_WARP = 9;
 constexpr int WG_MAX_UNITS = 32;
 constexpr int WG_MAX_PS = 4;
+constexpr int WG_TS = 3;             // patch-table ring slots
 constexpr int WG_SMEM_CAP = 227 * 1024;
-constexpr int WG_MISC = 128 + WG_MAX_UNITS * 16 + WG_LOADERS * 8 * 4;     // barriers, unit table, bias partials
+constexpr int WG_MISC = 256 + WG_YL * 8 * 4;     // barriers + tensor-memory slot, bias partials
 
 struct WgPlan {
   int CinP, CoutP;
@@ -64,9 +66,10 @@ struct WgPlan {
 struct WgP {
   const __nv_bfloat16 *x, *dy, *mask_y;
   const int32_t *tabx;        // [6][G] patch position -> source pixel of one batch element or -1
-  const int32_t *ytab;        // [tpf*TP] linear position -> output pixel r*Wo + c of one face or -1
   float *ws, *ws_b;           // [ncta][nacc][128][NJ], [ncta][NJ]
   int batch, ppbx, ppfy;      // x pixels per batch element, dy pixels per face
+  int Ho, Wo;
+  int knock;                  // bottleneck analysis (DLWPCS_WG_KNOCK): 1 no x gathers, 2 no dy loads, 4 no MMAs, 8 no dump
   int cin, cout;
   int act;
   float slope, maxv;
@@ -89,6 +92,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// KH / MBU / NBJ: compile-time copies of the plan's kh / MBu / NBJ (0 = read them at run time) so that the MMA issue
+// loops unroll -- an un-unrolled iteration costs ~110 cycles of uniform-datapath latency (tools/umma_mn_rate.cu)
+template <int KH, int MBU, int NBJT>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgP P) {
   extern __shared__ uint8_t smem_raw[];
   const WgPlan &L = P.pl;
@@ -96,8 +102,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t stage0 = base;
   const uint32_t misc = stage0 + (uint32_t)L.PS * L.stageBytes;
-  const uint32_t bar_full = misc, bar_empty = misc + 32, bar_done = misc + 64, tmem_slot = misc + 72;
-  float *s_bsum = reinterpret_cast<float *>(gen + (misc - base) + 128 + WG_MAX_UNITS * 16);
+  const uint32_t bar_full = misc, bar_empty = misc + 32, bar_done = misc + 64, tmem_slot = misc + 72,
+                 bar_tfull = misc + 96, bar_tempty = misc + 128;
+  float *s_bsum = reinterpret_cast<float *>(gen + (misc - base) + 256);
+  const uint32_t tabring = misc + WG_MISC;                                  // WG_TS slots of NPX int32
+  const int32_t *s_tab = reinterpret_cast<const int32_t *>(gen + (tabring - base));
 
   // warp index broadcast from lane 0: tells the compiler the role branches are warp-uniform (uniform datapath usable)
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -110,11 +119,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   else if (ic >= L.ng[0]) { grp = 1; idx = ic - L.ng[0]; nin = L.ng[1]; }
   const int T = (grp == 0 ? 4 : 1) * P.batch * L.tpf;
   const int my_tiles = idx < T ? (T - idx + nin - 1) / nin : 0;
+  // tile k of this CTA -> (batch element, face, tile of the face)
+  auto decode = [&](int k, int &b, int &f, int &tf) {
+    const int t = idx + k * nin;
+    if (grp == 0) { const int bf = t / L.tpf; tf = t - bf * L.tpf; b = bf >> 2; f = bf & 3; }
+    else { b = t / L.tpf; tf = t - b * L.tpf; f = 3 + grp; }
+  };
 
   if (tid == 0) {
     for (int i = 0; i < L.PS; ++i) {
       mbar_init(bar_full + 8 * i, WG_LOADERS);
       mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < WG_TS; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, WG_XL);
     }
     mbar_init(bar_done, 1);
     fence_mbar_init();
@@ -125,7 +144,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(gen + (tmem_slot - base));
 
-  if (warp == WG_MMA_WARP) {
+  if (warp == WG_TAB_WARP) {
+    // ===== patch-table producer: the slice of every tile's halo table goes to shared memory ahead of the x loaders, so
+    // that their lookups do not queue behind their own gathers =====
+    if (lane == 0) {
+      int ts = 0, tp = 0;
+      for (int k = 0; k < my_tiles; ++k) {
+        int b, f, tf;
+        decode(k, b, f, tf);
+        mbar_wait(bar_tempty + 8 * ts, tp ^ 1);
+        mbar_expect_tx(bar_tfull + 8 * ts, (uint32_t)L.NPX * 4u);
+        tma_bulk_g2s(tabring + (uint32_t)ts * L.NPX * 4u, P.tabx + (size_t)f * L.G + (size_t)tf * L.TP, (uint32_t)L.NPX * 4u,
+                     bar_tfull + 8 * ts);
+        if (++ts == WG_TS) { ts = 0; tp ^= 1; }
+      }
+    }
+  } else if (warp == WG_MMA_WARP) {
     // ===== MMA issuer =====
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(L.NBlk >> 3) << 17) |
                            (8u << 24);
@@ -143,20 +177,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       const uint32_t st_addr = stage0 + (uint32_t)s * L.stageBytes;
       const uint32_t a_stage = a_lbo | (st_addr >> 4), b_stage = b_lbo | ((st_addr + (uint32_t)L.xBytes) >> 4);
       // whole-warp loops, one elected lane per instruction: every descriptor stays in uniform registers
-#pragma unroll 1
-      for (int ks = 0; ks < ksteps; ++ks) {
+      const int khc = KH ? KH : L.kh, mbuc = MBU ? MBU : L.MBu, nbjc = NBJT ? NBJT : L.NBJ;
+#pragma unroll 2
+      for (int ks = 0; ks < ((P.knock & 4) ? 0 : ksteps); ++ks) {
         const uint32_t a_ks = a_stage + (uint32_t)ks * a_kstep, b_ks = b_stage + (uint32_t)ks * b_kstep;
         const uint32_t acc = (k > 0 || ks > 0) ? 1u : 0u;
-        uint32_t a_u = a_ks, dcol = tmem_base;
-#pragma unroll 1
-        for (int u = 0; u < L.kh; ++u, a_u += a_ustep) {
-          uint32_t a_m = a_u;
-#pragma unroll 1
-          for (int mbu = 0; mbu < L.MBu; ++mbu, a_m += a_mstep) {
-            uint32_t b_n = b_ks;
-#pragma unroll 1
-            for (int nbj = 0; nbj < L.NBJ; ++nbj, b_n += b_nstep, dcol += (uint32_t)L.NBlk)
-              umma_bf16_elect(dcol, a_hi | (uint64_t)a_m, b_hi | (uint64_t)b_n, idesc, acc);
+#pragma unroll
+        for (int u = 0; u < khc; ++u) {
+#pragma unroll
+          for (int mbu = 0; mbu < mbuc; ++mbu) {
+#pragma unroll
+            for (int nbj = 0; nbj < nbjc; ++nbj)
+              umma_bf16_elect(tmem_base + (uint32_t)((u * mbuc + mbu) * nbjc + nbj) * (uint32_t)L.NBlk,
+                              a_hi | (uint64_t)(a_ks + (uint32_t)u * a_ustep + (uint32_t)mbu * a_mstep),
+                              b_hi | (uint64_t)(b_ks + (uint32_t)nbj * b_nstep), idesc, acc);
           }
         }
       }
@@ -164,39 +198,32 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       if (k == my_tiles - 1) umma_commit_elect(bar_done);
       if (++s == L.PS) { s = 0; ph ^= 1; }
     }
-  } else {
-    // ===== loaders =====
+  } else if (warp < 4) {
+    // ===== x loaders: rows q0 .. q0 + NPX of the virtual face through the halo table, 16-byte cp.async gathers =====
     const int lt = tid;
-    const int Sx = L.CinBlk / 8, Sy = L.NJ / 8;
-    const int chx = lt & (Sx - 1), chy = lt & (Sy - 1);
-    const int cx = cb * L.CinBlk + chx * 8;                       // first input channel of this thread's x chunk
-    const int cy = ngi * L.NJ + chy * 8;                          // first output channel of this thread's dy chunk
-    const bool okx = cx < P.cin, oky = cy < P.cout;
-    const int pstx = WG_LOADERS >> L.logSx, psty = WG_LOADERS >> L.logSy;
-    const uint32_t swx = (uint32_t)(L.RBx / 16 - 1), swy = (uint32_t)(L.RBy / 16 - 1);
-    const uint32_t yblk = (uint32_t)(chy / (L.RBy / 16)), ycw = (uint32_t)(chy % (L.RBy / 16));
-    float bsum[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) bsum[e] = 0.f;
-    int s = 0, ph = 0;
+    const int Sx = L.CinBlk / 8;
+    const int chx = lt & (Sx - 1);
+    const int cx = cb * L.CinBlk + chx * 8;                       // first input channel of this thread's chunk
+    const bool okx = cx < P.cin;
+    const int pstx = WG_XL >> L.logSx;
+    const uint32_t swx = (uint32_t)(L.RBx / 16 - 1);
+    int s = 0, ph = 0, ts = 0, tp = 0;
     for (int k = 0; k < my_tiles; ++k) {
-      const int t = idx + k * nin;
       int b, f, tf;
-      if (grp == 0) { const int bf = t / L.tpf; tf = t - bf * L.tpf; b = bf >> 2; f = bf & 3; }
-      else { b = t / L.tpf; tf = t - b * L.tpf; f = 3 + grp; }
-      const int q0 = tf * L.TP;
+      decode(k, b, f, tf);
       mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      mbar_wait(bar_tfull + 8 * ts, tp);
       const uint32_t st_addr = stage0 + (uint32_t)s * L.stageBytes;
-      // -- x patch: rows q0 .. q0 + NPX of the virtual face through the halo table
-      const int32_t *tab = P.tabx + (size_t)f * L.G + q0;
+      const int32_t *tab = s_tab + (size_t)ts * L.NPX;
       const size_t xb = (size_t)b * P.ppbx;
-      if (L.vecx) {
+      if (P.knock & 1) {
+      } else if (L.vecx) {
         for (int i0 = lt >> L.logSx; i0 < L.NPX; i0 += 8 * pstx) {
           int px[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int i = i0 + e * pstx;
-            px[e] = (i < L.NPX && okx) ? __ldg(tab + i) : -1;
+            px[e] = (i < L.NPX && okx) ? tab[i] : -1;
           }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -211,7 +238,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       } else {
 #pragma unroll 1
         for (int i = lt >> L.logSx; i < L.NPX; i += pstx) {
-          const int px = okx ? __ldg(tab + i) : -1;
+          const int px = okx ? tab[i] : -1;
           float a[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) a[e] = 0.f;
@@ -221,39 +248,75 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                       make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7])));
         }
       }
-      // -- dy tile through registers: activation-derivative mask, bias partial sums, bf16 rounding of the product
-      const int32_t *yt = P.ytab + q0;
+      mbar_arrive(bar_tempty + 8 * ts);
+      if (++ts == WG_TS) { ts = 0; tp ^= 1; }
+      fence_proxy_async();
+      cp_async_mbar_arrive(bar_full + 8 * s);
+      if (++s == L.PS) { s = 0; ph ^= 1; }
+    }
+  } else {
+    // ===== dy loaders: through registers -- activation-derivative mask, bias partial sums, bf16 rounding of the product.
+    // Rows with a discarded column (c >= Wout) or beyond the face are zero. =====
+    const int lt = tid - WG_XL;
+    const int Sy = L.NJ / 8;
+    const int chy = lt & (Sy - 1);
+    const int cy = ngi * L.NJ + chy * 8;                          // first output channel of this thread's chunk
+    const bool oky = cy < P.cout;
+    const int psty = WG_YL >> L.logSy;
+    const uint32_t swy = (uint32_t)(L.RBy / 16 - 1);
+    const uint32_t yblk = (uint32_t)(chy / (L.RBy / 16)), ycw = (uint32_t)(chy % (L.RBy / 16));
+    float bsum[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) bsum[e] = 0.f;
+    int s = 0, ph = 0;
+    for (int k = 0; k < my_tiles; ++k) {
+      int b, f, tf;
+      decode(k, b, f, tf);
+      const int q0 = tf * L.TP;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      const uint32_t st_addr = stage0 + (uint32_t)s * L.stageBytes;
       const size_t yb = (size_t)(b * 6 + f) * P.ppfy;
       const uint32_t ybase = st_addr + (uint32_t)L.xBytes + yblk * (uint32_t)L.yBlockBytes;
-      for (int i0 = lt >> L.logSy; i0 < L.TP; i0 += 4 * psty) {
-        int px[4];
-        float v[4][8], m[4][8];
+      if (!(P.knock & 2))
+      for (int i0 = lt >> L.logSy; i0 < L.TP; i0 += 8 * psty) {
+        int px[8];
+        uint4 dv[8], mv[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = i0 + e * psty;
-          px[e] = (i < L.TP && oky) ? __ldg(yt + i) : -1;
+        for (int e = 0; e < 8; ++e) {
+          const int i = i0 + e * psty, q = q0 + i;
+          const int r = q / L.Wv, c = q - r * L.Wv;
+          px[e] = (i < L.TP && oky && r < P.Ho && c < P.Wo) ? r * P.Wo + c : -1;
         }
+        if (L.vecy) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (px[e] >= 0) {
-            load8(P.dy, yb + px[e], P.cout, cy, L.vecy, v[e]);
-            if (P.mask_y) load8(P.mask_y, yb + px[e], P.cout, cy, L.vecy, m[e]);
+          for (int e = 0; e < 8; ++e) {
+            if (px[e] >= 0) {
+              dv[e] = __ldg(reinterpret_cast<const uint4 *>(P.dy + (yb + px[e]) * P.cout + cy));
+              if (P.mask_y) mv[e] = __ldg(reinterpret_cast<const uint4 *>(P.mask_y + (yb + px[e]) * P.cout + cy));
+            }
           }
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < 8; ++e) {
           const int i = i0 + e * psty;
           if (i < L.TP) {
             uint4 o = make_uint4(0, 0, 0, 0);
             if (px[e] >= 0) {
+              float v[8], m[8];
+              if (L.vecy) {
+                unpack_bf16x8(dv[e], v);
+                if (P.mask_y) unpack_bf16x8(mv[e], m);
+              } else {
+                load8(P.dy, yb + px[e], P.cout, cy, false, v);
+                if (P.mask_y) load8(P.mask_y, yb + px[e], P.cout, cy, false, m);
+              }
               if (P.mask_y) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) v[e][c] *= act_grad_from_y(m[e][c], P.act, P.slope, P.maxv);
+                for (int c = 0; c < 8; ++c) v[c] *= act_grad_from_y(m[c], P.act, P.slope, P.maxv);
               }
 #pragma unroll
-              for (int c = 0; c < 8; ++c) bsum[c] += v[e][c];
-              o = make_uint4(pack_bf16x2(v[e][0], v[e][1]), pack_bf16x2(v[e][2], v[e][3]), pack_bf16x2(v[e][4], v[e][5]),
-                             pack_bf16x2(v[e][6], v[e][7]));
+              for (int c = 0; c < 8; ++c) bsum[c] += v[c];
+              o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
             }
             const uint32_t row = ybase + (uint32_t)i * L.RBy;
             st_shared16(row + ((ycw ^ ((row >> 7) & swy)) << 4), o);
@@ -261,22 +324,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         }
       }
       fence_proxy_async();
-      cp_async_mbar_arrive(bar_full + 8 * s);
+      mbar_arrive(bar_full + 8 * s);
       if (++s == L.PS) { s = 0; ph ^= 1; }
     }
-    // ---- bias partials of this CTA (only the cin-block-0 jobs report them): fixed-order sum over the loader threads
+    // ---- bias partials of this CTA (only the cin-block-0 jobs report them): fixed-order sum over the dy loaders
     if (cb == 0 && P.ws_b) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) s_bsum[lt * 8 + e] = bsum[e];
-      named_bar_sync(1, WG_LOADERS);
+      named_bar_sync(1, WG_YL);
       if (lt < L.NJ) {
         const int ch = lt >> 3, e = lt & 7;
         float acc = 0.f;
-        for (int th = ch; th < WG_LOADERS; th += Sy) acc += s_bsum[th * 8 + e];
+        for (int th = ch; th < WG_YL; th += Sy) acc += s_bsum[th * 8 + e];
         P.ws_b[(size_t)blockIdx.x * L.NJ + lt] = acc;
       }
     }
-    // ---- accumulator dump: TMEM -> workspace [acc][lane][NJ]
+  }
+  if (warp < 8) {
+    // ---- accumulator dump by the eight loader warps: TMEM -> workspace [acc][lane][NJ]
     if (my_tiles > 0) {
       mbar_wait(bar_done, 0);
       tc_fence_after();
@@ -284,7 +349,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const int quarter = warp & 3, half = warp >> 2;
     float *wsc = P.ws + (size_t)blockIdx.x * L.nacc * 128 * L.NJ;
     const int nchunks = L.nacc * L.NJ / 16;
-    for (int cc = half; cc < nchunks; cc += 2) {
+    for (int cc = half; cc < ((P.knock & 8) ? 0 : nchunks); cc += 2) {
       uint32_t v[16];
       if (my_tiles > 0) {
         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * 16), v);
@@ -430,7 +495,7 @@ const char *make_wg_plan(const dlwpcs_conv_desc *d, const Geometry &g, WgPlan *L
     const int np = (tpb * 128 + extX + 7) / 8 * 8;
     const int xb = (np * L->RBx + 1023) / 1024 * 1024;
     const int stage = xb + L->NBJ * tpb * 128 * L->RBy;
-    if (2 * stage + WG_MISC + 1024 <= WG_SMEM_CAP) best = tpb;
+    if (2 * stage + WG_MISC + WG_TS * np * 4 + 1024 <= WG_SMEM_CAP) best = tpb;
   }
   if (!best) return "tile does not fit shared memory";
   if (best > nmb) best = nmb;
@@ -444,12 +509,12 @@ const char *make_wg_plan(const dlwpcs_conv_desc *d, const Geometry &g, WgPlan *L
   L->xBytes = (L->NPX * L->RBx + 1023) / 1024 * 1024;
   L->yBlockBytes = L->TP * L->RBy;
   L->stageBytes = L->xBytes + L->NBJ * L->yBlockBytes;
-  L->PS = (WG_SMEM_CAP - WG_MISC - 1024) / L->stageBytes;
+  L->PS = (WG_SMEM_CAP - WG_MISC - WG_TS * L->NPX * 4 - 1024) / L->stageBytes;
   int ps_max = env_int_wg("DLWPCS_WG_PS", 3);
   if (ps_max > WG_MAX_PS) ps_max = WG_MAX_PS;
   if (L->PS > ps_max) L->PS = ps_max;
   if (L->PS < 1) return "tile does not fit shared memory";
-  L->smemBytes = 1024 + L->PS * L->stageBytes + WG_MISC;
+  L->smemBytes = 1024 + L->PS * L->stageBytes + WG_MISC + WG_TS * L->NPX * 4;
   // CTAs: equal share per job, split 4 : 1 : 1 over the face groups (equatorial faces hold 4/6 of the tiles)
   L->J = L->NCB * L->NNG;
   const long long tiles_all = 6LL * d->batch * L->tpf;
@@ -464,41 +529,6 @@ const char *make_wg_plan(const dlwpcs_conv_desc *d, const Geometry &g, WgPlan *L
   L->ng[0] = n0; L->ng[1] = n1; L->ng[2] = nc - n0 - n1;
   L->ncta = L->J * nc;
   return nullptr;
-}
-
-// linear position of the virtual face -> output pixel of one face (or -1: discarded column / beyond the face)
-struct YKey {
-  int dev, Ho, Wo, Wv, len;
-  bool operator<(const YKey &o) const { return memcmp(this, &o, sizeof(YKey)) < 0; }
-};
-std::mutex g_ytab_mu;
-std::map<YKey, int32_t *> g_ytabs;
-
-const int32_t *get_ytab(int Ho, int Wo, int Wv, int len) {
-  YKey key;
-  memset(&key, 0, sizeof(key));
-  if (cudaGetDevice(&key.dev) != cudaSuccess) {
-    set_error("cudaGetDevice failed");
-    return nullptr;
-  }
-  key.Ho = Ho; key.Wo = Wo; key.Wv = Wv; key.len = len;
-  std::lock_guard<std::mutex> lk(g_ytab_mu);
-  auto it = g_ytabs.find(key);
-  if (it != g_ytabs.end()) return it->second;
-  std::vector<int32_t> tab((size_t)len);
-  for (int q = 0; q < len; ++q) {
-    const int r = q / Wv, c = q % Wv;
-    tab[q] = (r < Ho && c < Wo) ? r * Wo + c : -1;
-  }
-  int32_t *dev = nullptr;
-  cudaError_t e = cudaMalloc(&dev, tab.size() * sizeof(int32_t));
-  if (e == cudaSuccess) e = cudaMemcpy(dev, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) {
-    set_error("wgrad table upload failed: %s", cudaGetErrorString(e));
-    return nullptr;
-  }
-  g_ytabs[key] = dev;
-  return dev;
 }
 
 bool aligned16p(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -535,20 +565,31 @@ int tc_conv_wgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, 
   P.act = d->act; P.slope = d->act_slope; P.maxv = d->act_max;
   P.tabx = get_patch_table(g, L.Wv, L.G, d->n, d->halo, DLWPCS_SRC_SAME);
   if (!P.tabx) return 3;
-  P.ytab = get_ytab(g.Hout, g.Wout, L.Wv, L.tpf * L.TP);
-  if (!P.ytab) return 3;
   P.ws = (float *)workspace;
   P.ws_b = P.ws + (size_t)L.ncta * L.nacc * 128 * L.NJ;
   P.batch = d->batch; P.ppbx = 6 * d->n * d->n; P.ppfy = g.Hout * g.Wout;
-  P.cin = d->cin; P.cout = d->cout;
+  P.cin = d->cin; P.cout = d->cout; P.Ho = g.Hout; P.Wo = g.Wout;
   L.vecx = (d->cin % 8 == 0) && aligned16p(x0);
   L.vecy = (d->cout % 8 == 0) && aligned16p(dy) && (!P.mask_y || aligned16p(y));
-  static bool attr_set = false;
-  if (!attr_set) {
-    CS_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_CAP));
-    attr_set = true;
+  static const int knock = env_int_wg("DLWPCS_WG_KNOCK", 0);
+  P.knock = knock;
+  if (env_int_wg("DLWPCS_WG_VERBOSE", 0))
+    fprintf(stderr, "[wgrad plan] cin=%d cout=%d n=%d CinBlk=%d NCB=%d MBu=%d NBlk=%d NBJ=%d NNG=%d TPB=%d tpf=%d PS=%d NPX=%d smem=%d ncta=%d ng=%d/%d/%d tmem=%d\n",
+            d->cin, d->cout, d->n, L.CinBlk, L.NCB, L.MBu, L.NBlk, L.NBJ, L.NNG, L.TPB, L.tpf, L.PS, L.NPX, L.smemBytes, L.ncta, L.ng[0], L.ng[1], L.ng[2], L.tmemCols);
+  typedef void (*kern_t)(const WgP);
+  static const kern_t kerns[5] = {wgrad_tc_kernel<0, 0, 0>, wgrad_tc_kernel<3, 1, 1>, wgrad_tc_kernel<3, 2, 1>,
+                                  wgrad_tc_kernel<3, 1, 2>, wgrad_tc_kernel<1, 1, 1>};
+  static bool attr_set[5] = {};
+  int ki = 0;
+  if (L.kh == 3 && L.MBu == 1 && L.NBJ == 1) ki = 1;
+  else if (L.kh == 3 && L.MBu == 2 && L.NBJ == 1) ki = 2;
+  else if (L.kh == 3 && L.MBu == 1 && L.NBJ == 2) ki = 3;
+  else if (L.kh == 1 && L.MBu == 1 && L.NBJ == 1) ki = 4;
+  if (!attr_set[ki]) {
+    CS_CUDA(cudaFuncSetAttribute(kerns[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_CAP));
+    attr_set[ki] = true;
   }
-  wgrad_tc_kernel<<<L.ncta, WG_THREADS, L.smemBytes, st>>>(P);
+  kerns[ki]<<<L.ncta, WG_THREADS, L.smemBytes, st>>>(P);
   CS_CUDA(cudaGetLastError());
   const long long total = (long long)g.taps * d->cin * d->cout + d->cout;
   wgrad_tc_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(

@@ -206,7 +206,14 @@ class CubeSphereConv2D(nn.modules.lazy.LazyModuleMixin, nn.Module):
     def forward(self, inputs):
         x = _to_channels_last(inputs, self.data_format)
         fused = self._fused_act is not None
-        y = F_cs.cube_sphere_conv2d(x, self.equatorial_kernel, self.polar_kernel, self.north_pole_kernel,
+        kernels = (self.equatorial_kernel, self.polar_kernel, self.north_pole_kernel)
+        pad = (-x.shape[-1]) % 8
+        if pad and x.dtype == torch.bfloat16:
+            # bf16 tensor-core path: 16-byte gathers need channel counts that are multiples of 8 -- zero channels with
+            # zero weights leave the result unchanged (autograd slices the gradients back)
+            x = torch.nn.functional.pad(x, (0, pad))
+            kernels = tuple(None if w is None else torch.nn.functional.pad(w, (0, 0, 0, pad)) for w in kernels)
+        y = F_cs.cube_sphere_conv2d(x, kernels[0], kernels[1], kernels[2],
                                     self.equatorial_bias, self.polar_bias, self.north_pole_bias, self.strides,
                                     self.padding, self.dilation_rate, self.flip_north_pole, self.fuse_padding,
                                     self.activation if fused else None)
