@@ -65,6 +65,7 @@ def load():
         'dlwpcs_conv2d_fwd_host': (i32, [dp, wp, vp, vp]),
         'dlwpcs_mse_loss_grad': (i32, [vp, vp, vp, vp, i64, f32, i32, vp]),
         'dlwpcs_adam_step': (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp]),
+        'dlwpcs_adam_step_dev': (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)          # AttributeError here == header and library out of sync
@@ -79,7 +80,7 @@ EXPORTED = ('dlwpcs_version', 'dlwpcs_last_error', 'dlwpcs_conv_out_edge', 'dlwp
             'dlwpcs_pad_bwd', 'dlwpcs_packed_weight_bytes', 'dlwpcs_pack_weights', 'dlwpcs_conv2d_fwd',
             'dlwpcs_dgrad_workspace_bytes', 'dlwpcs_conv2d_dgrad', 'dlwpcs_wgrad_workspace_bytes',
             'dlwpcs_conv2d_wgrad', 'dlwpcs_act_fwd', 'dlwpcs_act_bwd', 'dlwpcs_conv2d_fwd_host',
-            'dlwpcs_mse_loss_grad', 'dlwpcs_adam_step')
+            'dlwpcs_mse_loss_grad', 'dlwpcs_adam_step', 'dlwpcs_adam_step_dev')
 
 
 class DlwpcsError(RuntimeError):
@@ -146,6 +147,15 @@ def make_desc(batch, n, cin, cout, kernel_size=(3, 3), strides=(1, 1), dilation=
     d.c0 = cin - c1 if c0 is None else c0
     d.mode0, d.c1, d.mode1 = mode0, c1, mode1
     return d
+
+
+def copy_desc(d, **changes):
+    """A copy of a conv descriptor with some fields replaced."""
+    c = ConvDesc()
+    ctypes.memmove(ctypes.byref(c), ctypes.byref(d), ctypes.sizeof(ConvDesc))
+    for k, v in changes.items():
+        setattr(c, k, v)
+    return c
 
 
 def out_shape(d):
@@ -277,3 +287,16 @@ def adam_step(param, grad, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
             raise DlwpcsError('adam_step needs contiguous float32 buffers')
     check(load().dlwpcs_adam_step(ptr(param), ptr(grad), ptr(m), ptr(v), param.numel(), lr, beta1, beta2, eps, int(step),
                                   grad_scale, stream_ptr()))
+
+
+def adam_step_dev(param, grad, m, v, lr, beta1, beta2, eps, step_counter, grad_scale=1.0):
+    """Keras-Adam update with the step counter in a 1-element int32 device tensor (incremented by the call): replayable
+    from a CUDA graph."""
+    require_cuda(param, grad, m, v, step_counter)
+    for t in (param, grad, m, v):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise DlwpcsError('adam_step_dev needs contiguous float32 buffers')
+    if step_counter.dtype != torch.int32 or step_counter.numel() != 1:
+        raise DlwpcsError('step_counter must be a 1-element int32 tensor')
+    check(load().dlwpcs_adam_step_dev(ptr(param), ptr(grad), ptr(m), ptr(v), param.numel(), lr, beta1, beta2, eps,
+                                      ptr(step_counter), grad_scale, stream_ptr()))

@@ -275,6 +275,31 @@ __global__ void act_bwd_kernel(const T *__restrict__ dy, const T *__restrict__ y
   for (; i < n; i += stride) dx[i] = from_f<T>(to_f<T>(dy[i]) * act_grad_from_y(to_f<T>(y[i]), act, slope, maxv));
 }
 
+// 16 bytes per thread (count a multiple of 8 bf16 / 4 fp32, aligned pointers)
+template <typename T, bool BWD>
+__global__ void act_vec_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ yv, uint4 *__restrict__ out,
+                               long long nvec, int act, float slope, float maxv) {
+  constexpr int E = 16 / sizeof(T);
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < nvec; i += stride) {
+    const uint4 av = __ldg(a + i);
+    uint4 o;
+    const T *ap = reinterpret_cast<const T *>(&av);
+    T *op = reinterpret_cast<T *>(&o);
+    if (BWD) {
+      const uint4 y4 = __ldg(yv + i);
+      const T *yp = reinterpret_cast<const T *>(&y4);
+#pragma unroll
+      for (int e = 0; e < E; ++e) op[e] = from_f<T>(to_f<T>(ap[e]) * act_grad_from_y(to_f<T>(yp[e]), act, slope, maxv));
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) op[e] = from_f<T>(act_apply(to_f<T>(ap[e]), act, slope, maxv));
+    }
+    out[i] = o;
+  }
+}
+
 template <typename T>
 __global__ void mse_kernel(const T *__restrict__ y, const T *__restrict__ t, T *__restrict__ dy, float *loss, long long n,
                            float inv) {
@@ -424,6 +449,18 @@ int dlwpcs_act_bwd(const void *dy, const void *y, void *dx, int64_t count, int a
   CS_CHECK(elem_size(dtype) != 0 && dy && y && dx && count >= 0, "bad arguments to dlwpcs_act_bwd");
   if (count == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  const int epv = 16 / (int)elem_size(dtype);
+  if (count % epv == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
+    const long long nv = count / epv;
+    if (dtype == DLWPCS_F32)
+      act_vec_kernel<float, true><<<grid_for(nv, 256), 256, 0, st>>>((const uint4 *)dy, (const uint4 *)y, (uint4 *)dx, nv, act,
+                                                                       slope, maxv);
+    else
+      act_vec_kernel<__nv_bfloat16, true><<<grid_for(nv, 256), 256, 0, st>>>((const uint4 *)dy, (const uint4 *)y, (uint4 *)dx,
+                                                                               nv, act, slope, maxv);
+    CS_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (dtype == DLWPCS_F32)
     act_bwd_kernel<float><<<grid_for(count, 256), 256, 0, st>>>((const float *)dy, (const float *)y, (float *)dx, count,
                                                                   act, slope, maxv);
@@ -445,6 +482,36 @@ int dlwpcs_mse_loss_grad(const void *y, const void *t, void *dy, float *loss_acc
   else
     mse_kernel<__nv_bfloat16><<<grid_for(count, 256), 256, 0, st>>>(
         (const __nv_bfloat16 *)y, (const __nv_bfloat16 *)t, (__nv_bfloat16 *)dy, loss_accum, count, inv_count);
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// step counter on the device: graph-replayable (a captured launch cannot carry a changing host scalar)
+__global__ void adam_dev_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                                float *__restrict__ v, long long n, float lr, float b1, float b2, float eps, float gscale,
+                                const int32_t *__restrict__ step) {
+  const double t = (double)(*step);
+  const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+__global__ void incr_kernel(int32_t *c) { *c += 1; }
+
+int dlwpcs_adam_step_dev(float *param, const float *grad, float *m, float *v, int64_t count, float lr, float beta1,
+                         float beta2, float eps, int32_t *step_counter, float grad_scale, void *stream) {
+  CS_CHECK(param && grad && m && v && step_counter && count >= 0, "bad arguments to dlwpcs_adam_step_dev");
+  incr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter);
+  if (count > 0)
+    adam_dev_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, count, lr, beta1, beta2, eps,
+                                                                             grad_scale, step_counter);
   CS_CUDA(cudaGetLastError());
   return 0;
 }

@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const int psty = WG_YL >> L.logSy;
     const uint32_t swy = (uint32_t)(L.RBy / 16 - 1);
     const uint32_t yblk = (uint32_t)(chy / (L.RBy / 16)), ycw = (uint32_t)(chy % (L.RBy / 16));
+    const bool direct = L.vecy && !P.mask_y;
     float bsum[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) bsum[e] = 0.f;
@@ -277,7 +278,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       const uint32_t st_addr = stage0 + (uint32_t)s * L.stageBytes;
       const size_t yb = (size_t)(b * 6 + f) * P.ppfy;
       const uint32_t ybase = st_addr + (uint32_t)L.xBytes + yblk * (uint32_t)L.yBlockBytes;
-      if (!(P.knock & 2))
+      if (P.knock & 2) {
+      } else if (direct) {
+        // no mask: 16-byte cp.async straight into the tile (the bias sums come from bias_sum_kernel)
+        for (int i0 = lt >> L.logSy; i0 < L.TP; i0 += 8 * psty) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int i = i0 + e * psty, q = q0 + i;
+            if (i < L.TP) {
+              const int r = q / L.Wv, c = q - r * L.Wv;
+              const bool ok = oky && r < P.Ho && c < P.Wo;
+              const uint32_t row = ybase + (uint32_t)i * L.RBy;
+              const __nv_bfloat16 *g = ok ? P.dy + (yb + (size_t)(r * P.Wo + c)) * P.cout + cy : P.dy;
+              cp_async16(row + ((ycw ^ ((row >> 7) & swy)) << 4), g, ok ? 16u : 0u);
+            }
+          }
+        }
+      } else
       for (int i0 = lt >> L.logSy; i0 < L.TP; i0 += 8 * psty) {
         int px[8];
         uint4 dv[8], mv[8];
@@ -324,11 +341,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         }
       }
       fence_proxy_async();
-      mbar_arrive(bar_full + 8 * s);
+      cp_async_mbar_arrive(bar_full + 8 * s);
       if (++s == L.PS) { s = 0; ph ^= 1; }
     }
     // ---- bias partials of this CTA (only the cin-block-0 jobs report them): fixed-order sum over the dy loaders
-    if (cb == 0 && P.ws_b) {
+    if (cb == 0 && P.ws_b && !direct) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) s_bsum[lt * 8 + e] = bsum[e];
       named_bar_sync(1, WG_YL);
@@ -369,6 +386,62 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   if (warp == WG_MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)L.tmemCols);
+}
+
+// Bias partial sums for the un-masked (cp.async) dy path: virtual CTA (job with cin block 0, index ic) sums the dy rows of
+// exactly the tiles the wgrad CTA of that index owns, per-thread in tile order and then over the threads in a fixed
+// order, into ws_b[cta][NJ] -- the layout the reduce kernel reads.
+__global__ void __launch_bounds__(256) bias_sum_kernel(const __grid_constant__ WgP P) {
+  __shared__ float s_b[256 * 8];
+  const WgPlan &L = P.pl;
+  const int ngi = blockIdx.x / L.nc, ic = blockIdx.x - ngi * L.nc;
+  int grp = 0, idx = ic, nin = L.ng[0];
+  if (ic >= L.ng[0] + L.ng[1]) { grp = 2; idx = ic - L.ng[0] - L.ng[1]; nin = L.ng[2]; }
+  else if (ic >= L.ng[0]) { grp = 1; idx = ic - L.ng[0]; nin = L.ng[1]; }
+  const int T = (grp == 0 ? 4 : 1) * P.batch * L.tpf;
+  const int my_tiles = idx < T ? (T - idx + nin - 1) / nin : 0;
+  const int lt = threadIdx.x, Sy = L.NJ / 8, chy = lt & (Sy - 1), cy = ngi * L.NJ + chy * 8, pst = 256 >> L.logSy;
+  const bool oky = cy < P.cout;
+  float bsum[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) bsum[e] = 0.f;
+  for (int k = 0; k < my_tiles; ++k) {
+    const int t = idx + k * nin;
+    int b, f, tf;
+    if (grp == 0) { const int bf = t / L.tpf; tf = t - bf * L.tpf; b = bf >> 2; f = bf & 3; }
+    else { b = t / L.tpf; tf = t - b * L.tpf; f = 3 + grp; }
+    const int q0 = tf * L.TP;
+    const size_t yb = (size_t)(b * 6 + f) * P.ppfy;
+    for (int i0 = lt >> L.logSy; i0 < L.TP; i0 += 8 * pst) {
+      uint4 dv[8];
+      bool ok[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int i = i0 + e * pst, q = q0 + i;
+        const int r = q / L.Wv, c = q - r * L.Wv;
+        ok[e] = i < L.TP && oky && r < P.Ho && c < P.Wo;
+        if (ok[e]) dv[e] = __ldg(reinterpret_cast<const uint4 *>(P.dy + (yb + (size_t)(r * P.Wo + c)) * P.cout + cy));
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (ok[e]) {
+          float v[8];
+          unpack_bf16x8(dv[e], v);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) bsum[c] += v[c];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s_b[lt * 8 + e] = bsum[e];
+  __syncthreads();
+  if (lt < L.NJ) {
+    const int ch = lt >> 3, e = lt & 7;
+    float acc = 0.f;
+    for (int th = ch; th < 256; th += Sy) acc += s_b[th * 8 + e];
+    P.ws_b[(size_t)(ngi * L.NCB * L.nc + ic) * L.NJ + lt] = acc;
+  }
 }
 
 // second pass: fixed-order sum of the CTA partials of each (job, face group); un-flip / merge the north-pole share
@@ -590,6 +663,8 @@ int tc_conv_wgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, 
     attr_set[ki] = true;
   }
   kerns[ki]<<<L.ncta, WG_THREADS, L.smemBytes, st>>>(P);
+  CS_CUDA(cudaGetLastError());
+  if (d->use_bias && L.vecy && !P.mask_y) bias_sum_kernel<<<L.NNG * L.nc, 256, 0, st>>>(P);
   CS_CUDA(cudaGetLastError());
   const long long total = (long long)g.taps * d->cin * d->cout + d->cout;
   wgrad_tc_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(

@@ -76,6 +76,12 @@ class _CubeSphereConv(torch.autograd.Function):
         if d.x_dtype != d.y_dtype:
             raise _lib.DlwpcsError('backward needs the output dtype to equal the input dtype')
         dy = dy.contiguous()
+        if d.act != _lib.ACT_NONE and d.x_dtype == _lib.BF16:
+            # bf16 path: the activation derivative is applied once (dgrad and wgrad both need dy * act'(y)); both kernels
+            # then stream the product with plain asynchronous 16-byte copies instead of masking in registers
+            dy = _lib.act_bwd(dy, y, d.act, d.act_slope, d.act_max)
+            d = _lib.copy_desc(d, act=_lib.ACT_NONE)
+            y = None
         dx = None
         if ctx.needs_input_grad[0]:
             packed_t = _lib.pack_weights(d, w_eq, w_pol, w_np, transposed=True)

@@ -75,8 +75,11 @@ class DataParallelTrainer(object):
     shards are equal (the reference scales the batch by the GPU count: Azure/train_tf.py:166).
     """
 
-    def __init__(self, model, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, group=None):
+    def __init__(self, model, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, group=None, use_graph=True):
         self.model = model
+        self.use_graph = use_graph
+        self._graph = None
+        self._static = None
         self.flat = FlatBuffers(model)
         if self.flat.param.device.type != 'cuda':
             raise _lib.DlwpcsError('DataParallelTrainer needs the model on a CUDA device (no CPU path)')
@@ -85,6 +88,7 @@ class DataParallelTrainer(object):
         self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
         self.group = group
         self.t = 0
+        self.step_counter = torch.zeros(1, dtype=torch.int32, device=self.flat.param.device)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.flat.param.device)
         self.flat.broadcast_params(group=group)
 
@@ -97,10 +101,44 @@ class DataParallelTrainer(object):
         y.backward(dy)
         return self.loss
 
-    def step(self, x, target):
+    def _step_body(self, x, target):
         loss = self.forward_backward(x, target)
         world = self.flat.all_reduce(self.group)
-        self.t += 1
-        _lib.adam_step(self.flat.param, self.flat.grad, self.m, self.v, self.lr, self.beta1, self.beta2, self.eps, self.t,
-                       1.0 / world)
+        # the step counter lives on the device (incremented by the call), so the same launches serve every step
+        _lib.adam_step_dev(self.flat.param, self.flat.grad, self.m, self.v, self.lr, self.beta1, self.beta2, self.eps,
+                           self.step_counter, 1.0 / world)
         return loss
+
+    def step(self, x, target):
+        """One optimizer step.  With ``use_graph`` the whole step (forward, loss, backward, all-reduce, Adam: ~150
+        launches) is captured once per input shape into a CUDA graph and replayed; x / target are copied into the
+        graph's static input buffers."""
+        self.t += 1
+        if not self.use_graph:
+            return self._step_body(x, target)
+        key = (tuple(x.shape), x.dtype, tuple(target.shape), target.dtype)
+        if self._graph is None or self._static[0] != key:
+            sx, st = torch.empty_like(x), torch.empty_like(target)
+            sx.copy_(x)
+            st.copy_(target)
+            state = [t.clone() for t in (self.flat.param, self.m, self.v, self.step_counter)]
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side):                   # warm-up off the capture: lazy tables, autograd buffers
+                for _ in range(2):
+                    self._step_body(sx, st)
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            torch.cuda.synchronize(x.device)
+            for dst, src in zip((self.flat.param, self.m, self.v, self.step_counter), state):
+                dst.copy_(src)                              # the warm-up steps do not count
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_body(sx, st)
+            for dst, src in zip((self.flat.param, self.m, self.v, self.step_counter), state):
+                dst.copy_(src)                              # neither does the capture (nothing ran, but be explicit)
+            self._graph, self._static = g, (key, sx, st)
+        _, sx, st = self._static
+        sx.copy_(x, non_blocking=True)
+        st.copy_(target, non_blocking=True)
+        self._graph.replay()
+        return self.loss

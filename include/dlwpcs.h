@@ -118,6 +118,10 @@ int dlwpcs_mse_loss_grad(const void *y, const void *t, void *dy, float *loss_acc
                          int dtype, void *stream);
 int dlwpcs_adam_step(float *param, const float *grad, float *m, float *v, int64_t count, float lr, float beta1,
                      float beta2, float eps, int step, float grad_scale, void *stream);
+/* The same update with the step counter t in device memory: *step_counter is incremented first, then used.  No host
+ * scalar changes between calls, so the whole training step can be replayed from a CUDA graph.                         */
+int dlwpcs_adam_step_dev(float *param, const float *grad, float *m, float *v, int64_t count, float lr, float beta1,
+                         float beta2, float eps, int32_t *step_counter, float grad_scale, void *stream);
 
 /* Host-buffer entry point: the call a reference-side binding makes with numpy arrays.  Copies x (and weights) to the
  * device, runs pad(halo)+conv, copies y back; synchronous.                                                            */

@@ -216,3 +216,27 @@ def test_tc_backward_vs_oracle_autograd(lib, c):
         close(a.grad, b.grad, 2e-3)
     for a, b in zip(bc, bo):
         close(a.grad, b.grad, 2e-3)
+
+
+@pytest.mark.parametrize('n,cin,cout', [(12, 32, 32), (24, 64, 64)])
+def test_tc_in_kernel_mask_equals_separate_act_bwd(lib, n, cin, cout):
+    """C ABI: dgrad / wgrad with the activation derivative applied inside the kernels (register path) against the same
+    kernels fed with dy * act'(y) from dlwpcs_act_bwd (asynchronous-copy path, bias sums from the side kernel)."""
+    g = torch.Generator().manual_seed(n + cin)
+    b = 2
+    x = bf(torch.randn(b, 6, n, n, cin, generator=g)).cuda()
+    y = bf(torch.randn(b, 6, n, n, cout, generator=g) * 6).cuda()          # spans both kinks (0 and the cap 10)
+    dy = bf(torch.randn(b, 6, n, n, cout, generator=g)).cuda()
+    ws = [(torch.randn(3, 3, cin, cout, generator=g) * 0.05).cuda() for _ in range(2)]
+    d = lib.make_desc(b, n, cin, cout, (3, 3), (1, 1), (1, 1), 1, False, True, False, True, lib.ACT_CAPPED_LEAKY_RELU, 0.1,
+                      10.0, lib.BF16, lib.BF16)
+    d0 = lib.copy_desc(d, act=lib.ACT_NONE)
+    dym = lib.act_bwd(dy, y, lib.ACT_CAPPED_LEAKY_RELU, 0.1, 10.0)
+    packed_t = lib.pack_weights(d, ws[0], ws[1], None, transposed=True)
+    assert torch.equal(lib.conv2d_dgrad(d, dy, y, packed_t), lib.conv2d_dgrad(d0, dym, None, packed_t))
+    a = lib.conv2d_wgrad(d, x, dy, y)
+    e = lib.conv2d_wgrad(d0, x, dym, None)
+    for u, v in zip(a, e):
+        if u is not None:
+            # weights: identical bf16 operands -> identical sums; bias: the in-kernel path sums the unrounded products
+            np.testing.assert_allclose(u.cpu().numpy(), v.cpu().numpy(), rtol=2e-3, atol=2e-3 * float(v.abs().max()))

@@ -82,3 +82,27 @@ def test_trainer_step_matches_oracle_autograd_and_keras_adam(lib):
         # the first Adam step moves every weight by ~lr * sign(g); tiny gradients make the direction itself ill-conditioned
         big = np.abs(gref) > 1e-4 * np.abs(gref).max()
         np.testing.assert_allclose(p.detach().double().cpu().numpy()[big], pref[big], rtol=0, atol=2e-5)
+
+
+def test_trainer_graph_replay_equals_eager_steps(lib):
+    """Three bf16 optimizer steps replayed from the captured CUDA graph (device-side Adam step counter) leave exactly the
+    parameters the eager launches leave; inputs change every step."""
+    from dlwp_cs_b200.unet import CubeSphereUNet2
+    from dlwp_cs_b200.train import DataParallelTrainer
+    n, b, cin, cout, base = 8, 2, 6, 4, 8
+    params = O.make_unet2_params(cin, cout, base=base, seed=11)
+    g = torch.Generator().manual_seed(3)
+    xs = [torch.randn(b, 6, n, n, cin, generator=g).cuda().bfloat16() for _ in range(3)]
+    ts = [torch.randn(b, 6, n, n, cout, generator=g).cuda().bfloat16() for _ in range(3)]
+    out = []
+    for use_graph in (False, True):
+        model = CubeSphereUNet2(cin, cout, base=base).cuda()
+        model.load_oracle_params(params)
+        tr = DataParallelTrainer(model, lr=1e-2, use_graph=use_graph)
+        losses = [float(tr.step(x, t)) for x, t in zip(xs, ts)]
+        assert int(tr.step_counter) == 3
+        out.append((tr.flat.param.clone(), losses))
+    assert torch.equal(out[0][0], out[1][0])
+    # the loss is a float atomicAdd over blocks: equal up to summation order
+    np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-5)
+    assert out[0][1][2] < out[0][1][0]          # and it learns
