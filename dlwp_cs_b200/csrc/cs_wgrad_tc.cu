@@ -444,56 +444,73 @@ __global__ void __launch_bounds__(256) bias_sum_kernel(const __grid_constant__ W
   }
 }
 
-// second pass: fixed-order sum of the CTA partials of each (job, face group); un-flip / merge the north-pole share
-__global__ void wgrad_tc_reduce_kernel(const float *__restrict__ ws, const float *__restrict__ ws_b, float *dw_eq,
-                                       float *dw_pol, float *dw_np, float *db_eq, float *db_pol, float *db_np, int kh,
-                                       int kw, int cin, int cout, int flip, const WgPlan L) {
+// second pass: fixed-order sum of the CTA partials of each (job, face group); un-flip / merge the north-pole share.
+// A block handles 32 consecutive outputs (lanes; consecutive output channels -> coalesced) with 8 warps that each add
+// every 8th CTA partial; the 8 slice sums are then added in slice order (deterministic).
+__global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float *__restrict__ ws, const float *__restrict__ ws_b,
+                                                              float *dw_eq, float *dw_pol, float *dw_np, float *db_eq,
+                                                              float *db_pol, float *db_np, int kh, int kw, int cin,
+                                                              int cout, int flip, const WgPlan L) {
+  __shared__ float sh[3][8][32];
+  const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const long long per = (long long)kh * kw * cin * cout;
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long i = blockIdx.x * 32LL + o;
   const size_t cta_stride = (size_t)L.nacc * 128 * L.NJ;
+  const int gfirst[3] = {0, L.ng[0], L.ng[0] + L.ng[1]};
+  float part[3] = {0.f, 0.f, 0.f};
+  int u = 0;
   if (i < per) {
     const int co = (int)(i % cout);
     long long r = i / cout;
     const int ci = (int)(r % cin); r /= cin;
-    const int v = (int)(r % kw), u = (int)(r / kw);
+    const int v = (int)(r % kw);
+    u = (int)(r / kw);
     const int cbk = ci / L.CinBlk, cil = ci - cbk * L.CinBlk;
     const int ngi = co / L.NJ, col = co - ngi * L.NJ;
     const int job = ngi * L.NCB + cbk;
     const int mbu = v / L.SPB, js = v - mbu * L.SPB, lane = js * L.CinBlk + cil;
-    auto group_sum = [&](int g, int uu) {
-      const int first = job * L.nc + (g == 0 ? 0 : (g == 1 ? L.ng[0] : L.ng[0] + L.ng[1]));
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      const int uu = (g == 2 && flip) ? kh - 1 - u : u;              // packed kernel row that reads source row u
       const size_t off = ((size_t)(uu * L.MBu + mbu) * 128 + lane) * L.NJ + col;
-      float s = 0.f;
-      for (int c = 0; c < L.ng[g]; ++c) s += ws[(size_t)(first + c) * cta_stride + off];
-      return s;
-    };
-    dw_eq[i] = group_sum(0, u);
-    const float south = group_sum(1, u);
-    const float north = group_sum(2, flip ? kh - 1 - u : u);       // packed kernel row that reads source row u
-    if (dw_np) {
-      dw_pol[i] = south;
-      dw_np[i] = north;
-    } else {
-      dw_pol[i] = south + north;
+      const float *src = ws + (size_t)(job * L.nc + gfirst[g]) * cta_stride + off;
+      float acc = 0.f;
+      for (int c = sl; c < L.ng[g]; c += 8) acc += src[(size_t)c * cta_stride];
+      part[g] = acc;
     }
   } else if (db_eq && i < per + cout) {
     const int co = (int)(i - per);
     const int ngi = co / L.NJ, col = co - ngi * L.NJ;
     const int job = ngi * L.NCB;
-    auto group_sum = [&](int g) {
-      const int first = job * L.nc + (g == 0 ? 0 : (g == 1 ? L.ng[0] : L.ng[0] + L.ng[1]));
-      float s = 0.f;
-      for (int c = 0; c < L.ng[g]; ++c) s += ws_b[(size_t)(first + c) * L.NJ + col];
-      return s;
-    };
-    db_eq[co] = group_sum(0);
-    const float south = group_sum(1), north = group_sum(2);
-    if (db_np) {
-      db_pol[co] = south;
-      db_np[co] = north;
-    } else {
-      db_pol[co] = south + north;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      const float *src = ws_b + (size_t)(job * L.nc + gfirst[g]) * L.NJ + col;
+      float acc = 0.f;
+      for (int c = sl; c < L.ng[g]; c += 8) acc += src[(size_t)c * L.NJ];
+      part[g] = acc;
     }
+  }
+#pragma unroll
+  for (int g = 0; g < 3; ++g) sh[g][sl][o] = part[g];
+  __syncthreads();
+  if (sl != 0) return;
+  float tot[3];
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += sh[g][k][o];
+    tot[g] = acc;
+  }
+  if (i < per) {
+    dw_eq[i] = tot[0];
+    if (dw_np) { dw_pol[i] = tot[1]; dw_np[i] = tot[2]; }
+    else dw_pol[i] = tot[1] + tot[2];
+  } else if (db_eq && i < per + cout) {
+    const int co = (int)(i - per);
+    db_eq[co] = tot[0];
+    if (db_np) { db_pol[co] = tot[1]; db_np[co] = tot[2]; }
+    else db_pol[co] = tot[1] + tot[2];
   }
 }
 
@@ -667,7 +684,7 @@ int tc_conv_wgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, 
   if (d->use_bias && L.vecy && !P.mask_y) bias_sum_kernel<<<L.NNG * L.nc, 256, 0, st>>>(P);
   CS_CUDA(cudaGetLastError());
   const long long total = (long long)g.taps * d->cin * d->cout + d->cout;
-  wgrad_tc_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+  wgrad_tc_reduce_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(
       P.ws, P.ws_b, out->dw_eq, out->dw_pol, d->independent_north_pole ? out->dw_np : nullptr,
       d->use_bias ? out->db_eq : nullptr, d->use_bias ? out->db_pol : nullptr,
       (d->use_bias && d->independent_north_pole) ? out->db_np : nullptr, d->kh, d->kw, d->cin, d->cout,
