@@ -65,6 +65,7 @@ def load():
         'dlwpcs_conv2d_fwd_host': (i32, [dp, wp, vp, vp]),
         'dlwpcs_mse_loss_grad': (i32, [vp, vp, vp, vp, i64, f32, i32, vp]),
         'dlwpcs_adam_step': (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp]),
+        'dlwpcs_insolation': (i32, [vp, i32, i32, i64, i32, i32, i32, vp, vp, vp, vp, f32, vp]),
         'dlwpcs_adam_step_dev': (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp]),
     }
     for name, (res, args) in sigs.items():
@@ -80,7 +81,7 @@ EXPORTED = ('dlwpcs_version', 'dlwpcs_last_error', 'dlwpcs_conv_out_edge', 'dlwp
             'dlwpcs_pad_bwd', 'dlwpcs_packed_weight_bytes', 'dlwpcs_pack_weights', 'dlwpcs_conv2d_fwd',
             'dlwpcs_dgrad_workspace_bytes', 'dlwpcs_conv2d_dgrad', 'dlwpcs_wgrad_workspace_bytes',
             'dlwpcs_conv2d_wgrad', 'dlwpcs_act_fwd', 'dlwpcs_act_bwd', 'dlwpcs_conv2d_fwd_host',
-            'dlwpcs_mse_loss_grad', 'dlwpcs_adam_step', 'dlwpcs_adam_step_dev')
+            'dlwpcs_mse_loss_grad', 'dlwpcs_adam_step', 'dlwpcs_adam_step_dev', 'dlwpcs_insolation')
 
 
 class DlwpcsError(RuntimeError):
@@ -300,3 +301,20 @@ def adam_step_dev(param, grad, m, v, lr, beta1, beta2, eps, step_counter, grad_s
         raise DlwpcsError('step_counter must be a 1-element int32 tensor')
     check(load().dlwpcs_adam_step_dev(ptr(param), ptr(grad), ptr(m), ptr(v), param.numel(), lr, beta1, beta2, eps,
                                       ptr(step_counter), grad_scale, stream_ptr()))
+
+
+def insolation(out, c_first, n_sol, sinlat, coslat, lon, days, S=1.0):
+    """Write the insolation channels [c_first, c_first + n_sol) of the channels_last tensor out (B, ..., C) in place.
+    sinlat / coslat float64 (npix,), lon float32 (npix,) degrees, days float64 (n_sol, B) day of year."""
+    require_cuda(out, sinlat, coslat, lon, days)
+    b, c = out.shape[0], out.shape[-1]
+    npix = out.numel() // max(b * c, 1)
+    if (sinlat.dtype, coslat.dtype, lon.dtype, days.dtype) != (torch.float64, torch.float64, torch.float32, torch.float64):
+        raise DlwpcsError('insolation: sinlat / coslat / days must be float64 and lon float32')
+    if sinlat.numel() != npix or coslat.numel() != npix or lon.numel() != npix or tuple(days.shape) != (n_sol, b):
+        raise DlwpcsError('insolation: geometry / days arrays do not match the output tensor')
+    if not out.is_contiguous():
+        raise DlwpcsError('insolation: the output tensor must be contiguous')
+    check(load().dlwpcs_insolation(ptr(out), dtype_code(out.dtype), b, npix, c, c_first, n_sol, ptr(sinlat), ptr(coslat),
+                                   ptr(lon), ptr(days.contiguous()), S, stream_ptr()))
+    return out

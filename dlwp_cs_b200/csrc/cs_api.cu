@@ -342,6 +342,49 @@ static int grid_for(long long total, int block) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// insolation of the forced rollout (DLWP/util.py:306-364 as re-evaluated every forecast iteration by
+// TimeSeriesEstimator.predict, DLWP/model/extensions.py:272-288).  Mixed precision exactly like the reference's numpy
+// expression: the day and the hour angle in float32 (util.py:340, 348, 357), orbit / declination in float64.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) insolation_kernel(T *__restrict__ out, long long npix, int c_total, int c_first,
+                                                         int n_sol, const double *__restrict__ sinlat,
+                                                         const double *__restrict__ coslat, const float *__restrict__ lon,
+                                                         const double *__restrict__ days, int batch, float S) {
+  __shared__ double s_sd[8], s_cd[8], s_r2[8];
+  __shared__ float s_day[8];
+  const int b = blockIdx.y;
+  if (threadIdx.x < n_sol) {
+    const double PI = 3.141592653589793;
+    const double eps = 23.4441 * PI / 180., ecc = 0.016715, om = 282.7 * PI / 180.;
+    const double beta = sqrt(1 - ecc * ecc);
+    const float d = (float)days[(size_t)threadIdx.x * batch + b];
+    const double lambda_m0 = ecc * (1. + beta) * sin(om);
+    const float term = __fdiv_rn(__fmul_rn(6.2831855f, __fsub_rn(d, 80.5f)), 365.f);
+    const double lambda_m = lambda_m0 + (double)term;
+    const double lambda_ = lambda_m + 2. * ecc * sin(lambda_m - om);
+    const double dec = asin(sin(eps) * sin(lambda_));
+    const double rho = (1. - ecc * ecc) / (1. + ecc * cos(lambda_ - om));
+    s_sd[threadIdx.x] = sin(dec);
+    s_cd[threadIdx.x] = cos(dec);
+    s_r2[threadIdx.x] = 1.0 / (rho * rho);
+    s_day[threadIdx.x] = d;
+  }
+  __syncthreads();
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+    const double sl = sinlat[p], cl = coslat[p];
+    const float lo = __fdiv_rn(lon[p], 360.f);
+    for (int n = 0; n < n_sol; ++n) {
+      const float h = __fmul_rn(6.2831855f, __fadd_rn(s_day[n], lo));
+      const float ch = (float)cos((double)h);              // float32 cosine of the float32 hour angle, like np.cos
+      double sol = (double)S * (sl * s_sd[n] - cl * s_cd[n] * (double)ch) * s_r2[n];
+      if (sol < 0.) sol = 0.;
+      out[((size_t)b * npix + p) * c_total + c_first + n] = from_f<T>((float)sol);
+    }
+  }
+}
+
 }  // namespace dlwpcs
 
 using namespace dlwpcs;
@@ -467,6 +510,25 @@ int dlwpcs_act_bwd(const void *dy, const void *y, void *dx, int64_t count, int a
   else
     act_bwd_kernel<__nv_bfloat16><<<grid_for(count, 256), 256, 0, st>>>(
         (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)y, (__nv_bfloat16 *)dx, count, act, slope, maxv);
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dlwpcs_insolation(void *out, int dtype, int batch, int64_t npix, int c_total, int c_first, int n_sol,
+                      const double *sinlat, const double *coslat, const float *lon, const double *days, float S,
+                      void *stream) {
+  CS_CHECK(elem_size(dtype) != 0 && out && sinlat && coslat && lon && days, "bad arguments to dlwpcs_insolation");
+  CS_CHECK(batch >= 0 && npix > 0 && n_sol >= 1 && n_sol <= 8 && c_first >= 0 && c_first + n_sol <= c_total,
+           "bad channel range for dlwpcs_insolation");
+  if (batch == 0) return 0;
+  dim3 grid((unsigned)((npix + 255) / 256 > 64 ? 64 : (npix + 255) / 256), (unsigned)batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DLWPCS_F32)
+    insolation_kernel<float><<<grid, 256, 0, st>>>((float *)out, npix, c_total, c_first, n_sol, sinlat, coslat, lon, days,
+                                                  batch, S);
+  else
+    insolation_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16 *)out, npix, c_total, c_first, n_sol, sinlat, coslat,
+                                                          lon, days, batch, S);
   CS_CUDA(cudaGetLastError());
   return 0;
 }

@@ -74,6 +74,19 @@ class CubeSphereUNet2(nn.Module):
                 p.copy_(params[name].to(p.dtype))
 
 
+def reference_input_order(t_in, n_var, n_const, n_sol_per_step=1):
+    """Engine slots of the reference's input channel packing (generators.py:880-899, train_cs.py:396-407): per input time
+    step the variables then the insolation, constants appended -- for ``RolloutEngine(input_order=...)``.  Prognostic slot
+    t * n_var + v, forcing slots: insolation of time step t first, then the constants."""
+    cp = t_in * n_var
+    order = []
+    for t in range(t_in):
+        order += [t * n_var + v for v in range(n_var)]
+        order += [cp + t * n_sol_per_step + k for k in range(n_sol_per_step)]
+    order += [cp + t_in * n_sol_per_step + k for k in range(n_const)]
+    return order
+
+
 class RolloutEngine(object):
     """
     Device-resident forecast loop for a ``CubeSphereUNet2``.
@@ -87,7 +100,7 @@ class RolloutEngine(object):
     """
 
     def __init__(self, model, batch, n, steps, forcing_channels=0, dtype=torch.float32, use_graph=True,
-                 per_step_forcing=False, device=None):
+                 per_step_forcing=False, device=None, input_order=None):
         if n % 4 != 0:
             raise ValueError('unet2 pools twice: face edge must be divisible by 4')
         self.model, self.batch, self.n, self.steps = model, batch, n, steps
@@ -97,6 +110,12 @@ class RolloutEngine(object):
             raise ValueError('prognostic (%d) + forcing (%d) channels != model input channels (%d)'
                              % (self.cp, self.cf, model.in_channels))
         self.dtype = dtype
+        # input_order[i] = engine slot read by the model's i-th input channel: k < Cp is prognostic channel k (fed back from
+        # the output), Cp + k is forcing channel k.  Default: prognostic channels first (see reference_input_order).
+        self.input_order = list(range(model.in_channels)) if input_order is None else [int(k) for k in input_order]
+        if sorted(self.input_order) != list(range(model.in_channels)):
+            raise ValueError('input_order must be a permutation of range(%d)' % model.in_channels)
+        self.solar = None
         # channel counts padded to multiples of 8 so that every gather is a 16-byte copy: the pad channels carry zero
         # weights on the way in and are written as exact zeros by the output layer
         self.cp_pad = -(-self.cp // 8) * 8
@@ -163,9 +182,8 @@ class RolloutEngine(object):
     def _pad_in(self, w):
         kh, kw, _, co = w.shape
         out = w.new_zeros((kh, kw, self.cp_pad + self.cf_pad, co))
-        out[:, :, :self.cp] = w[:, :, :self.cp]
-        if self.cf:
-            out[:, :, self.cp_pad:self.cp_pad + self.cf] = w[:, :, self.cp:]
+        for i, k in enumerate(self.input_order):     # model input channel i reads engine slot k
+            out[:, :, k if k < self.cp else self.cp_pad + (k - self.cp)] = w[:, :, i]
         return out
 
     @property
@@ -181,7 +199,46 @@ class RolloutEngine(object):
             return self.forcing[t] if self.per_step_forcing else self.forcing
         return self.buf[key]
 
+    def set_solar(self, lat, lon, dt_days, t_in, t_out, day0=None, start_dates=None, S=1.0):
+        """
+        Forced rollout (TimeSeriesEstimator.predict, extensions.py:259-308): before forecast iteration s the first `t_in`
+        forcing channels are overwritten on the device with the insolation (util.py:306-364) at
+        t_sample + (s * t_out + n) * dt, n = 0..t_in-1; the remaining forcing channels (constants) stay as loaded.
+
+        lat, lon: (6,N,N) degrees (lon 0-360).  Either `day0` ((B,) day of year of each member's first input time; no
+        new-year wrap) or `start_dates` ((B,) numpy datetime64; the day of year restarts on 1 January like util.py:301).
+        """
+        import numpy as np
+        if self.per_step_forcing:
+            raise ValueError('set_solar computes the forcing on the device; build the engine without per_step_forcing')
+        if t_in > self.cf:
+            raise ValueError('%d insolation channels do not fit %d forcing channels' % (t_in, self.cf))
+        lat = np.asarray(lat, dtype=np.float64).reshape(-1)
+        lon = np.asarray(lon, dtype=np.float64).reshape(-1)
+        if lat.size != 6 * self.n * self.n or lon.size != lat.size:
+            raise ValueError('lat / lon must have 6 x %d x %d entries' % (self.n, self.n))
+        days = np.empty((self.steps, t_in, self.batch), dtype=np.float64)
+        for s in range(self.steps):
+            for k in range(t_in):
+                off = (s * t_out + k) * dt_days
+                if start_dates is not None:
+                    d = np.asarray(start_dates, dtype='datetime64[s]') + np.timedelta64(int(round(off * 86400)), 's')
+                    y0 = d.astype('datetime64[Y]').astype('datetime64[s]')
+                    days[s, k] = (d - y0) / np.timedelta64(1, 's') / 3600. / 24.
+                else:
+                    days[s, k] = np.asarray(day0, dtype=np.float64) + off
+        dev = self.device
+        self.solar = dict(n=t_in, S=float(S), days=torch.from_numpy(days).to(dev),
+                          sinlat=torch.from_numpy(np.sin(np.pi / 180. * lat)).to(dev),
+                          coslat=torch.from_numpy(np.cos(np.pi / 180. * lat)).to(dev),
+                          lon=torch.from_numpy(lon.astype(np.float32)).to(dev))
+        self.graph = None
+        self.graph_host = None
+
     def _step(self, t):
+        if self.solar is not None:
+            so = self.solar
+            _lib.insolation(self.forcing, 0, so['n'], so['sinlat'], so['coslat'], so['lon'], so['days'][t], so['S'])
         for name, d, s0, s1, dst, packed in self.plan:
             out = self.ring[t] if dst == 'out' else self.buf[dst]
             _lib.conv2d_fwd(d, self._src(s0, t), self._src(s1, t), packed, out=out)

@@ -123,6 +123,16 @@ int dlwpcs_adam_step(float *param, const float *grad, float *m, float *v, int64_
 int dlwpcs_adam_step_dev(float *param, const float *grad, float *m, float *v, int64_t count, float lr, float beta1,
                          float beta2, float eps, int32_t *step_counter, float grad_scale, void *stream);
 
+/* Insolation channels of the forced rollout: DLWP/util.py:306-364 (`insolation`) as TimeSeriesEstimator.predict
+ * re-evaluates it before every forecast iteration (DLWP/model/extensions.py:272-288), written in place into channels
+ * [c_first, c_first + n_sol) of a channels_last tensor out (batch, npix, c_total) -- the engine's forcing buffer -- so the
+ * autoregressive loop never leaves the device.  sinlat / coslat: sin / cos of the latitude of every pixel (float64, npix),
+ * lon: longitude in degrees, 0-360 (float32, npix), days: day of year (util.py:301-303) of every sample for each of the
+ * n_sol input time steps, float64 [n_sol][batch].  Same mixed precision as the reference's numpy expression.          */
+int dlwpcs_insolation(void *out, int dtype, int batch, int64_t npix, int c_total, int c_first, int n_sol,
+                      const double *sinlat, const double *coslat, const float *lon, const double *days, float S,
+                      void *stream);
+
 /* Host-buffer entry point: the call a reference-side binding makes with numpy arrays.  Copies x (and weights) to the
  * device, runs pad(halo)+conv, copies y back; synchronous.                                                            */
 int dlwpcs_conv2d_fwd_host(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, const void *x_host, void *y_host);

@@ -297,6 +297,10 @@ def install():
     losses.mean_absolute_error = lambda a, b: np.mean(np.abs(a - b), axis=-1)
     losses.mean_squared_error = lambda a, b: np.mean((a - b) ** 2, axis=-1)
     keras.callbacks, keras.layers, keras.losses = callbacks, layers, losses
+    kmodels = mod('tensorflow.keras.models')              # DLWP/util.py imports these two names at module level
+    kutils = mod('tensorflow.keras.utils')
+    kutils.multi_gpu_model = lambda model, gpus=None: model
+    keras.models, keras.utils = kmodels, kutils
     for nm, table in (('activations', {'linear': _linear, 'relu': _relu}),
                       ('initializers', {'glorot_uniform': _glorot_uniform, 'zeros': _zeros}),
                       ('regularizers', {}), ('constraints', {})):
@@ -328,6 +332,16 @@ def load_reference_custom(path='/root/reference/DLWP/custom.py'):
     import importlib.util
     install()
     spec = importlib.util.spec_from_file_location('_dlwp_reference_custom', path)
+    module = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(module)
+    return module
+
+
+def load_reference_util(path='/root/reference/DLWP/util.py'):
+    """Import the reference's util.py by file path on top of the shim (for `insolation`, util.py:306-364)."""
+    import importlib.util
+    install()
+    spec = importlib.util.spec_from_file_location('_dlwp_reference_util', path)
     module = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(module)
     return module

@@ -164,3 +164,33 @@ def test_unet2_and_rollout_shapes():
     torch.testing.assert_close(out, fast2, rtol=1e-9, atol=1e-9)
     xp = torch.randn(2, 6, 6, 6, 3, dtype=torch.float64)
     assert torch.equal(O.cube_sphere_pad_fast(xp, 2), O.cube_sphere_pad(xp, 2))
+
+
+def test_insolation_oracle_matches_reference_golden():
+    """oracle/cs_solar.insolation against outputs of the reference's own DLWP.util.insolation (util.py:306-364), generated
+    by tests/golden/make_golden_solar.py -- bit for bit, 2-d cubed-sphere lat/lon, 1-d lat/lon meshes and daily=True."""
+    import os
+    import numpy as np
+    import cs_solar as S
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'insolation.npz'))
+    assert np.array_equal(np.array([S.day_of_year(np.datetime64(x)) for x in g['dates']]), g['days'])
+    for n in (4, 12):
+        assert np.array_equal(S.insolation(g['days'], g['lat_%d' % n], g['lon_%d' % n]), g['sol_%d' % n])
+        assert np.array_equal(S.insolation(g['days'], g['lat_%d' % n], g['lon_%d' % n], S=2.5, daily=True),
+                              g['sol_daily_%d' % n])
+    assert np.array_equal(S.insolation(g['days'], g['lat_1d'], g['lon_1d']), g['sol_1d'])
+    sol = g['sol_12']
+    assert sol.min() == 0.0 and 0.9 < sol.max() < 1.1          # night side clipped, sub-solar point ~ S / rho^2
+
+
+def test_cubed_sphere_latlon_geometry():
+    import numpy as np
+    import cs_solar as S
+    lat, lon = S.cubed_sphere_latlon(8)
+    assert lat.shape == lon.shape == (6, 8, 8)
+    assert np.all(lat[5] > 35) and np.all(lat[4] < -35) and np.all(np.abs(lat[:4]) < 45.0001)
+    assert np.all((lon >= 0) & (lon < 360))
+    # unit vectors of all cells cover the sphere evenly enough: mean position is the origin
+    v = np.stack([np.cos(np.radians(lat)) * np.cos(np.radians(lon)), np.cos(np.radians(lat)) * np.sin(np.radians(lon)),
+                  np.sin(np.radians(lat))])
+    assert np.abs(v.reshape(3, -1).mean(axis=1)).max() < 1e-12
