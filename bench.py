@@ -178,6 +178,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64, help='ensemble members (initial conditions) per GPU')
     ap.add_argument('--rollout-steps', type=int, default=100)
+    ap.add_argument('--face-edge', type=int, default=48, help='48 = C48 (headline config), 96 = C96 (BASELINE configs[4])')
+    ap.add_argument('--variables', type=int, default=7, help='prognostic variables per time step (x2 time steps)')
     ap.add_argument('--dtype', default='auto', choices=['auto', 'bf16', 'fp32'])
     ap.add_argument('--ref-batch', type=int, default=16)
     ap.add_argument('--ref-steps', type=int, default=100)
@@ -190,6 +192,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
+    global N_FACE, C_PROG
+    N_FACE, C_PROG = args.face_edge, 2 * args.variables
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -375,12 +379,12 @@ def main():
                 'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if dtype == 'bf16' else 'f32',
                 'data': 'synthetic',
-                'config': {'workload': 'unet2 (Weyn-2020) C48 rollout, 7 vars x 2 tsteps in/out (+2 solar +2 const), '
+                'config': {'workload': 'unet2 (Weyn-2020) C%d rollout, %d vars x 2 tsteps in/out (+2 solar +2 const), ' % (N_FACE, C_PROG // 2) +
                                        '%d 6-hr steps, ensemble of %d members per GPU, random-init weights'
                                        % (args.rollout_steps, args.batch),
                            'rollout_steps': args.rollout_steps, 'batch_per_gpu': args.batch, 'face_edge': N_FACE,
                            'l2': '512 MiB flush write between bench steps; per-step activation set %.0f MiB > L2'
-                                 % (args.batch * 6 * 48 * 48 * 32 * esz * 4 / 2 ** 20),
+                                 % (args.batch * 6 * N_FACE * N_FACE * 32 * esz * 4 / 2 ** 20),
                            'cuda_graph': not args.no_graph, 'parallelism': 'replicas x%d' % world},
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': e2e_ms / args.steps},

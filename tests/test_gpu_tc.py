@@ -240,3 +240,22 @@ def test_tc_in_kernel_mask_equals_separate_act_bwd(lib, n, cin, cout):
         if u is not None:
             # weights: identical bf16 operands -> identical sums; bias: the in-kernel path sums the unrounded products
             np.testing.assert_allclose(u.cpu().numpy(), v.cpu().numpy(), rtol=2e-3, atol=2e-3 * float(v.abs().max()))
+
+
+def test_tc_rollout_c96_12var_vs_oracle(lib):
+    """BASELINE.json configs[4] shape: C96 faces, 12 variables x 2 time steps (+2 insolation +2 constants), base 32; one
+    bf16 model step against the float64 oracle on bf16-rounded weights / inputs."""
+    from dlwp_cs_b200.unet import CubeSphereUNet2, RolloutEngine
+    n, b, cp, cf, steps, base = 96, 1, 24, 4, 1, 32
+    params = {k: bf(v).float() for k, v in O.make_unet2_params(cp + cf, cp, base=base, seed=8).items()}
+    model = CubeSphereUNet2(cp + cf, cp, base=base).cuda()
+    model.load_oracle_params(params)
+    g = torch.Generator().manual_seed(6)
+    state = bf(torch.randn(b, 6, n, n, cp, generator=g))
+    forcing = bf(torch.rand(b, 6, n, n, cf, generator=g))
+    ref = O.rollout({k: v.double() for k, v in params.items()}, state.double(), forcing.double(), steps)
+    eng = RolloutEngine(model, b, n, steps, forcing_channels=cf, dtype=torch.bfloat16)
+    out = eng.run(state.cuda(), forcing.cuda())
+    torch.cuda.synchronize()
+    err = (out.double().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 3e-2, err
