@@ -65,6 +65,9 @@ def load():
         'dlwpcs_conv2d_fwd_host': (i32, [dp, wp, vp, vp]),
         'dlwpcs_mse_loss_grad': (i32, [vp, vp, vp, vp, i64, f32, i32, vp]),
         'dlwpcs_adam_step': (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp]),
+        'dlwpcs_pool2': (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
+        'dlwpcs_up2cat_fwd': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+        'dlwpcs_up2cat_bwd': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         'dlwpcs_insolation': (i32, [vp, i32, i32, i64, i32, i32, i32, vp, vp, vp, vp, f32, vp]),
         'dlwpcs_adam_step_dev': (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp]),
     }
@@ -81,7 +84,8 @@ EXPORTED = ('dlwpcs_version', 'dlwpcs_last_error', 'dlwpcs_conv_out_edge', 'dlwp
             'dlwpcs_pad_bwd', 'dlwpcs_packed_weight_bytes', 'dlwpcs_pack_weights', 'dlwpcs_conv2d_fwd',
             'dlwpcs_dgrad_workspace_bytes', 'dlwpcs_conv2d_dgrad', 'dlwpcs_wgrad_workspace_bytes',
             'dlwpcs_conv2d_wgrad', 'dlwpcs_act_fwd', 'dlwpcs_act_bwd', 'dlwpcs_conv2d_fwd_host',
-            'dlwpcs_mse_loss_grad', 'dlwpcs_adam_step', 'dlwpcs_adam_step_dev', 'dlwpcs_insolation')
+            'dlwpcs_mse_loss_grad', 'dlwpcs_adam_step', 'dlwpcs_adam_step_dev', 'dlwpcs_insolation', 'dlwpcs_pool2',
+            'dlwpcs_up2cat_fwd', 'dlwpcs_up2cat_bwd')
 
 
 class DlwpcsError(RuntimeError):
@@ -318,3 +322,42 @@ def insolation(out, c_first, n_sol, sinlat, coslat, lon, days, S=1.0):
     check(load().dlwpcs_insolation(ptr(out), dtype_code(out.dtype), b, npix, c, c_first, n_sol, ptr(sinlat), ptr(coslat),
                                    ptr(lon), ptr(days.contiguous()), S, stream_ptr()))
     return out
+
+
+def resample_vec_ok(*tensors):
+    """True when the 16-byte resampling kernels apply: CUDA, contiguous, float32 / bf16, channels fill 16-byte chunks."""
+    for t in tensors:
+        if not (t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.bfloat16)):
+            return False
+        if t.shape[-1] % (16 // t.element_size()) or t.data_ptr() % 16:
+            return False
+    return True
+
+
+def pool2(x, backward=False):
+    """AveragePooling3D((1,2,2)) on (B,6,2n,2n,C) -> (B,6,n,n,C); backward=True: its adjoint (B,6,n,n,C) -> (B,6,2n,2n,C)."""
+    require_cuda(x)
+    b, _, e, _, c = x.shape
+    n = e if backward else e // 2
+    out = torch.empty((b, 6, 2 * n, 2 * n, c) if backward else (b, 6, n, n, c), dtype=x.dtype, device=x.device)
+    check(load().dlwpcs_pool2(ptr(x), ptr(out), b, n, c, int(backward), dtype_code(x.dtype), stream_ptr()))
+    return out
+
+
+def up2cat_fwd(a, b):
+    require_cuda(a, b)
+    bs, _, n, _, cb = b.shape
+    ca = a.shape[-1]
+    t = torch.empty((bs, 6, n, n, ca + cb), dtype=b.dtype, device=b.device)
+    check(load().dlwpcs_up2cat_fwd(ptr(a), ptr(b), ptr(t), bs, n, ca, cb, dtype_code(b.dtype), stream_ptr()))
+    return t
+
+
+def up2cat_bwd(dt, ca):
+    require_cuda(dt)
+    bs, _, n, _, ct = dt.shape
+    cb = ct - ca
+    da = torch.empty((bs, 6, n // 2, n // 2, ca), dtype=dt.dtype, device=dt.device)
+    db = torch.empty((bs, 6, n, n, cb), dtype=dt.dtype, device=dt.device)
+    check(load().dlwpcs_up2cat_bwd(ptr(dt), ptr(da), ptr(db), bs, n, ca, cb, dtype_code(dt.dtype), stream_ptr()))
+    return da, db

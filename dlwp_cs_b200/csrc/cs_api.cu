@@ -7,6 +7,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <initializer_list>
 #include "cs_common.cuh"
 
 namespace dlwpcs {
@@ -385,6 +386,120 @@ __global__ void __launch_bounds__(256) insolation_kernel(T *__restrict__ out, lo
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// resampling steps either side of the conv for the TRAINING path (materialised tensors; the rollout engine folds them into
+// the conv's load stage): AveragePooling3D((1,2,2)), UpSampling3D((1,2,2)) + concatenate (Azure/train_cs.py:197-198,
+// 282-299) and their adjoints.  16 bytes per thread; channel counts multiples of 8 (bf16) / 4 (fp32).
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct Vec16 {
+  static constexpr int E = 16 / sizeof(T);
+  __device__ static void load(const uint4 *p, float *f) {
+    const uint4 q = __ldg(p);
+    const T *t = reinterpret_cast<const T *>(&q);
+#pragma unroll
+    for (int e = 0; e < E; ++e) f[e] = to_f<T>(t[e]);
+  }
+  __device__ static uint4 pack(const float *f) {
+    uint4 o;
+    T *t = reinterpret_cast<T *>(&o);
+#pragma unroll
+    for (int e = 0; e < E; ++e) t[e] = from_f<T>(f[e]);
+    return o;
+  }
+};
+
+// y (BF, n, n, vpp) <- mean of the 2x2 blocks of x (BF, 2n, 2n, vpp);  bwd: dx (BF, 2n, 2n, vpp) <- 0.25 * dy (BF, n, n, vpp)
+template <typename T, bool BWD>
+__global__ void pool2_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int n, int vpp, long long total) {
+  constexpr int E = Vec16<T>::E;
+  const int no = BWD ? 2 * n : n;                          // edge of the output
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int v = (int)(i % vpp);
+    long long q = i / vpp;
+    const int c = (int)(q % no); q /= no;
+    const int r = (int)(q % no);
+    const long long bf = q / no;
+    float a[E];
+    if (BWD) {
+      Vec16<T>::load(in + ((bf * n + (r >> 1)) * n + (c >> 1)) * vpp + v, a);
+#pragma unroll
+      for (int e = 0; e < E; ++e) a[e] *= 0.25f;
+    } else {
+      float t[E];
+      const uint4 *src = in + ((bf * 2 * n + 2 * r) * 2 * n + 2 * c) * vpp + v;
+      Vec16<T>::load(src, a);
+      Vec16<T>::load(src + vpp, t);
+#pragma unroll
+      for (int e = 0; e < E; ++e) a[e] += t[e];
+      Vec16<T>::load(src + (long long)2 * n * vpp, t);
+#pragma unroll
+      for (int e = 0; e < E; ++e) a[e] += t[e];
+      Vec16<T>::load(src + (long long)(2 * n + 1) * vpp, t);
+#pragma unroll
+      for (int e = 0; e < E; ++e) a[e] = 0.25f * (a[e] + t[e]);
+    }
+    out[i] = Vec16<T>::pack(a);
+  }
+}
+
+// t (BF, n, n, va + vb) <- [nearest-upsampled a (BF, n/2, n/2, va) | b (BF, n, n, vb)]
+template <typename T>
+__global__ void up2cat_fwd_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b, uint4 *__restrict__ t, int n,
+                                  int va, int vb, long long total) {
+  const int vt = va + vb, h = n >> 1;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int v = (int)(i % vt);
+    long long q = i / vt;
+    const int c = (int)(q % n); q /= n;
+    const int r = (int)(q % n);
+    const long long bf = q / n;
+    t[i] = v < va ? __ldg(a + ((bf * h + (r >> 1)) * h + (c >> 1)) * va + v)
+                  : __ldg(b + ((bf * n + r) * n + c) * vb + (v - va));
+  }
+}
+
+// adjoint: da (BF, n/2, n/2, va) <- sum of the 2x2 blocks of dt[..., :va];  db (BF, n, n, vb) <- dt[..., va:]
+template <typename T>
+__global__ void up2cat_bwd_kernel(const uint4 *__restrict__ dt, uint4 *__restrict__ da, uint4 *__restrict__ db, int n,
+                                  int va, int vb, long long total_a, long long total) {
+  constexpr int E = Vec16<T>::E;
+  const int vt = va + vb, h = n >> 1;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    if (i < total_a) {
+      const int v = (int)(i % va);
+      long long q = i / va;
+      const int c = (int)(q % h); q /= h;
+      const int r = (int)(q % h);
+      const long long bf = q / h;
+      const uint4 *src = dt + ((bf * n + 2 * r) * n + 2 * c) * vt + v;
+      float s[E], u[E];
+      Vec16<T>::load(src, s);
+      Vec16<T>::load(src + vt, u);
+#pragma unroll
+      for (int e = 0; e < E; ++e) s[e] += u[e];
+      Vec16<T>::load(src + (long long)n * vt, u);
+#pragma unroll
+      for (int e = 0; e < E; ++e) s[e] += u[e];
+      Vec16<T>::load(src + (long long)(n + 1) * vt, u);
+#pragma unroll
+      for (int e = 0; e < E; ++e) s[e] += u[e];
+      da[i] = Vec16<T>::pack(s);
+    } else {
+      const long long j = i - total_a;
+      const int v = (int)(j % vb);
+      const long long px = j / vb;
+      db[j] = __ldg(dt + px * vt + va + v);
+    }
+  }
+}
+
 }  // namespace dlwpcs
 
 using namespace dlwpcs;
@@ -510,6 +625,70 @@ int dlwpcs_act_bwd(const void *dy, const void *y, void *dx, int64_t count, int a
   else
     act_bwd_kernel<__nv_bfloat16><<<grid_for(count, 256), 256, 0, st>>>(
         (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)y, (__nv_bfloat16 *)dx, count, act, slope, maxv);
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static bool vec_ok(int dtype, std::initializer_list<int> channels, std::initializer_list<const void *> ptrs) {
+  const int epv = 16 / (int)elem_size(dtype);
+  for (int c : channels)
+    if (c % epv) return false;
+  for (const void *p : ptrs)
+    if (reinterpret_cast<uintptr_t>(p) & 15) return false;
+  return true;
+}
+
+int dlwpcs_pool2(const void *in, void *out, int batch, int n, int c, int backward, int dtype, void *stream) {
+  CS_CHECK(elem_size(dtype) != 0 && in && out && batch >= 0 && n > 0 && c > 0, "bad arguments to dlwpcs_pool2");
+  CS_CHECK(vec_ok(dtype, {c}, {in, out}), "dlwpcs_pool2 needs 16-byte aligned tensors and a channel count that fills 16-byte chunks");
+  if (batch == 0) return 0;
+  const int vpp = c / (16 / (int)elem_size(dtype)), no = backward ? 2 * n : n;
+  const long long total = (long long)batch * 6 * no * no * vpp;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = grid_for(total, 256);
+  if (dtype == DLWPCS_F32) {
+    if (backward) pool2_kernel<float, true><<<g, 256, 0, st>>>((const uint4 *)in, (uint4 *)out, n, vpp, total);
+    else pool2_kernel<float, false><<<g, 256, 0, st>>>((const uint4 *)in, (uint4 *)out, n, vpp, total);
+  } else {
+    if (backward) pool2_kernel<__nv_bfloat16, true><<<g, 256, 0, st>>>((const uint4 *)in, (uint4 *)out, n, vpp, total);
+    else pool2_kernel<__nv_bfloat16, false><<<g, 256, 0, st>>>((const uint4 *)in, (uint4 *)out, n, vpp, total);
+  }
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dlwpcs_up2cat_fwd(const void *a, const void *b, void *t, int batch, int n, int ca, int cb, int dtype, void *stream) {
+  CS_CHECK(elem_size(dtype) != 0 && a && b && t && batch >= 0 && n > 0 && n % 2 == 0 && ca > 0 && cb > 0,
+           "bad arguments to dlwpcs_up2cat_fwd");
+  CS_CHECK(vec_ok(dtype, {ca, cb}, {a, b, t}), "dlwpcs_up2cat_fwd needs 16-byte aligned tensors and channel counts that fill 16-byte chunks");
+  if (batch == 0) return 0;
+  const int epv = 16 / (int)elem_size(dtype), va = ca / epv, vb = cb / epv;
+  const long long total = (long long)batch * 6 * n * n * (va + vb);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DLWPCS_F32)
+    up2cat_fwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const uint4 *)a, (const uint4 *)b, (uint4 *)t, n, va, vb, total);
+  else
+    up2cat_fwd_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>((const uint4 *)a, (const uint4 *)b, (uint4 *)t, n, va, vb,
+                                                                            total);
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dlwpcs_up2cat_bwd(const void *dt, void *da, void *db, int batch, int n, int ca, int cb, int dtype, void *stream) {
+  CS_CHECK(elem_size(dtype) != 0 && dt && da && db && batch >= 0 && n > 0 && n % 2 == 0 && ca > 0 && cb > 0,
+           "bad arguments to dlwpcs_up2cat_bwd");
+  CS_CHECK(vec_ok(dtype, {ca, cb}, {dt, da, db}), "dlwpcs_up2cat_bwd needs 16-byte aligned tensors and channel counts that fill 16-byte chunks");
+  if (batch == 0) return 0;
+  const int epv = 16 / (int)elem_size(dtype), va = ca / epv, vb = cb / epv;
+  const long long total_a = (long long)batch * 6 * (n / 2) * (n / 2) * va;
+  const long long total = total_a + (long long)batch * 6 * n * n * vb;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DLWPCS_F32)
+    up2cat_bwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const uint4 *)dt, (uint4 *)da, (uint4 *)db, n, va, vb, total_a,
+                                                                    total);
+  else
+    up2cat_bwd_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>((const uint4 *)dt, (uint4 *)da, (uint4 *)db, n, va, vb,
+                                                                            total_a, total);
   CS_CUDA(cudaGetLastError());
   return 0;
 }

@@ -132,3 +132,41 @@ class _Act(torch.autograd.Function):
 def capped_leaky_relu(x, negative_slope=0.1, max_value=10.0):
     """keras ReLU(negative_slope, max_value) (Azure/train_cs.py:199) as a standalone op."""
     return _Act.apply(x, (_lib.ACT_CAPPED_LEAKY_RELU, float(negative_slope), float(max_value)))
+
+
+class _Pool2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return _lib.pool2(x, backward=False)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _lib.pool2(dy.contiguous(), backward=True)
+
+
+class _Up2Cat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.ca = a.shape[-1]
+        return _lib.up2cat_fwd(a, b)
+
+    @staticmethod
+    def backward(ctx, dt):
+        return _lib.up2cat_bwd(dt.contiguous(), ctx.ca)
+
+
+def avg_pool_2x2(x):
+    """AveragePooling3D((1,2,2)) (Azure/train_cs.py:197), channels_last; one 16-byte kernel each way."""
+    _check_cl(x)
+    if x.shape[2] % 2:
+        raise ValueError('face edge %d is not divisible by 2' % x.shape[2])
+    return _Pool2.apply(x.contiguous())
+
+
+def upsample_concat(a, b):
+    """concatenate([UpSampling3D((1,2,2))(a), b]) (Azure/train_cs.py:198, 293, 299): a (B,6,n/2,n/2,Ca), b (B,6,n,n,Cb)."""
+    _check_cl(a)
+    _check_cl(b)
+    if 2 * a.shape[2] != b.shape[2] or a.shape[0] != b.shape[0] or a.dtype != b.dtype:
+        raise ValueError('upsample_concat: incompatible tensors %r and %r' % (tuple(a.shape), tuple(b.shape)))
+    return _Up2Cat.apply(a.contiguous(), b.contiguous())

@@ -58,13 +58,19 @@ class CubeSphereUNet2(nn.Module):
         return [getattr(self, s[0]) for s in unet2_layer_specs(self.in_channels, self.out_channels, self.base)]
 
     def forward(self, x):
+        # pooling / upsampling + concatenation: one 16-byte kernel each way when the channel counts allow it (they do for
+        # every base that is a multiple of 8), torch ops otherwise
+        def pool(t):
+            return F_cs.avg_pool_2x2(t) if _lib.resample_vec_ok(t) else _avg_pool(t)
+
+        def upcat(a, b):
+            return F_cs.upsample_concat(a, b) if _lib.resample_vec_ok(a, b) else torch.cat([_upsample(a), b], dim=-1)
+
         x0 = self.conv_2d_1_2(self.conv_2d_1(x))
-        x1 = self.conv_2d_2_2(self.conv_2d_2(_avg_pool(x0)))
-        x2 = self.conv_2d_5(self.conv_2d_5_2(_avg_pool(x1)))
-        t = torch.cat([_upsample(x2), x1], dim=-1)
-        t = self.conv_2d_6(self.conv_2d_6_2(t))
-        t = torch.cat([_upsample(t), x0], dim=-1)
-        t = self.conv_2d_7_2(self.conv_2d_7(t))
+        x1 = self.conv_2d_2_2(self.conv_2d_2(pool(x0)))
+        x2 = self.conv_2d_5(self.conv_2d_5_2(pool(x1)))
+        t = self.conv_2d_6(self.conv_2d_6_2(upcat(x2, x1)))
+        t = self.conv_2d_7_2(self.conv_2d_7(upcat(t, x0)))
         return self.conv_2d_8(t)
 
     def load_oracle_params(self, params):

@@ -107,6 +107,17 @@ int dlwpcs_act_fwd(const void *x, void *y, int64_t count, int act, float slope, 
 int dlwpcs_act_bwd(const void *dy, const void *y, void *dx, int64_t count, int act, float slope, float maxv,
                    int dtype, void *stream);
 
+/* Materialised resampling steps of the training path (the rollout folds them into the conv's load stage), float32 or
+ * bf16, 16 bytes per thread (channel counts multiples of 4 / 8, 16-byte aligned tensors):
+ *   dlwpcs_pool2      AveragePooling3D((1,2,2)) train_cs.py:197: backward = 0: in (B,6,2n,2n,c) -> out (B,6,n,n,c), mean
+ *                     of each 2x2 block; backward = 1 (adjoint): in (B,6,n,n,c) -> out (B,6,2n,2n,c) = 0.25 * in.
+ *   dlwpcs_up2cat_fwd UpSampling3D((1,2,2)) + concatenate train_cs.py:198, 293, 299: t (B,6,n,n,ca+cb) =
+ *                     [nearest-upsampled a (B,6,n/2,n/2,ca) | b (B,6,n,n,cb)];  _bwd: da = 2x2 block sums of dt[..., :ca],
+ *                     db = dt[..., ca:].                                                                               */
+int dlwpcs_pool2(const void *in, void *out, int batch, int n, int c, int backward, int dtype, void *stream);
+int dlwpcs_up2cat_fwd(const void *a, const void *b, void *t, int batch, int n, int ca, int cb, int dtype, void *stream);
+int dlwpcs_up2cat_bwd(const void *dt, void *da, void *db, int batch, int n, int ca, int cb, int dtype, void *stream);
+
 /* Training-step helpers on flat float32 buffers (the engine keeps all parameters / gradients of a model in one buffer so
  * that data-parallel training needs a single all-reduce).
  *   dlwpcs_mse_loss_grad: keras 'mse' (Azure/train_cs.py:424): adds sum((y-t)^2) * inv_count to *loss_accum (device

@@ -224,3 +224,38 @@ def test_errors(cs):
     with pytest.raises(lib.DlwpcsError):
         layer = pkg.CubeSphereConv2D(4, 9, data_format='channels_last', in_channels=3).cuda()
         layer(torch.zeros(1, 6, 8, 8, 3).cuda())                              # kernel larger than the face
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_resampling_kernels_vs_oracle(cs, dtype):
+    """dlwpcs_pool2 / dlwpcs_up2cat_fwd / _bwd (AveragePooling3D((1,2,2)), UpSampling3D((1,2,2)) + concatenate,
+    train_cs.py:197-198, 293) against the oracle's slicing restatement, forward and adjoint."""
+    from dlwp_cs_b200 import functional as F
+    g = torch.Generator().manual_seed(17)
+    b, n, ca, cb = 2, 8, 16, 8
+    x = torch.randn(b, 6, 2 * n, 2 * n, cb, generator=g).to(dtype)
+    a = torch.randn(b, 6, n // 2, n // 2, ca, generator=g).to(dtype)
+    bb = torch.randn(b, 6, n, n, cb, generator=g).to(dtype)
+    tol = 1e-6 if dtype == torch.float32 else 2.0 ** -8
+
+    def close(u, v):
+        np.testing.assert_allclose(u.double().cpu().numpy(), v.double().numpy(), rtol=tol, atol=tol)
+    # forward
+    xc = x.cuda().requires_grad_(True)
+    y = F.avg_pool_2x2(xc)
+    close(y.detach(), O.avg_pool_2x2(x.double()))
+    ac, bc = a.cuda().requires_grad_(True), bb.cuda().requires_grad_(True)
+    t = F.upsample_concat(ac, bc)
+    assert torch.equal(t.detach().cpu(), torch.cat([O.upsample_2x2(a), bb], dim=-1))
+    # adjoints against autograd of the oracle
+    gy = torch.randn(y.shape, generator=g).to(dtype)
+    gt = torch.randn(t.shape, generator=g).to(dtype)
+    y.backward(gy.cuda())
+    t.backward(gt.cuda())
+    xo = x.double().requires_grad_(True)
+    O.avg_pool_2x2(xo).backward(gy.double())
+    ao, bo = a.double().requires_grad_(True), bb.double().requires_grad_(True)
+    torch.cat([O.upsample_2x2(ao), bo], dim=-1).backward(gt.double())
+    close(xc.grad, xo.grad)
+    np.testing.assert_allclose(ac.grad.double().cpu().numpy(), ao.grad.numpy(), rtol=tol, atol=4 * tol)
+    assert torch.equal(bc.grad.cpu().double(), bo.grad)
