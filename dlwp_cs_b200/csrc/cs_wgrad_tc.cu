@@ -266,9 +266,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const uint32_t swy = (uint32_t)(L.RBy / 16 - 1);
     const uint32_t yblk = (uint32_t)(chy / (L.RBy / 16)), ycw = (uint32_t)(chy % (L.RBy / 16));
     const bool direct = L.vecy && !P.mask_y;
+    const bool want_bias = cb == 0 && P.ws_b != nullptr;
     float bsum[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) bsum[e] = 0.f;
+    uint32_t prev_ybase = 0;
+    // add this thread's own chunks of one dy tile (zero rows included: they add nothing) to its bias partial sums
+    auto readback = [&](uint32_t yb_s) {
+      for (int i = lt >> L.logSy; i < L.TP; i += psty) {
+        const uint32_t row = yb_s + (uint32_t)i * L.RBy;
+        uint4 v4;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v4.x), "=r"(v4.y), "=r"(v4.z), "=r"(v4.w)
+                     : "r"(row + ((ycw ^ ((row >> 7) & swy)) << 4)));
+        float f[8];
+        unpack_bf16x8(v4, f);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) bsum[c] += f[c];
+      }
+    };
     int s = 0, ph = 0;
     for (int k = 0; k < my_tiles; ++k) {
       int b, f, tf;
@@ -280,7 +295,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       const uint32_t ybase = st_addr + (uint32_t)L.xBytes + yblk * (uint32_t)L.yBlockBytes;
       if (P.knock & 2) {
       } else if (direct) {
-        // no mask: 16-byte cp.async straight into the tile (the bias sums come from bias_sum_kernel)
+        // no mask: 16-byte cp.async straight into the tile.  The bias partial sums are taken from shared memory one tile
+        // later: every thread reads back the chunks it copied itself once its previous copy group has landed.
         for (int i0 = lt >> L.logSy; i0 < L.TP; i0 += 8 * psty) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -293,6 +309,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
               cp_async16(row + ((ycw ^ ((row >> 7) & swy)) << 4), g, ok ? 16u : 0u);
             }
           }
+        }
+        if (want_bias) {
+          cp_async_commit();
+          if (k > 0) {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            readback(prev_ybase);
+          }
+          prev_ybase = ybase;
         }
       } else
       for (int i0 = lt >> L.logSy; i0 < L.TP; i0 += 8 * psty) {
@@ -344,8 +368,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       cp_async_mbar_arrive(bar_full + 8 * s);
       if (++s == L.PS) { s = 0; ph ^= 1; }
     }
+    if (direct && want_bias && my_tiles > 0 && !(P.knock & 2)) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      readback(prev_ybase);
+    }
     // ---- bias partials of this CTA (only the cin-block-0 jobs report them): fixed-order sum over the dy loaders
-    if (cb == 0 && P.ws_b && !direct) {
+    if (want_bias) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) s_bsum[lt * 8 + e] = bsum[e];
       named_bar_sync(1, WG_YL);
@@ -386,62 +414,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   if (warp == WG_MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)L.tmemCols);
-}
-
-// Bias partial sums for the un-masked (cp.async) dy path: virtual CTA (job with cin block 0, index ic) sums the dy rows of
-// exactly the tiles the wgrad CTA of that index owns, per-thread in tile order and then over the threads in a fixed
-// order, into ws_b[cta][NJ] -- the layout the reduce kernel reads.
-__global__ void __launch_bounds__(256) bias_sum_kernel(const __grid_constant__ WgP P) {
-  __shared__ float s_b[256 * 8];
-  const WgPlan &L = P.pl;
-  const int ngi = blockIdx.x / L.nc, ic = blockIdx.x - ngi * L.nc;
-  int grp = 0, idx = ic, nin = L.ng[0];
-  if (ic >= L.ng[0] + L.ng[1]) { grp = 2; idx = ic - L.ng[0] - L.ng[1]; nin = L.ng[2]; }
-  else if (ic >= L.ng[0]) { grp = 1; idx = ic - L.ng[0]; nin = L.ng[1]; }
-  const int T = (grp == 0 ? 4 : 1) * P.batch * L.tpf;
-  const int my_tiles = idx < T ? (T - idx + nin - 1) / nin : 0;
-  const int lt = threadIdx.x, Sy = L.NJ / 8, chy = lt & (Sy - 1), cy = ngi * L.NJ + chy * 8, pst = 256 >> L.logSy;
-  const bool oky = cy < P.cout;
-  float bsum[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) bsum[e] = 0.f;
-  for (int k = 0; k < my_tiles; ++k) {
-    const int t = idx + k * nin;
-    int b, f, tf;
-    if (grp == 0) { const int bf = t / L.tpf; tf = t - bf * L.tpf; b = bf >> 2; f = bf & 3; }
-    else { b = t / L.tpf; tf = t - b * L.tpf; f = 3 + grp; }
-    const int q0 = tf * L.TP;
-    const size_t yb = (size_t)(b * 6 + f) * P.ppfy;
-    for (int i0 = lt >> L.logSy; i0 < L.TP; i0 += 8 * pst) {
-      uint4 dv[8];
-      bool ok[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int i = i0 + e * pst, q = q0 + i;
-        const int r = q / L.Wv, c = q - r * L.Wv;
-        ok[e] = i < L.TP && oky && r < P.Ho && c < P.Wo;
-        if (ok[e]) dv[e] = __ldg(reinterpret_cast<const uint4 *>(P.dy + (yb + (size_t)(r * P.Wo + c)) * P.cout + cy));
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        if (ok[e]) {
-          float v[8];
-          unpack_bf16x8(dv[e], v);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) bsum[c] += v[c];
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < 8; ++e) s_b[lt * 8 + e] = bsum[e];
-  __syncthreads();
-  if (lt < L.NJ) {
-    const int ch = lt >> 3, e = lt & 7;
-    float acc = 0.f;
-    for (int th = ch; th < 256; th += Sy) acc += s_b[th * 8 + e];
-    P.ws_b[(size_t)(ngi * L.NCB * L.nc + ic) * L.NJ + lt] = acc;
-  }
 }
 
 // second pass: fixed-order sum of the CTA partials of each (job, face group); un-flip / merge the north-pole share.
@@ -681,7 +653,6 @@ int tc_conv_wgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, 
   }
   kerns[ki]<<<L.ncta, WG_THREADS, L.smemBytes, st>>>(P);
   CS_CUDA(cudaGetLastError());
-  if (d->use_bias && L.vecy && !P.mask_y) bias_sum_kernel<<<L.NNG * L.nc, 256, 0, st>>>(P);
   CS_CUDA(cudaGetLastError());
   const long long total = (long long)g.taps * d->cin * d->cout + d->cout;
   wgrad_tc_reduce_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(
