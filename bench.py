@@ -392,7 +392,14 @@ def main():
                 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'train': train, 'layers': layers}
         print(json.dumps(line), flush=True)
     if dist is not None:
-        dist.destroy_process_group()
+        # the captured training step holds NCCL kernels: tearing the communicator down under a live CUDA graph can block
+        # (observed: the process hung in destroy_process_group after the result line).  Everything is measured and printed;
+        # synchronise the ranks and leave without the communicator teardown.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':
