@@ -103,3 +103,41 @@ def test_layer_constructors_mirror_reference():
         CubeSphereConv2D(4, 3, padding='full')
     with pytest.raises(TypeError):
         CubeSphereConv2D(4, 3, bogus=1)
+
+
+def test_wgrad_plan_workspace_host_logic(lib):
+    """Host side of the tcgen05 wgrad plan (no GPU needed): every unet2 layer shape at the training batch gets a plan whose
+    workspace holds one accumulator image per CTA; shapes outside the kernel's reach (horizontal dilation, windows whose
+    accumulators exceed tensor memory) fall back to the float32 kernel's workspace; strides are refused like the
+    reference-free backward contract says."""
+    import ctypes
+    L = lib.load()
+    shapes = [(48, 18, 32, 3), (48, 32, 32, 3), (24, 32, 64, 3), (24, 64, 64, 3), (12, 64, 128, 3), (12, 128, 64, 3),
+              (24, 128, 64, 3), (24, 64, 32, 3), (48, 64, 32, 3), (48, 32, 14, 1)]
+    for n, ci, co, k in shapes:
+        d = lib.make_desc(32, n, ci, co, (k, k), (1, 1), (1, 1), 1 if k == 3 else 0, False, True, False, True,
+                          lib.ACT_NONE, 0.1, 10.0, lib.BF16, lib.BF16)
+        nbytes = L.dlwpcs_wgrad_workspace_bytes(ctypes.byref(d))
+        assert nbytes > 0, (n, ci, co, k)
+        # 148 CTAs (or fewer) x accumulators x 128 lanes x N fp32 + bias partials: a few tens of MB at most
+        assert nbytes < 64 << 20, (n, ci, co, k, nbytes)
+        d32 = lib.copy_desc(d, x_dtype=lib.F32, y_dtype=lib.F32)
+        assert L.dlwpcs_wgrad_workspace_bytes(ctypes.byref(d32)) > 0
+    # horizontal dilation: not stackable along M -> float32 kernel's (different) workspace, still served
+    dd = lib.make_desc(2, 12, 16, 16, (3, 3), (1, 1), (1, 2), 0, True, True, False, True, lib.ACT_NONE, 0.1, 10.0, lib.BF16,
+                       lib.BF16)
+    assert L.dlwpcs_wgrad_workspace_bytes(ctypes.byref(dd)) > 0
+    ds = lib.make_desc(2, 12, 16, 16, (3, 3), (2, 2), (1, 1), 0, False, True, False, True, lib.ACT_NONE, 0.1, 10.0, lib.BF16,
+                       lib.BF16)
+    assert L.dlwpcs_wgrad_workspace_bytes(ctypes.byref(ds)) < 0
+    assert b'stride' in L.dlwpcs_last_error()
+
+
+def test_reference_input_order_and_solar_days_host_logic():
+    """reference_input_order: the reference's channel packing (generators.py:880-899) as engine slots; a permutation whose
+    inverse puts the prognostic channels first."""
+    from dlwp_cs_b200.unet import reference_input_order
+    order = reference_input_order(2, 7, 2)
+    assert sorted(order) == list(range(18))
+    assert order[:7] == list(range(7)) and order[7] == 14 and order[8:15] == list(range(7, 14)) and order[15] == 15
+    assert order[16:] == [16, 17]
