@@ -259,3 +259,24 @@ def test_tc_rollout_c96_12var_vs_oracle(lib):
     torch.cuda.synchronize()
     err = (out.double().cpu() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 3e-2, err
+
+
+def test_tc_conv_ragged_tiles_many_per_cta(lib):
+    """A face whose m-blocks do not divide evenly into tiles (19 = 4+4+4+4+3 at C48) with enough images that every CTA
+    walks many tiles: exercises the per-m-block accumulator barriers across short last tiles (a phase slip deadlocks or
+    reads a stale accumulator)."""
+    y_ref = None
+    for batch in (40,):
+        g = torch.Generator().manual_seed(3)
+        x = bf(torch.randn(batch, 6, 48, 48, 32, generator=g))
+        ws = [bf(torch.randn(3, 3, 32, 32, generator=g) * 0.1).float() for _ in range(2)]
+        bs = [torch.randn(32, generator=g) * 0.1 for _ in range(2)]
+        d = lib.make_desc(batch, 48, 32, 32, (3, 3), (1, 1), (1, 1), 1, False, True, False, True, lib.ACT_CAPPED_LEAKY_RELU,
+                          0.1, 10.0, lib.BF16, lib.BF16)
+        packed = lib.pack_weights(d, ws[0].cuda(), ws[1].cuda(), None, bs[0].cuda(), bs[1].cuda(), None)
+        y = lib.conv2d_fwd(d, x.cuda(), None, packed)
+        torch.cuda.synchronize()
+        sel = [0, 17, batch - 1]                         # oracle on three images only (float64 CPU)
+        ref = O.capped_leaky_relu(O.cube_sphere_conv2d(O.cube_sphere_pad(x[sel].double(), 1), ws[0].double(), ws[1].double(),
+                                                       None, bs[0].double(), bs[1].double(), None))
+        check(y[sel], ref, stored_bf16=True)
