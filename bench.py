@@ -23,9 +23,18 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, 'oracle')):
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def _oracle():
+    """The CPU restatement under oracle/ -- imported by the two CPU legs only (cpu_baseline, --impl reference); the GPU
+    arm never touches it."""
+    p = os.path.join(ROOT, 'oracle')
     if p not in sys.path:
         sys.path.insert(0, p)
+    import cs_oracle
+    return cs_oracle
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -103,7 +112,7 @@ def synth_inputs(batch, seed=0):
 
 def cpu_rollout_rate(batch, steps, threads, repeats=1):
     """The reference path's CPU restatement: oracle rollout, oneDNN conv, numpy hop per step.  -> sample-steps/s"""
-    import cs_oracle as O
+    O = _oracle()
     torch.set_num_threads(threads)
     params = O.make_unet2_params(C_PROG + C_FORC, C_PROG, base=BASE, seed=1)
     state, forcing = synth_inputs(batch)
@@ -123,7 +132,7 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     b, s = args.ref_batch, args.ref_steps
-    import cs_oracle as O
+    O = _oracle()
     torch.set_num_threads(threads)
     params = O.make_unet2_params(C_PROG + C_FORC, C_PROG, base=BASE, seed=1)
     state, forcing = synth_inputs(b)
@@ -203,8 +212,7 @@ def main():
         return
 
     from dlwp_cs_b200 import _lib
-    from dlwp_cs_b200.unet import CubeSphereUNet2, RolloutEngine
-    import cs_oracle as O
+    from dlwp_cs_b200.unet import CubeSphereUNet2, RolloutEngine, unet2_layer_specs
     _lib.load()
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
@@ -222,9 +230,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    params = O.make_unet2_params(C_PROG + C_FORC, C_PROG, base=BASE, seed=1)
+    torch.manual_seed(1)                      # random-init weights of the architecture (glorot-uniform kernels, zero biases)
     model = CubeSphereUNet2(C_PROG + C_FORC, C_PROG, base=BASE).to(dev)
-    model.load_oracle_params(params)
     dtype = args.dtype
     eng = None
     if dtype in ('auto', 'bf16'):
@@ -297,7 +304,7 @@ def main():
     if rank == 0:
         pk = peaks()
         lt = time_layers(eng)
-        specs = {s[0]: s for s in O.unet2_shapes(C_PROG + C_FORC, C_PROG, BASE)}
+        specs = {s[0]: s for s in unet2_layer_specs(C_PROG + C_FORC, C_PROG, BASE)}
         edges = {name: d.n for name, d, *_ in eng.plan}
         tot = sum(ms for _, ms in lt)
         for name, ms in lt:
@@ -334,8 +341,8 @@ def main():
         del eng, flush
         torch.cuda.empty_cache()
         from dlwp_cs_b200.train import DataParallelTrainer
+        torch.manual_seed(1)
         tmodel = CubeSphereUNet2(C_PROG + C_FORC, C_PROG, base=BASE).to(dev)
-        tmodel.load_oracle_params(params)
         trainer = DataParallelTrainer(tmodel, lr=1e-3)
         g = torch.Generator().manual_seed(100 + rank)
         tb = args.train_batch

@@ -2,7 +2,7 @@
 C ABI.  One JSON line."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, 'oracle')]
+sys.path[:0] = [ROOT]
 import torch
 from dlwp_cs_b200 import _lib
 from dlwp_cs_b200.unet import unet2_layer_specs

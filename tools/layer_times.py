@@ -2,19 +2,17 @@
 Used with DLWPCS_TC_KNOCK=<mask> for knock-out bottleneck analysis (timings under a knock-out are not results)."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, 'oracle')]
+sys.path[:0] = [ROOT]
 import torch
 import bench as B
-import cs_oracle as O
 from dlwp_cs_b200 import _lib
 from dlwp_cs_b200.unet import CubeSphereUNet2, RolloutEngine
 _lib.load()
 dev = torch.device('cuda:0')
 n = int(os.environ.get('N_FACE', '48'))
 batch = int(os.environ.get('BATCH', '64'))
-params = O.make_unet2_params(18, 14, base=32, seed=1)
 model = CubeSphereUNet2(18, 14, base=32).to(dev)
-model.load_oracle_params(params)
+torch.manual_seed(1)
 eng = RolloutEngine(model, batch, n, 2, forcing_channels=4, dtype=torch.bfloat16, use_graph=False)
 g = torch.Generator().manual_seed(0)
 eng.load_inputs(torch.randn(batch, 6, n, n, 14, generator=g), torch.rand(batch, 6, n, n, 4, generator=g))

@@ -2,9 +2,8 @@
 backward kernels (wgrad / dgrad / halo scatter-add)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, 'oracle')]
+sys.path[:0] = [ROOT]
 import torch
-import cs_oracle as O
 from dlwp_cs_b200 import _lib
 from dlwp_cs_b200.unet import CubeSphereUNet2
 from dlwp_cs_b200.train import DataParallelTrainer
@@ -12,7 +11,7 @@ _lib.load()
 dev = torch.device('cuda:0')
 tb = int(os.environ.get('BATCH', '32'))
 m = CubeSphereUNet2(18, 14, base=32).to(dev)
-m.load_oracle_params(O.make_unet2_params(18, 14, base=32, seed=1))
+torch.manual_seed(1)
 tr = DataParallelTrainer(m, lr=1e-3, use_graph=False)
 g = torch.Generator().manual_seed(1)
 xs = torch.randn(tb, 6, 48, 48, 18, generator=g).to(dev).bfloat16()

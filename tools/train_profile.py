@@ -1,9 +1,8 @@
 """Kernel-level breakdown of one training step (unet2 C48, batch 32, bf16) with torch.profiler (CUPTI)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, 'oracle')]
+sys.path[:0] = [ROOT]
 import torch
-import cs_oracle as O
 from dlwp_cs_b200 import _lib
 from dlwp_cs_b200.unet import CubeSphereUNet2
 from dlwp_cs_b200.train import DataParallelTrainer
@@ -11,9 +10,8 @@ _lib.load()
 dev = torch.device('cuda:0')
 tb = int(os.environ.get('BATCH', '32'))
 dt = torch.bfloat16 if os.environ.get('DTYPE', 'bf16') == 'bf16' else torch.float32
-params = O.make_unet2_params(18, 14, base=32, seed=1)
 m = CubeSphereUNet2(18, 14, base=32).to(dev)
-m.load_oracle_params(params)
+torch.manual_seed(1)
 tr = DataParallelTrainer(m, lr=1e-3)
 g = torch.Generator().manual_seed(1)
 xs = torch.randn(tb, 6, 48, 48, 18, generator=g).to(dev).to(dt)

@@ -1,7 +1,7 @@
 """Knock-out timing of the tcgen05 wgrad kernel (DLWPCS_WG_KNOCK=<mask>) for two layer shapes; graph-timed."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, 'oracle')]
+sys.path[:0] = [ROOT]
 import torch
 from dlwp_cs_b200 import _lib
 _lib.load()
