@@ -891,6 +891,10 @@ int launch_tc(TcP &P, cudaStream_t st) {
   CS_CHECK(ntiles < (1LL << 30), "batch too large");
   int grid = num_sms();
   if (grid > ntiles) grid = (int)ntiles;
+  // CTA c walks tiles c, c + grid, ...: when the tiles of a face differ in size (e.g. 5 m-blocks = 3 + 2) and grid and
+  // tiles-per-face share a factor, some CTAs would only ever see the large tiles -- keep the two coprime
+  auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+  while (grid > 1 && L.nmb % L.MB != 0 && gcd(grid, L.tpf) != 1) --grid;
   static const int timing = env_int("DLWPCS_TC_TIMING", 0);
   static const int knock = env_int("DLWPCS_TC_KNOCK", 0);
   P.knock = knock;
