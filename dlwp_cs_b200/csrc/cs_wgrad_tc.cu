@@ -563,6 +563,15 @@ const char *make_wg_plan(const dlwpcs_conv_desc *d, const Geometry &g, WgPlan *L
   if (best > nmb) best = nmb;
   const int tiles = (nmb + best - 1) / best;
   best = (nmb + tiles - 1) / tiles;                 // even out the tiles of a face
+  if (forced <= 0) {
+    // tiles are uniform (positions beyond the face are zero rows that still cost MMAs): take a smaller tile when it
+    // removes at least 10 % of the padded 128-blocks (5 blocks at 24x24: 5 tiles of 1 instead of 2 tiles of 3)
+    const int padded = (nmb + best - 1) / best * best;
+    for (int tpb = best - 1; tpb >= 1; --tpb) {
+      const int p2 = (nmb + tpb - 1) / tpb * tpb;
+      if (10 * p2 <= 9 * padded) { best = tpb; break; }
+    }
+  }
   L->TPB = best;
   L->TP = best * 128;
   L->tpf = (nmb + best - 1) / best;
