@@ -73,6 +73,33 @@ class CubeSphereUNet2(nn.Module):
         t = self.conv_2d_7_2(self.conv_2d_7(upcat(t, x0)))
         return self.conv_2d_8(t)
 
+    # ---- weight interop with the reference's Keras model ----------------------------------------
+    def get_weights(self):
+        """numpy arrays in the order ``keras.Model.get_weights()`` returns them for the reference's ``unet2`` built by
+        Azure/train_cs.py:277-305: layers in creation order (conv_2d_1, conv_2d_1_2, ..., output), each layer in its
+        ``add_weight`` order (custom.py:882-914: equatorial_kernel, polar_kernel, [north_pole_kernel,] equatorial_bias,
+        polar_bias[, north_pole_bias]); kernels HWIO."""
+        out = []
+        for layer in self.layers_in_order():
+            out += layer.get_weights()
+        return out
+
+    def set_weights(self, weights):
+        """Inverse of ``get_weights``: takes the list a reference checkpoint yields (``model.get_weights()`` /
+        the arrays of its h5 file in the same order)."""
+        weights = list(weights)
+        per = 6 if self.independent_north_pole else 4
+        layers = self.layers_in_order()
+        if len(weights) != per * len(layers):
+            raise ValueError('expected %d weight arrays (%d layers x %d), got %d' % (per * len(layers), len(layers), per,
+                                                                                      len(weights)))
+        for i, layer in enumerate(layers):
+            chunk = weights[per * i:per * (i + 1)]
+            want = (layer.kernel_size[0], layer.kernel_size[1], layer.equatorial_kernel.shape[2], layer.filters)
+            if tuple(chunk[0].shape) != want:
+                raise ValueError('layer %d: kernel shape %r, expected %r (HWIO)' % (i, tuple(chunk[0].shape), want))
+            layer.set_weights(chunk)
+
     def load_oracle_params(self, params):
         """params: dict 'layer.equatorial_kernel' -> tensor, as produced by oracle.make_unet2_params (tests / bench)."""
         with torch.no_grad():

@@ -141,3 +141,26 @@ def test_reference_input_order_and_solar_days_host_logic():
     assert sorted(order) == list(range(18))
     assert order[:7] == list(range(7)) and order[7] == 14 and order[8:15] == list(range(7, 14)) and order[15] == 15
     assert order[16:] == [16, 17]
+
+
+def test_unet2_keras_weight_order_roundtrip():
+    """CubeSphereUNet2.get_weights / set_weights use the reference's Keras ordering (layers in creation order,
+    custom.py:882-914 add_weight order inside a layer) -- host logic, parameters on the CPU."""
+    from dlwp_cs_b200.unet import CubeSphereUNet2
+    torch.manual_seed(0)
+    a = CubeSphereUNet2(18, 14, base=8)
+    w = a.get_weights()
+    assert len(w) == 44
+    assert w[0].shape == (3, 3, 18, 8) and w[1].shape == (3, 3, 18, 8) and w[2].shape == (8,) and w[3].shape == (8,)
+    assert w[40].shape == (1, 1, 8, 14) and w[43].shape == (14,)
+    assert sum(x.size for x in CubeSphereUNet2(18, 14, base=32).get_weights()) == 675932      # SURVEY.md section 8 a4
+    b = CubeSphereUNet2(18, 14, base=8)
+    b.set_weights([x + 1.0 for x in w])
+    for x, y in zip(w, b.get_weights()):
+        np.testing.assert_array_equal(x + 1.0, y)
+    with pytest.raises(ValueError):
+        b.set_weights(w[:-1])
+    with pytest.raises(ValueError):
+        b.set_weights([w[1].transpose(3, 2, 0, 1)] + w[1:])
+    c = CubeSphereUNet2(18, 14, base=8, independent_north_pole=True)
+    assert len(c.get_weights()) == 66
