@@ -35,13 +35,31 @@ class FlatBuffers(object):
         self.param = torch.empty(self.count, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(self.count, dtype=torch.float32, device=dev)
         off = 0
+        self.grad_views = []
         for p in params:
             n = p.numel()
             self.param[off:off + n].copy_(p.detach().reshape(-1))
             p.data = self.param[off:off + n].view(p.shape)
-            p.grad = self.grad[off:off + n].view(p.shape)
+            self.grad_views.append(self.grad[off:off + n].view(p.shape))
+            p.grad = self.grad_views[-1]
             off += n
         self.params = params
+
+    def collect_grads(self):
+        """Gather freshly produced per-parameter gradients (``p.grad`` tensors that are not views of the flat buffer) into
+        the flat buffer with one multi-tensor copy and re-point ``p.grad`` at the views.  Used by the trainer, which clears
+        ``p.grad`` before backward so that autograd hands the gradients over instead of launching one accumulation kernel
+        per parameter."""
+        src, dst = [], []
+        for p, v in zip(self.params, self.grad_views):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                src.append(p.grad)
+                dst.append(v)
+            p.grad = v
+        if src:
+            torch._foreach_copy_(dst, src)
 
     def zero_grad(self):
         self.grad.zero_()
@@ -94,11 +112,13 @@ class DataParallelTrainer(object):
 
     def forward_backward(self, x, target):
         """Gradients of mean((model(x) - target)^2) accumulated into the flat buffer; returns the loss (device scalar)."""
-        self.flat.zero_grad()
         self.loss.zero_()
+        for p in self.flat.params:          # every parameter is used exactly once: take the gradients, do not accumulate
+            p.grad = None
         y = self.model(x)
         dy = _lib.mse_loss_grad(y.detach(), target, self.loss)
         y.backward(dy)
+        self.flat.collect_grads()
         return self.loss
 
     def _step_body(self, x, target):

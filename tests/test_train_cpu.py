@@ -89,3 +89,30 @@ def test_gloo_all_reduce_matches_single_process(tmp_path):
     (net(x) - t).pow(2).mean().backward()                      # equal shards: mean of shard means == global mean
     assert torch.equal(got['param'], flat.param)
     assert torch.allclose(got['grad'], flat.grad, atol=1e-6)
+
+
+def test_flat_buffers_collect_grads_cpu():
+    """FlatBuffers.collect_grads: gradients handed over by autograd (p.grad cleared before backward) end up in the flat
+    buffer, p.grad points at the flat views again, parameters without a gradient read as zero."""
+    import torch
+    from dlwp_cs_b200.train import FlatBuffers
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Linear(4, 3))
+    unused = torch.nn.Parameter(torch.ones(2))
+    m.register_parameter('unused', unused)
+    fb = FlatBuffers(m)
+    x = torch.randn(7, 5)
+    ref = torch.autograd.grad(m(x).pow(2).sum(), [p for p in m.parameters() if p is not unused])
+    fb.grad.fill_(123.0)
+    for p in fb.params:
+        p.grad = None
+    m(x).pow(2).sum().backward()
+    fb.collect_grads()
+    off = 0
+    it = iter(ref)
+    for p, v in zip(fb.params, fb.grad_views):
+        assert p.grad.data_ptr() == v.data_ptr()
+        n = p.numel()
+        want = torch.zeros_like(p) if p is unused else next(it)
+        assert torch.equal(fb.grad[off:off + n].view(p.shape), want)
+        off += n
