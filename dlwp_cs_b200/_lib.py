@@ -68,6 +68,7 @@ def load():
         'dlwpcs_pool2': (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
         'dlwpcs_up2cat_fwd': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         'dlwpcs_up2cat_bwd': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+        'dlwpcs_feed_gather': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
         'dlwpcs_insolation': (i32, [vp, i32, i32, i64, i32, i32, i32, vp, vp, vp, vp, f32, vp]),
         'dlwpcs_adam_step_dev': (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp]),
     }
@@ -85,7 +86,7 @@ EXPORTED = ('dlwpcs_version', 'dlwpcs_last_error', 'dlwpcs_conv_out_edge', 'dlwp
             'dlwpcs_dgrad_workspace_bytes', 'dlwpcs_conv2d_dgrad', 'dlwpcs_wgrad_workspace_bytes',
             'dlwpcs_conv2d_wgrad', 'dlwpcs_act_fwd', 'dlwpcs_act_bwd', 'dlwpcs_conv2d_fwd_host',
             'dlwpcs_mse_loss_grad', 'dlwpcs_adam_step', 'dlwpcs_adam_step_dev', 'dlwpcs_insolation', 'dlwpcs_pool2',
-            'dlwpcs_up2cat_fwd', 'dlwpcs_up2cat_bwd')
+            'dlwpcs_up2cat_fwd', 'dlwpcs_up2cat_bwd', 'dlwpcs_feed_gather')
 
 
 class DlwpcsError(RuntimeError):

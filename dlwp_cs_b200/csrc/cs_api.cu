@@ -500,6 +500,54 @@ __global__ void up2cat_bwd_kernel(const uint4 *__restrict__ dt, uint4 *__restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// device-side data feed: ArrayDataGenerator.generate (DLWP/model/generators.py:872-984; convolutional, channels_last, no
+// sequence) as one transposing gather.  The training array (time, varlev, P) stays in HBM in the reference's layout (one
+// plane of P = 6*N*N pixels per variable); a batch is read plane-wise (coalesced along the pixels), transposed in shared
+// memory and written channels_last (coalesced along the channels).  blockIdx.z = 0: predictors, 1: targets.
+// ---------------------------------------------------------------------------------------------------------------------
+struct FeedP {
+  const float *array, *insol, *consts;     // (T, V, P), (T, P) or null, (n_const, P) or null
+  const long long *samples;                // (B)
+  const int *in_vars, *out_vars;           // variable indices of the input / output selections
+  void *x, *y;                             // (B, P, cx), (B, P, cy)
+  long long P;
+  int V, v_in, v_out, t_in, t_out, interval, n_const, has_sol, cx, cy, out_bf16;
+};
+
+__global__ void __launch_bounds__(256) feed_gather_kernel(const __grid_constant__ FeedP F) {
+  extern __shared__ float tile[];          // [32 pixels][C + 1]
+  const bool tgt = blockIdx.z == 1;
+  const int C = tgt ? F.cy : F.cx, ld = C + 1;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int b = blockIdx.y, px = threadIdx.x & 31, cl = threadIdx.x >> 5;
+  const long long s = F.samples[b];
+  const int per_t = F.v_in + F.has_sol;
+  for (int c = cl; c < C; c += 8) {
+    const float *plane;
+    if (tgt) {
+      const int t = c / F.v_out, v = c - t * F.v_out;
+      plane = F.array + ((s + (long long)F.interval * (F.t_in + t)) * F.V + F.out_vars[v]) * F.P;
+    } else if (c < F.t_in * per_t) {
+      const int t = c / per_t, v = c - t * per_t;
+      const long long time = s + (long long)t * F.interval;
+      plane = v < F.v_in ? F.array + (time * F.V + F.in_vars[v]) * F.P : F.insol + time * F.P;
+    } else {
+      plane = F.consts + (long long)(c - F.t_in * per_t) * F.P;
+    }
+    tile[px * ld + c] = p0 + px < F.P ? __ldg(plane + p0 + px) : 0.f;
+  }
+  __syncthreads();
+  const int npx = (int)((F.P - p0) < 32 ? (F.P - p0) : 32);
+  void *out = tgt ? F.y : F.x;
+  const long long base = ((long long)b * F.P + p0) * C;
+  for (int i = threadIdx.x; i < npx * C; i += 256) {
+    const float v = tile[(i / C) * ld + (i % C)];
+    if (F.out_bf16) reinterpret_cast<__nv_bfloat16 *>(out)[base + i] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float *>(out)[base + i] = v;
+  }
+}
+
 }  // namespace dlwpcs
 
 using namespace dlwpcs;
@@ -689,6 +737,31 @@ int dlwpcs_up2cat_bwd(const void *dt, void *da, void *db, int batch, int n, int 
   else
     up2cat_bwd_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>((const uint4 *)dt, (uint4 *)da, (uint4 *)db, n, va, vb,
                                                                             total_a, total);
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dlwpcs_feed_gather(const float *array, const float *insolation, const float *constants, const int64_t *samples,
+                       const int32_t *in_vars, const int32_t *out_vars, void *x, void *y, int batch, int64_t npix,
+                       int n_var, int v_in, int v_out, int t_in, int t_out, int interval, int n_const, int dtype,
+                       void *stream) {
+  CS_CHECK(elem_size(dtype) != 0 && array && samples && in_vars && out_vars && x && y, "null pointer / bad dtype in dlwpcs_feed_gather");
+  CS_CHECK(batch >= 0 && npix > 0 && n_var > 0 && v_in > 0 && v_out > 0 && t_in > 0 && t_out > 0 && interval > 0 &&
+               n_const >= 0 && (n_const == 0 || constants),
+           "bad arguments to dlwpcs_feed_gather");
+  if (batch == 0) return 0;
+  FeedP F;
+  F.array = array; F.insol = insolation; F.consts = constants;
+  F.samples = (const long long *)samples; F.in_vars = in_vars; F.out_vars = out_vars;
+  F.x = x; F.y = y; F.P = npix; F.V = n_var; F.v_in = v_in; F.v_out = v_out; F.t_in = t_in; F.t_out = t_out;
+  F.interval = interval; F.n_const = n_const; F.has_sol = insolation ? 1 : 0;
+  F.cx = t_in * (v_in + F.has_sol) + n_const;
+  F.cy = t_out * v_out;
+  F.out_bf16 = dtype == DLWPCS_BF16;
+  const int cmax = F.cx > F.cy ? F.cx : F.cy;
+  CS_CHECK(cmax <= 1024, "more than 1024 channels per sample");
+  dim3 grid((unsigned)((npix + 31) / 32), (unsigned)batch, 2);
+  feed_gather_kernel<<<grid, 256, (size_t)32 * (cmax + 1) * sizeof(float), (cudaStream_t)stream>>>(F);
   CS_CUDA(cudaGetLastError());
   return 0;
 }

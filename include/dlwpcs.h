@@ -144,6 +144,19 @@ int dlwpcs_insolation(void *out, int dtype, int batch, int64_t npix, int c_total
                       const double *sinlat, const double *coslat, const float *lon, const double *days, float S,
                       void *stream);
 
+/* Device-side data feed: ArrayDataGenerator.generate (DLWP/model/generators.py:872-984; convolutional model,
+ * channels_last, no sequence) for one batch of sample indices, with the training array resident in HBM in the reference's
+ * own layout.  array (T, n_var, npix) float32, insolation (T, npix) or NULL, constants (n_const, npix) or NULL, all device;
+ * samples (batch) int64 start times; in_vars / out_vars: variable indices of the input / output selections (device int32).
+ *   x (batch, npix, t_in*(v_in + has_insolation) + n_const):  channel t*(v_in+1)+v = array[s + t*interval, in_vars[v]],
+ *       insolation last within each time step (generators.py:880-899), constants appended (train_cs.py:396-407);
+ *   y (batch, npix, t_out*v_out):  channel t*v_out+v = array[s + interval*(t_in + t), out_vars[v]]  (generators.py:943-946).
+ * dtype = element type of x and y (float32 or bf16).                                                                   */
+int dlwpcs_feed_gather(const float *array, const float *insolation, const float *constants, const int64_t *samples,
+                       const int32_t *in_vars, const int32_t *out_vars, void *x, void *y, int batch, int64_t npix,
+                       int n_var, int v_in, int v_out, int t_in, int t_out, int interval, int n_const, int dtype,
+                       void *stream);
+
 /* Host-buffer entry point: the call a reference-side binding makes with numpy arrays.  Copies x (and weights) to the
  * device, runs pad(halo)+conv, copies y back; synchronous.                                                            */
 int dlwpcs_conv2d_fwd_host(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, const void *x_host, void *y_host);

@@ -300,6 +300,7 @@ def install():
     kmodels = mod('tensorflow.keras.models')              # DLWP/util.py imports these two names at module level
     kutils = mod('tensorflow.keras.utils')
     kutils.multi_gpu_model = lambda model, gpus=None: model
+    kutils.Sequence = type('Sequence', (object,), {})        # base class of the reference's data generators
     keras.models, keras.utils = kmodels, kutils
     for nm, table in (('activations', {'linear': _linear, 'relu': _relu}),
                       ('initializers', {'glorot_uniform': _glorot_uniform, 'zeros': _zeros}),
@@ -345,3 +346,25 @@ def load_reference_util(path='/root/reference/DLWP/util.py'):
     module = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(module)
     return module
+
+
+def load_reference_generators(root='/root/reference'):
+    """Import the reference's DLWP/model/generators.py (ArrayDataGenerator, generators.py:636-1011) on top of the shim.
+    The module uses a relative import of ..util, so stub package objects for ``DLWP`` and ``DLWP.model`` are registered
+    without running their __init__ (which would pull in Keras models); xarray is only needed by the other generator
+    classes and is replaced by an empty module; numpy >= 1.24 dropped the ``np.int`` alias generators.py:874 still uses."""
+    import importlib
+    import os
+    import numpy
+    install()
+    if not hasattr(numpy, 'int'):
+        numpy.int = int
+    if 'xarray' not in sys.modules:
+        sys.modules['xarray'] = types.ModuleType('xarray')
+    for name, sub in (('DLWP', 'DLWP'), ('DLWP.model', os.path.join('DLWP', 'model'))):
+        if name not in sys.modules:
+            pkg = types.ModuleType(name)
+            pkg.__path__ = [os.path.join(root, sub)]
+            sys.modules[name] = pkg
+    importlib.import_module('DLWP.util')
+    return importlib.import_module('DLWP.model.generators')

@@ -17,3 +17,9 @@ CONV_CASES = [
     ('k23_rect', dict(filters=3, kernel_size=(2, 3)), 1, 7, 2),
     ('k5_valid', dict(filters=2, kernel_size=5), 1, 9, 2),
 ]
+
+
+# device-side data feed (tests/golden/make_golden_feed.py): keyword arguments of oracle/cs_feed.generate per golden case
+FEED_CASES = {'a': dict(input_slice=slice(0, 4), output_slice=slice(0, 3), t_in=2, t_out=2, interval=2),
+              'b': dict(input_slice=slice(None), output_slice=slice(None), t_in=2, t_out=2, interval=1),
+              'c': dict(input_slice=slice(1, 5, 2), output_slice=slice(3, 4), t_in=1, t_out=3, interval=3)}

@@ -194,3 +194,18 @@ def test_cubed_sphere_latlon_geometry():
     v = np.stack([np.cos(np.radians(lat)) * np.cos(np.radians(lon)), np.cos(np.radians(lat)) * np.sin(np.radians(lon)),
                   np.sin(np.radians(lat))])
     assert np.abs(v.reshape(3, -1).mean(axis=1)).max() < 1e-12
+
+
+def test_feed_oracle_matches_reference_generator_golden():
+    """oracle/cs_feed.generate against outputs of the reference's own ArrayDataGenerator.generate
+    (DLWP/model/generators.py:872-984), produced by tests/golden/make_golden_feed.py -- bit for bit."""
+    import os
+    import numpy as np
+    import cs_feed
+    from tests.golden.cases import FEED_CASES
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'feed.npz'))
+    for k, kw in FEED_CASES.items():
+        p, t = cs_feed.generate(g['array'], g['samples_' + k], insolation_array=g['insolation_array'],
+                                constants=g['constants'], **kw)
+        assert np.array_equal(p, np.concatenate([g['p_' + k], g['const_' + k]], axis=-1))
+        assert np.array_equal(t, g['t_' + k])
