@@ -759,7 +759,7 @@ int dlwpcs_feed_gather(const float *array, const float *insolation, const float 
   F.cy = t_out * v_out;
   F.out_bf16 = dtype == DLWPCS_BF16;
   const int cmax = F.cx > F.cy ? F.cx : F.cy;
-  CS_CHECK(cmax <= 1024, "more than 1024 channels per sample");
+  CS_CHECK(cmax <= 368, "more than 368 channels per sample (shared-memory transpose tile)");
   dim3 grid((unsigned)((npix + 31) / 32), (unsigned)batch, 2);
   feed_gather_kernel<<<grid, 256, (size_t)32 * (cmax + 1) * sizeof(float), (cudaStream_t)stream>>>(F);
   CS_CUDA(cudaGetLastError());
