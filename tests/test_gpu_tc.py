@@ -280,3 +280,66 @@ def test_tc_conv_ragged_tiles_many_per_cta(lib):
         ref = O.capped_leaky_relu(O.cube_sphere_conv2d(O.cube_sphere_pad(x[sel].double(), 1), ws[0].double(), ws[1].double(),
                                                        None, bs[0].double(), bs[1].double(), None))
         check(y[sel], ref, stored_bf16=True)
+
+
+def _exact_inputs(b, n, cin, cout, seed):
+    """Integer-valued activations and weights in multiples of 1/8: every product and every partial sum of the convolution
+    is exactly representable in float32, so the tensor-core result must equal the exact sum whatever the summation order."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randint(-4, 5, (b, 6, n, n, cin), generator=g).to(torch.bfloat16)
+    ws = [(torch.randint(-8, 9, (3, 3, cin, cout), generator=g).float() / 8.0) for _ in range(2)]
+    return x, ws
+
+
+def test_tc_full_size_properties_c48_batch64(lib):
+    """BASELINE.json full size (C48, batch 64, 32 -> 32 channels) through size-independent properties:
+    exactness on exactly-representable data (checked against the float64 oracle on three images), linearity in the input,
+    and agreement of the fused halo gather with the standalone padding kernel followed by an un-padded convolution."""
+    b, n, cin, cout = 64, 48, 32, 32
+    x1, ws = _exact_inputs(b, n, cin, cout, 11)
+    x2, _ = _exact_inputs(b, n, cin, cout, 12)
+    d = lib.make_desc(b, n, cin, cout, (3, 3), (1, 1), (1, 1), 1, False, True, False, False, lib.ACT_NONE, 0.1, 10.0, lib.BF16,
+                      lib.F32)
+    packed = lib.pack_weights(d, ws[0].cuda(), ws[1].cuda(), None)
+    y1 = lib.conv2d_fwd(d, x1.cuda(), None, packed)
+    y2 = lib.conv2d_fwd(d, x2.cuda(), None, packed)
+    y12 = lib.conv2d_fwd(d, (x1.float() + x2.float()).to(torch.bfloat16).cuda(), None, packed)     # |x1 + x2| <= 8: exact in bf16
+    assert torch.equal(y12, y1 + y2)
+    sel = [0, 31, 63]
+    ref = O.cube_sphere_conv2d(O.cube_sphere_pad(x1[sel].double(), 1), ws[0].double(), ws[1].double(), None)
+    assert torch.equal(y1[sel].double().cpu(), ref)
+    # fused halo gather == standalone pad kernel + convolution without halo (bf16 padded tensor, same arithmetic)
+    xp = lib.pad_fwd(x1.cuda(), 1)
+    d0 = lib.make_desc(b, n + 2, cin, cout, (3, 3), (1, 1), (1, 1), 0, False, True, False, False, lib.ACT_NONE, 0.1, 10.0,
+                       lib.BF16, lib.F32)
+    y1b = lib.conv2d_fwd(d0, xp, None, lib.pack_weights(d0, ws[0].cuda(), ws[1].cuda(), None))
+    assert torch.equal(y1b, y1)
+
+
+def test_tc_backward_full_size_exactness_c48_batch32(lib):
+    """Training size (C48, batch 32): dgrad and wgrad on exactly-representable data equal the float64 oracle's autograd
+    -- wgrad sums 32 x 4 x 2304 products per weight in tensor memory and must reproduce the integer-valued exact sum; dgrad
+    is checked on three images (its bf16 output stores the exact value as long as it has at most 8 significant bits, so the
+    weights are restricted to {-1, 0, 1} there)."""
+    b, n, cin, cout = 32, 48, 32, 32
+    g = torch.Generator().manual_seed(21)
+    x = torch.randint(-2, 3, (b, 6, n, n, cin), generator=g).to(torch.bfloat16)
+    dy = torch.randint(-1, 2, (b, 6, n, n, cout), generator=g).to(torch.bfloat16)
+    ws = [torch.randint(-1, 2, (3, 3, cin, cout), generator=g).float() for _ in range(2)]
+    d = lib.make_desc(b, n, cin, cout, (3, 3), (1, 1), (1, 1), 1, False, True, False, True, lib.ACT_NONE, 0.1, 10.0, lib.BF16,
+                      lib.BF16)
+    dw_eq, dw_pol, _, db_eq, db_pol, _ = lib.conv2d_wgrad(d, x.cuda(), dy.cuda(), None)
+    xo = x.double().requires_grad_(True)
+    wo = [w.double().requires_grad_(True) for w in ws]
+    bo = [torch.zeros(cout, dtype=torch.float64, requires_grad=True) for _ in range(2)]
+    yo = O.cube_sphere_conv2d(O.cube_sphere_pad(xo, 1), wo[0], wo[1], None, bo[0], bo[1], None)
+    yo.backward(dy.double())
+    assert torch.equal(dw_eq.double().cpu(), wo[0].grad) and torch.equal(dw_pol.double().cpu(), wo[1].grad)
+    assert torch.equal(db_eq.double().cpu(), bo[0].grad) and torch.equal(db_pol.double().cpu(), bo[1].grad)
+    packed_t = lib.pack_weights(d, ws[0].cuda(), ws[1].cuda(), None, transposed=True)
+    dx = lib.conv2d_dgrad(d, dy.cuda(), None, packed_t)
+    sel = [0, 13, 31]
+    # |dx| <= 9 * 32 * (corner multiplicity 5) ... the bf16 store keeps 8 significant bits: compare with one rounding
+    ref = xo.grad[sel]
+    got = dx[sel].double().cpu()
+    assert torch.equal(got, ref.to(torch.bfloat16).double())
