@@ -43,6 +43,8 @@ N_FACE = 48
 C_PROG = 14       # 7 variables x 2 time steps
 C_FORC = 4        # 2 insolation + 2 constants
 BASE = 32
+# face edge of every unet2 layer relative to the input (two poolings): Azure/train_cs.py:277-305
+EDGE_DIV = {'conv_2d_2': 2, 'conv_2d_2_2': 2, 'conv_2d_5_2': 4, 'conv_2d_5': 4, 'conv_2d_6_2': 2, 'conv_2d_6': 2}
 METRIC = 'forecast steps/sec C48 6-face U-Net rollout'
 UNIT = 'sample-steps/s'
 
@@ -362,15 +364,21 @@ def main():
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         tms = float(tt.item()) / args.train_steps
-        train = {'metric': 'train samples/sec, unet2 C48 fwd+bwd+Adam', 'value': tb * world / (tms * 1e-3),
+        train = {'metric': 'train samples/sec, unet2 C%d fwd+bwd+Adam' % N_FACE, 'value': tb * world / (tms * 1e-3),
                  'unit': 'samples/s', 'ms_per_step': tms, 'global_batch': tb * world, 'batch_per_gpu': tb,
                  'dtype': args.train_dtype, 'parallelism': 'dp%d, one flat all-reduce of %d float32 gradients per step'
                                                 % (world, trainer.flat.count),
                  'loss': float(loss.item()),
+                 # forward + dgrad + wgrad = 3 x the forward FLOP of every layer
+                 'algorithmic_gflop_per_sample': round(3e-9 * sum(
+                     layer_work(s[0], s[1], s[2], s[3], N_FACE // EDGE_DIV.get(s[0], 1), 1, 2, 2)[0]
+                     for s in unet2_layer_specs(C_PROG + C_FORC, C_PROG, BASE)), 3),
                  'note': ('bf16 activations: forward, dgrad and wgrad on tcgen05 kernels (fp32 accumulation in tensor '
                           'memory); float32 master weights, fused Adam')
                  if args.train_dtype == 'bf16' else 'float32 CUDA-core kernels (1e-5 parity path)'}
 
+    if train is not None:
+        train['tflops'] = round(train['value'] * train['algorithmic_gflop_per_sample'] * 1e-3, 1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
