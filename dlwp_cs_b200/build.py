@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError('nvcc failed on %s' % src)
-    cmd = [nvcc, '-shared', '-o', LIB_PATH] + objs + ['-lcudart']
+    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB_PATH] + objs + ['-lcudart']
     subprocess.check_call(cmd)
     return LIB_PATH
 
