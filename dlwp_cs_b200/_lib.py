@@ -274,14 +274,15 @@ def conv2d_fwd_host(d, x, w_eq, w_pol, w_np=None, b_eq=None, b_pol=None, b_np=No
     return y
 
 
-def mse_loss_grad(y, t, loss_accum):
-    """keras 'mse': adds mean((y-t)^2) to the 1-element float32 device tensor loss_accum, returns dL/dy."""
+def mse_loss_grad(y, t, loss_accum, scale=1.0):
+    """keras 'mse': adds scale * mean((y-t)^2) to the 1-element float32 device tensor loss_accum, returns its gradient
+    with respect to y (scale = the output's loss weight, 1/S for the S outputs of a multi-step model, train_cs.py:424-426)."""
     require_cuda(y, t, loss_accum)
     y, t = y.contiguous(), t.contiguous()
     dy = torch.empty_like(y)
     n = y.numel()
-    check(load().dlwpcs_mse_loss_grad(ptr(y), ptr(t), ptr(dy), ptr(loss_accum), n, 1.0 / max(n, 1), dtype_code(y.dtype),
-                                      stream_ptr()))
+    check(load().dlwpcs_mse_loss_grad(ptr(y), ptr(t), ptr(dy), ptr(loss_accum), n, float(scale) / max(n, 1),
+                                      dtype_code(y.dtype), stream_ptr()))
     return dy
 
 

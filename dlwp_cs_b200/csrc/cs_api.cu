@@ -512,12 +512,12 @@ struct FeedP {
   const int *in_vars, *out_vars;           // variable indices of the input / output selections
   void *x, *y;                             // (B, P, cx), (B, P, cy)
   long long P;
-  int V, v_in, v_out, t_in, t_out, interval, n_const, has_sol, cx, cy, out_bf16;
+  int V, v_in, v_out, t_in, t_out, interval, n_const, has_sol, cx, cy, out_bf16, z0;
 };
 
 __global__ void __launch_bounds__(256) feed_gather_kernel(const __grid_constant__ FeedP F) {
   extern __shared__ float tile[];          // [32 pixels][C + 1]
-  const bool tgt = blockIdx.z == 1;
+  const bool tgt = blockIdx.z + F.z0 == 1;
   const int C = tgt ? F.cy : F.cx, ld = C + 1;
   const long long p0 = (long long)blockIdx.x * 32;
   const int b = blockIdx.y, px = threadIdx.x & 31, cl = threadIdx.x >> 5;
@@ -745,7 +745,8 @@ int dlwpcs_feed_gather(const float *array, const float *insolation, const float 
                        const int32_t *in_vars, const int32_t *out_vars, void *x, void *y, int batch, int64_t npix,
                        int n_var, int v_in, int v_out, int t_in, int t_out, int interval, int n_const, int dtype,
                        void *stream) {
-  CS_CHECK(elem_size(dtype) != 0 && array && samples && in_vars && out_vars && x && y, "null pointer / bad dtype in dlwpcs_feed_gather");
+  // x == NULL or y == NULL: only the other part is produced (sequence mode asks for the targets of later steps alone)
+  CS_CHECK(elem_size(dtype) != 0 && array && samples && in_vars && out_vars && (x || y), "null pointer / bad dtype in dlwpcs_feed_gather");
   CS_CHECK(batch >= 0 && npix > 0 && n_var > 0 && v_in > 0 && v_out > 0 && t_in > 0 && t_out > 0 && interval > 0 &&
                n_const >= 0 && (n_const == 0 || constants),
            "bad arguments to dlwpcs_feed_gather");
@@ -760,7 +761,8 @@ int dlwpcs_feed_gather(const float *array, const float *insolation, const float 
   F.out_bf16 = dtype == DLWPCS_BF16;
   const int cmax = F.cx > F.cy ? F.cx : F.cy;
   CS_CHECK(cmax <= 368, "more than 368 channels per sample (shared-memory transpose tile)");
-  dim3 grid((unsigned)((npix + 31) / 32), (unsigned)batch, 2);
+  F.z0 = x ? 0 : 1;
+  dim3 grid((unsigned)((npix + 31) / 32), (unsigned)batch, (x && y) ? 2 : 1);
   feed_gather_kernel<<<grid, 256, (size_t)32 * (cmax + 1) * sizeof(float), (cudaStream_t)stream>>>(F);
   CS_CUDA(cudaGetLastError());
   return 0;

@@ -27,7 +27,7 @@ def _indices(sel, n):
 class DeviceDataFeed(object):
     def __init__(self, array, batch_size=32, input_slice=None, output_slice=None, input_time_steps=1,
                  output_time_steps=1, interval=1, shuffle=False, insolation_array=None, constants=None,
-                 drop_remainder=False, dtype=torch.float32, device='cuda', seed=0):
+                 drop_remainder=False, dtype=torch.float32, device='cuda', seed=0, sequence=None):
         for v, nm in ((input_time_steps, 'input_time_steps'), (output_time_steps, 'output_time_steps'),
                       (batch_size, 'batch_size'), (interval, 'interval')):
             if int(v) <= 0:
@@ -62,7 +62,13 @@ class DeviceDataFeed(object):
             self.constants = c.to(self.device, torch.float32).contiguous()
         self.dtype = dtype
         self.batch_size, self.shuffle, self.drop_remainder = int(batch_size), bool(shuffle), bool(drop_remainder)
-        self._n_sample = int(array.shape[0]) - self.interval * (self.t_in + self.t_out) + 1        # generators.py:695
+        self.sequence = None if sequence is None else int(sequence)
+        if self.sequence is not None and self.sequence <= 0:
+            raise ValueError('sequence must be positive')
+        if self.sequence is not None and self.insolation_array is None:
+            raise ValueError('sequence mode hands the insolation of the later steps to the model: insolation_array is required')
+        # generators.py:692-695
+        self._n_sample = int(array.shape[0]) - self.interval * (self.t_in + self.t_out * (self.sequence or 1)) + 1
         if self._n_sample <= 0:
             raise ValueError('the array is too short for %d + %d time steps at interval %d' % (self.t_in, self.t_out,
                                                                                                 self.interval))
@@ -94,19 +100,33 @@ class DeviceDataFeed(object):
             raise IndexError('batch index %d out of range' % index)
         return self.generate(self._indices[index * self.batch_size:(index + 1) * self.batch_size])
 
-    def generate(self, samples):
-        if len(samples) == 0:
-            samples = np.arange(self._n_sample)
-        samples = np.asarray(samples, dtype=np.int64)
-        if samples.min() < 0 or samples.max() >= self._n_sample:
-            raise IndexError('sample index out of range [0, %d)' % self._n_sample)
-        b = len(samples)
-        s_dev = torch.from_numpy(samples).to(self.device, non_blocking=True)
-        x = torch.empty((b, 6, self.n, self.n, self.n_input_channels), dtype=self.dtype, device=self.device)
-        y = torch.empty((b, 6, self.n, self.n, self.n_output_channels), dtype=self.dtype, device=self.device)
+    def _gather(self, s_dev, want_x, want_y):
+        b = int(s_dev.numel())
+        x = torch.empty((b, 6, self.n, self.n, self.n_input_channels), dtype=self.dtype, device=self.device) if want_x else None
+        y = torch.empty((b, 6, self.n, self.n, self.n_output_channels), dtype=self.dtype, device=self.device) if want_y else None
         _lib.check(_lib.load().dlwpcs_feed_gather(
             _lib.ptr(self.array), _lib.ptr(self.insolation_array), _lib.ptr(self.constants), _lib.ptr(s_dev),
             _lib.ptr(self._in_vars), _lib.ptr(self._out_vars), _lib.ptr(x), _lib.ptr(y), b, self.npix, self.n_var,
             len(self.in_idx), len(self.out_idx), self.t_in, self.t_out, self.interval,
             0 if self.constants is None else int(self.constants.shape[0]), _lib.dtype_code(self.dtype), _lib.stream_ptr()))
         return x, y
+
+    def generate(self, samples):
+        """-> (x, y); with ``sequence=S``: (x, [solar_1 .. solar_{S-1}], [y_0 .. y_{S-1}]) -- the inputs the reference's
+        generator hands to the multi-step Keras model (generators.py:884-893, 964-983) with the constants already appended
+        to x: solar_s (B, T_in, 6, N, N, 1) is the insolation at the input times of step s, y_s the targets of step s."""
+        if len(samples) == 0:
+            samples = np.arange(self._n_sample)
+        samples = np.asarray(samples, dtype=np.int64)
+        if samples.min() < 0 or samples.max() >= self._n_sample:
+            raise IndexError('sample index out of range [0, %d)' % self._n_sample)
+        s_dev = torch.from_numpy(samples).to(self.device, non_blocking=True)
+        x, y = self._gather(s_dev, True, True)
+        if self.sequence is None:
+            return x, y
+        solars, targets = [], [y]
+        for s in range(1, self.sequence):
+            sol = torch.stack([self.insolation_array[s_dev + self.interval * (self.t_in * s + k)] for k in range(self.t_in)], dim=1)
+            solars.append(sol.unsqueeze(-1).to(self.dtype))
+            targets.append(self._gather(s_dev + self.interval * self.t_out * s, False, True)[1])
+        return x, solars, targets

@@ -83,6 +83,18 @@ def shard_batch(global_batch, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def repack_reference(y, solar, x_first, t_in, n_var):
+    """Input of forecast step s >= 1 of the reference's multi-step model (`complete_model`, Azure/train_cs.py:391-409): per
+    input time step the n_var variables just predicted, then that time step's insolation; the constants are the trailing
+    channels of the first input.  y (B,6,N,N,t_in*n_var), solar (B,t_in,6,N,N,1), x_first (B,6,N,N,t_in*(n_var+1)+n_const)."""
+    parts = []
+    for t in range(t_in):
+        parts.append(y[..., t * n_var:(t + 1) * n_var])
+        parts.append(solar[:, t].to(y.dtype))
+    parts.append(x_first[..., t_in * (n_var + 1):])
+    return torch.cat(parts, dim=-1)
+
+
 class DataParallelTrainer(object):
     """
         trainer = DataParallelTrainer(model, lr=1e-3)
@@ -96,8 +108,7 @@ class DataParallelTrainer(object):
     def __init__(self, model, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, group=None, use_graph=True):
         self.model = model
         self.use_graph = use_graph
-        self._graph = None
-        self._static = None
+        self._graphs = {}
         self.flat = FlatBuffers(model)
         if self.flat.param.device.type != 'cuda':
             raise _lib.DlwpcsError('DataParallelTrainer needs the model on a CUDA device (no CPU path)')
@@ -129,36 +140,74 @@ class DataParallelTrainer(object):
                            self.step_counter, 1.0 / world)
         return loss
 
-    def step(self, x, target):
-        """One optimizer step.  With ``use_graph`` the whole step (forward, loss, backward, all-reduce, Adam: ~150
-        launches) is captured once per input shape into a CUDA graph and replayed; x / target are copied into the
-        graph's static input buffers."""
-        self.t += 1
+    def _graphed(self, tag, tensors, body):
+        """Run body(*tensors) -- one whole optimizer step -- from a CUDA graph captured once per (tag, shapes, dtypes); the
+        tensors are copied into the graph's static input buffers before every replay."""
         if not self.use_graph:
-            return self._step_body(x, target)
-        key = (tuple(x.shape), x.dtype, tuple(target.shape), target.dtype)
-        if self._graph is None or self._static[0] != key:
-            sx, st = torch.empty_like(x), torch.empty_like(target)
-            sx.copy_(x)
-            st.copy_(target)
-            state = [t.clone() for t in (self.flat.param, self.m, self.v, self.step_counter)]
-            side = torch.cuda.Stream(device=x.device)
-            side.wait_stream(torch.cuda.current_stream(x.device))
+            return body(*tensors)
+        key = (tag,) + tuple((tuple(t.shape), t.dtype) for t in tensors)
+        if key not in self._graphs:
+            dev = tensors[0].device
+            statics = [torch.empty_like(t) for t in tensors]
+            for s_, t in zip(statics, tensors):
+                s_.copy_(t)
+            keep = (self.flat.param, self.m, self.v, self.step_counter)
+            state = [t.clone() for t in keep]
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):                   # warm-up off the capture: lazy tables, autograd buffers
                 for _ in range(2):
-                    self._step_body(sx, st)
-            torch.cuda.current_stream(x.device).wait_stream(side)
-            torch.cuda.synchronize(x.device)
-            for dst, src in zip((self.flat.param, self.m, self.v, self.step_counter), state):
+                    body(*statics)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            for dst, src in zip(keep, state):
                 dst.copy_(src)                              # the warm-up steps do not count
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._step_body(sx, st)
-            for dst, src in zip((self.flat.param, self.m, self.v, self.step_counter), state):
+                body(*statics)
+            for dst, src in zip(keep, state):
                 dst.copy_(src)                              # neither does the capture (nothing ran, but be explicit)
-            self._graph, self._static = g, (key, sx, st)
-        _, sx, st = self._static
-        sx.copy_(x, non_blocking=True)
-        st.copy_(target, non_blocking=True)
-        self._graph.replay()
+            self._graphs[key] = (g, statics)
+        g, statics = self._graphs[key]
+        for s_, t in zip(statics, tensors):
+            s_.copy_(t, non_blocking=True)
+        g.replay()
         return self.loss
+
+    def step(self, x, target):
+        """One optimizer step.  With ``use_graph`` the whole step (forward, loss, backward, all-reduce, Adam: ~150
+        launches) is captured once per input shape into a CUDA graph and replayed."""
+        self.t += 1
+        return self._graphed('step', [x, target], self._step_body)
+
+    # ---- multi-step ("integration_steps") training of the reference: Azure/train_cs.py:101, 391-426 --------------------
+    def _sequence_body(self, t_in, n_var, n_steps, x, *rest):
+        solars, targets = rest[:n_steps - 1], rest[n_steps - 1:]
+        self.loss.zero_()
+        for p in self.flat.params:
+            p.grad = None
+        ys, xin = [], x
+        for s in range(n_steps):                 # the same layer objects (shared weights) at every step
+            y = self.model(xin)
+            ys.append(y)
+            if s + 1 < n_steps:
+                xin = repack_reference(y, solars[s], x, t_in, n_var)
+        # keras multi-output loss: sum_s w_s * mse(y_s, t_s) with w_s = 1/S (train_cs.py:424-426)
+        dys = [_lib.mse_loss_grad(y.detach(), t, self.loss, scale=1.0 / n_steps) for y, t in zip(ys, targets)]
+        torch.autograd.backward(ys, dys)
+        self.flat.collect_grads()
+        world = self.flat.all_reduce(self.group)
+        _lib.adam_step_dev(self.flat.param, self.flat.grad, self.m, self.v, self.lr, self.beta1, self.beta2, self.eps,
+                           self.step_counter, 1.0 / world)
+        return self.loss
+
+    def step_sequence(self, x, solars, targets, t_in, n_var):
+        """One optimizer step of the S-step model: x = input of step 0 in the reference's packing (per input time step the
+        n_var variables then its insolation, constants last), solars[s-1] (B,t_in,6,N,N,1) = insolation of step s, targets[s]
+        = truth of step s -- exactly what ``DeviceDataFeed(..., sequence=S).generate`` returns.  Needs t_out == t_in."""
+        n_steps = len(targets)
+        if len(solars) != n_steps - 1:
+            raise ValueError('%d targets need %d insolation tensors, got %d' % (n_steps, n_steps - 1, len(solars)))
+        self.t += 1
+        body = lambda *ts: self._sequence_body(t_in, n_var, n_steps, *ts)
+        return self._graphed(('sequence', t_in, n_var, n_steps), [x] + list(solars) + list(targets), body)

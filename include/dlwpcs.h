@@ -151,7 +151,8 @@ int dlwpcs_insolation(void *out, int dtype, int batch, int64_t npix, int c_total
  *   x (batch, npix, t_in*(v_in + has_insolation) + n_const):  channel t*(v_in+1)+v = array[s + t*interval, in_vars[v]],
  *       insolation last within each time step (generators.py:880-899), constants appended (train_cs.py:396-407);
  *   y (batch, npix, t_out*v_out):  channel t*v_out+v = array[s + interval*(t_in + t), out_vars[v]]  (generators.py:943-946).
- * dtype = element type of x and y (float32 or bf16).                                                                   */
+ * dtype = element type of x and y (float32 or bf16); x or y may be NULL to produce only the other one.
+ *                                                                   */
 int dlwpcs_feed_gather(const float *array, const float *insolation, const float *constants, const int64_t *samples,
                        const int32_t *in_vars, const int32_t *out_vars, void *x, void *y, int batch, int64_t npix,
                        int n_var, int v_in, int v_out, int t_in, int t_out, int interval, int n_const, int dtype,

@@ -19,6 +19,24 @@ concatenation as one tensor, which is what the engine's model takes.
 import numpy as np
 
 
+def generate_sequence(array, samples, input_slice, output_slice, t_in, t_out, interval, sequence, insolation_array,
+                      constants=None):
+    """``sequence=S`` mode (generators.py:884-893, 902-930, 964-983): the targets are S consecutive forecast steps and the
+    inputs are [p, insolation of steps 1..S-1, constants].  Returns (x, solars, targets): x as in ``generate`` (predictors of
+    step 0 with the constants appended), solars[s-1] = (B, T_in, 6, N, N, 1) insolation of the input times of step s,
+    targets[s] = (B, 6, N, N, T_out*V_out) with channel t*V_out+v = array[s_b + interval*(T_in + T_out*s + t), v]."""
+    samples = np.asarray(samples, dtype=np.int64)
+    x, _ = generate(array, samples, input_slice, output_slice, t_in, t_out, interval, insolation_array, constants)
+    solars = []
+    for s in range(1, sequence):
+        sol = np.concatenate([insolation_array[samples + interval * (t_in * s + k), np.newaxis, np.newaxis]
+                              for k in range(t_in)], axis=1)                               # (B, T_in, 1, 6, N, N)
+        solars.append(np.ascontiguousarray(sol.transpose((0, 1) + tuple(range(3, sol.ndim)) + (2,))))
+    targets = [generate(array, samples + interval * t_out * s, input_slice, output_slice, t_in, t_out, interval)[1]
+               for s in range(sequence)]
+    return x, solars, targets
+
+
 def generate(array, samples, input_slice, output_slice, t_in, t_out, interval, insolation_array=None, constants=None):
     samples = np.asarray(samples, dtype=np.int64)
     n = len(samples)

@@ -23,3 +23,5 @@ CONV_CASES = [
 FEED_CASES = {'a': dict(input_slice=slice(0, 4), output_slice=slice(0, 3), t_in=2, t_out=2, interval=2),
               'b': dict(input_slice=slice(None), output_slice=slice(None), t_in=2, t_out=2, interval=1),
               'c': dict(input_slice=slice(1, 5, 2), output_slice=slice(3, 4), t_in=1, t_out=3, interval=3)}
+FEED_SEQ_CASES = {'d': (dict(input_slice=slice(0, 4), output_slice=slice(0, 4), t_in=2, t_out=2, interval=1), 2),
+                  'e': (dict(input_slice=slice(None), output_slice=slice(1, 3), t_in=1, t_out=2, interval=2), 3)}

@@ -40,5 +40,22 @@ for k, kw in cases.items():
     out['p_%s' % k], out['const_%s' % k], out['t_%s' % k] = p[0], p[1], t
     out['samples_%s' % k] = np.array(samples[k])
     out['n_sample_%s' % k] = np.array(g._n_sample)
+# sequence mode (Azure/train_cs.py:159-163 passes sequence=integration_steps): inputs [p, solar_1.., constants], list targets
+seq_cases = {'d': (dict(input_slice=slice(0, 4), output_slice=slice(0, 4), input_time_steps=2, output_time_steps=2, interval=1), 2,
+                   [0, 5, 2]),
+             'e': (dict(input_slice=None, output_slice=slice(1, 3), input_time_steps=1, output_time_steps=2, interval=2), 3,
+                   [0, 0])}
+for k, (kw, S, smp) in seq_cases.items():
+    g = gen.ArrayDataGenerator(ModelStub(), array, rank=3, batch_size=4, insolation_array=insol, constants=consts,
+                               channels_last=True, sequence=S, **kw)
+    p, t = g.generate(smp)
+    assert isinstance(p, list) and len(p) == S + 1 and isinstance(t, list) and len(t) == S
+    out['p_%s' % k], out['const_%s' % k] = p[0], p[-1]
+    for s in range(1, S):
+        out['solar_%s_%d' % (k, s)] = p[s]
+    for s in range(S):
+        out['t_%s_%d' % (k, s)] = t[s]
+    out['samples_%s' % k] = np.array(smp)
+    out['n_sample_%s' % k] = np.array(g._n_sample)
 np.savez_compressed(os.path.join(HERE, 'feed.npz'), **out)
 print({k: v.shape for k, v in out.items()})

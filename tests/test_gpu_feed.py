@@ -46,3 +46,23 @@ def test_feed_c48_bf16_vs_oracle():
     assert torch.equal(x.cpu(), torch.from_numpy(xr).bfloat16()) and torch.equal(y.cpu(), torch.from_numpy(yr).bfloat16())
     with pytest.raises(IndexError):
         feed.generate([feed._n_sample])
+
+
+def test_feed_sequence_vs_reference_golden(golden_dir):
+    """sequence=S mode (Azure/train_cs.py:159-163): predictors of step 0, insolation of the later steps, list of targets --
+    against the reference generator's own outputs."""
+    from dlwp_cs_b200.feed import DeviceDataFeed
+    from tests.golden.cases import FEED_SEQ_CASES
+    g = np.load(os.path.join(golden_dir, 'feed.npz'))
+    for k, (kw, S) in FEED_SEQ_CASES.items():
+        feed = DeviceDataFeed(g['array'], batch_size=4, input_slice=kw['input_slice'], output_slice=kw['output_slice'],
+                              input_time_steps=kw['t_in'], output_time_steps=kw['t_out'], interval=kw['interval'],
+                              insolation_array=g['insolation_array'], constants=g['constants'], sequence=S)
+        assert feed._n_sample == int(g['n_sample_' + k])
+        x, solars, targets = feed.generate(g['samples_' + k])
+        assert len(solars) == S - 1 and len(targets) == S
+        assert np.array_equal(x.cpu().numpy(), np.concatenate([g['p_' + k], g['const_' + k]], axis=-1))
+        for s in range(1, S):
+            assert np.array_equal(solars[s - 1].cpu().numpy(), g['solar_%s_%d' % (k, s)])
+        for s in range(S):
+            assert np.array_equal(targets[s].cpu().numpy(), g['t_%s_%d' % (k, s)])

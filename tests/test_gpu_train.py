@@ -106,3 +106,34 @@ def test_trainer_graph_replay_equals_eager_steps(lib):
     # the loss is a float atomicAdd over blocks: equal up to summation order
     np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-5)
     assert out[0][1][2] < out[0][1][0]          # and it learns
+
+
+def test_trainer_sequence_step_matches_oracle_autograd(lib):
+    """Two-step ("integration_steps = 2", Azure/train_cs.py:101, 391-426) optimizer step: the same layers applied twice, the
+    second input re-packed from the first output + the next insolation + the constants, loss = (mse_0 + mse_1) / 2 --
+    float32 engine (graph-replayed) against float64 oracle autograd: loss and every parameter gradient."""
+    from dlwp_cs_b200.unet import CubeSphereUNet2
+    from dlwp_cs_b200.train import DataParallelTrainer, repack_reference
+    n, b, n_var, t_in, n_const, base = 8, 2, 3, 2, 2, 8
+    cin, cout = t_in * (n_var + 1) + n_const, t_in * n_var
+    params = O.make_unet2_params(cin, cout, base=base, seed=6)
+    model = CubeSphereUNet2(cin, cout, base=base).cuda()
+    model.load_oracle_params(params)
+    names = [k for k, _ in model.named_parameters()]
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(b, 6, n, n, cin, generator=g)
+    solar = torch.rand(b, t_in, 6, n, n, 1, generator=g)
+    ts = [torch.randn(b, 6, n, n, cout, generator=g) for _ in range(2)]
+    pd = {k: params[k].double().requires_grad_(True) for k in names}
+    y0 = O.unet2(pd, x.double())
+    y1 = O.unet2(pd, repack_reference(y0, solar.double(), x.double(), t_in, n_var))
+    loss_ref = 0.5 * ((y0 - ts[0].double()).pow(2).mean() + (y1 - ts[1].double()).pow(2).mean())
+    loss_ref.backward()
+    trainer = DataParallelTrainer(model, lr=1e-3)
+    loss = trainer.step_sequence(x.cuda(), [solar.cuda()], [t.cuda() for t in ts], t_in, n_var)
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) < 1e-5 * float(loss_ref.detach())
+    for k, p in model.named_parameters():
+        gref = pd[k].grad.numpy()
+        np.testing.assert_allclose(p.grad.double().cpu().numpy(), gref, rtol=1e-4,
+                                   atol=1e-5 * max(float(np.abs(gref).max()), 1e-30))
+    assert int(trainer.step_counter) == 1
