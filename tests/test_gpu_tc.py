@@ -221,7 +221,7 @@ def test_tc_backward_vs_oracle_autograd(lib, c):
 @pytest.mark.parametrize('n,cin,cout', [(12, 32, 32), (24, 64, 64)])
 def test_tc_in_kernel_mask_equals_separate_act_bwd(lib, n, cin, cout):
     """C ABI: dgrad / wgrad with the activation derivative applied inside the kernels (register path) against the same
-    kernels fed with dy * act'(y) from dlwpcs_act_bwd (asynchronous-copy path, bias sums from the side kernel)."""
+    kernels fed with dy * act'(y) from dlwpcs_act_bwd (asynchronous-copy path, bias sums read back from the dy tile in shared memory)."""
     g = torch.Generator().manual_seed(n + cin)
     b = 2
     x = bf(torch.randn(b, 6, n, n, cin, generator=g)).cuda()
