@@ -111,10 +111,21 @@ def stream_ptr():
 
 
 def require_cuda(*tensors):
+    """Every tensor handed to the library must live on the CURRENT CUDA device: the kernels are launched on that device's
+    current stream and the library caches its halo / patch tables per current device (call ``torch.cuda.set_device`` --
+    or wrap the call in ``torch.cuda.device(t.device)`` -- in a one-process-per-GPU launcher)."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise DlwpcsError('dlwp_cs_b200 runs on CUDA tensors only (got a %s tensor); there is no CPU path'
                               % t.device.type)
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise DlwpcsError('tensor on cuda:%d but the current device is cuda:%d -- call torch.cuda.set_device(%d) first'
+                              % (t.device.index, cur, t.device.index))
 
 
 def ptr(t):
@@ -278,6 +289,11 @@ def mse_loss_grad(y, t, loss_accum, scale=1.0):
     """keras 'mse': adds scale * mean((y-t)^2) to the 1-element float32 device tensor loss_accum, returns its gradient
     with respect to y (scale = the output's loss weight, 1/S for the S outputs of a multi-step model, train_cs.py:424-426)."""
     require_cuda(y, t, loss_accum)
+    if tuple(t.shape) != tuple(y.shape) or t.dtype != y.dtype:
+        raise DlwpcsError('mse_loss_grad: target %r %s does not match the model output %r %s'
+                          % (tuple(t.shape), t.dtype, tuple(y.shape), y.dtype))
+    if loss_accum.dtype != torch.float32 or loss_accum.numel() != 1:
+        raise DlwpcsError('mse_loss_grad: loss_accum must be a 1-element float32 tensor')
     y, t = y.contiguous(), t.contiguous()
     dy = torch.empty_like(y)
     n = y.numel()

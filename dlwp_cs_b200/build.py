@@ -12,9 +12,12 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libdlwpcs.so')
 SOURCES = ['cs_api.cu', 'cs_fp32.cu', 'cs_tc.cu', 'cs_wgrad_tc.cu']
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math',
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O3', '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
-# --use_fast_math only affects transcendental / division intrinsics; the kernels use fmaf and fminf only.
+# --use_fast_math (flush-to-zero, approximate division / square root) only for the two bf16 tensor-core translation
+# units, whose arithmetic outside the tensor core is fmaf / fminf / fmaxf on values that are rounded to bf16 anyway.  The
+# float32 parity kernels, the Adam update (m / (sqrt(v) + eps)), the loss and the insolation are compiled IEEE.
+FAST_MATH = {'cs_tc.cu', 'cs_wgrad_tc.cu'}
 
 
 def _nvcc():
@@ -42,7 +45,8 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(LIB_DIR, src.replace('.cu', '.o'))
-        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + (['--use_fast_math'] if src in FAST_MATH else []) + \
+            (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

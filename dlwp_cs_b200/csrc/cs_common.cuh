@@ -49,6 +49,14 @@ int derive_geometry(const dlwpcs_conv_desc *d, Geometry *g);
 
 static inline int face_group_host(int f) { return f < 4 ? 0 : f - 3; }
 
+// per-device one-time state (opt-in shared-memory attributes, SM counts) is indexed by the current device
+constexpr int kMaxDevices = 64;
+static inline int current_device_index() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
 // fp32 path (cs_fp32.cu)
 int fp32_pack_weights(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, int transposed, float *packed,
                       cudaStream_t st);

@@ -284,10 +284,11 @@ int launch_conv(ConvP &P, cudaStream_t st) {
   const size_t smem = sizeof(float) * ((size_t)CK * P.PHWp + (size_t)P.kh * P.kw * CK * COT) +
                       sizeof(int) * (size_t)P.PH * P.PW;
   CS_CHECK(smem <= 200 * 1024, "kernel window too large for the float32 kernel (%zu bytes of shared memory)", smem);
-  static size_t cur_max = 48 * 1024;
-  if (smem > cur_max) {
+  static bool big_smem[kMaxDevices] = {};     // the opt-in is per device (function attributes live in the context)
+  const int dev = current_device_index();
+  if (smem > 48 * 1024 && !big_smem[dev]) {
     CS_CUDA(cudaFuncSetAttribute(conv_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    cur_max = 200 * 1024;
+    big_smem[dev] = true;
   }
   const long long gz = (long long)P.B * 6;
   CS_CHECK(gz <= 65535, "batch too large for one launch (B*6 = %lld > 65535)", gz);
@@ -560,10 +561,11 @@ int fp32_conv_wgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0
   const size_t smem = sizeof(float) * ((size_t)P.PH * P.PW * WCK + (size_t)P.TH * P.TW * WCO) +
                       sizeof(int) * (size_t)P.PH * P.PW;
   CS_CHECK(smem <= 200 * 1024, "kernel window too large for the wgrad kernel (%zu bytes of shared memory)", smem);
-  static size_t cur_max = 48 * 1024;
-  if (smem > cur_max) {
+  static bool big_smem[kMaxDevices] = {};
+  const int dev = current_device_index();
+  if (smem > 48 * 1024 && !big_smem[dev]) {
     CS_CUDA(cudaFuncSetAttribute(wgrad_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    cur_max = 200 * 1024;
+    big_smem[dev] = true;
   }
   dim3 grid(P.cin_chunks * P.tap_blocks, (d->cout + WCO - 1) / WCO, 6 * P.strips);
   wgrad_fp32_kernel<<<grid, 256, smem, st>>>(P);

@@ -862,13 +862,11 @@ namespace {
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
-  return sms;
+  static int sms[kMaxDevices] = {};
+  const int dev = current_device_index();
+  if (!sms[dev] && (cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms[dev] <= 0))
+    sms[dev] = 148;
+  return sms[dev];
 }
 
 int launch_tc(TcP &P, cudaStream_t st) {
@@ -879,13 +877,13 @@ int launch_tc(TcP &P, cudaStream_t st) {
       {conv_tc_kernel<2, 1>, conv_tc_kernel<2, 2>, conv_tc_kernel<2, 3>, conv_tc_kernel<2, 4>},
       {conv_tc_kernel<3, 1>, conv_tc_kernel<3, 2>, conv_tc_kernel<3, 3>, conv_tc_kernel<3, 4>},
       {conv_tc_kernel<4, 1>, conv_tc_kernel<4, 2>, conv_tc_kernel<4, 3>, conv_tc_kernel<4, 4>}};
-  static bool attr_set[4][4] = {};
+  static bool attr_set[kMaxDevices][4][4] = {};      // the shared-memory opt-in is per device
   CS_CHECK(L.MB >= 1 && L.MB <= 4 && L.KC % 16 == 0 && L.KC <= 64, "internal: bad tile plan");
-  const int ki = L.MB - 1, kj = L.KC / 16 - 1;
+  const int ki = L.MB - 1, kj = L.KC / 16 - 1, dev_i = current_device_index();
   const kern_t kern = kerns[ki][kj];
-  if (!attr_set[ki][kj]) {
+  if (!attr_set[dev_i][ki][kj]) {
     CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
-    attr_set[ki][kj] = true;
+    attr_set[dev_i][ki][kj] = true;
   }
   const long long ntiles = 6LL * P.batch * L.tpf;
   CS_CHECK(ntiles < (1LL << 30), "batch too large");

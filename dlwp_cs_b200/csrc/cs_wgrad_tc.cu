@@ -650,15 +650,16 @@ int tc_conv_wgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, 
   typedef void (*kern_t)(const WgP);
   static const kern_t kerns[5] = {wgrad_tc_kernel<0, 0, 0>, wgrad_tc_kernel<3, 1, 1>, wgrad_tc_kernel<3, 2, 1>,
                                   wgrad_tc_kernel<3, 1, 2>, wgrad_tc_kernel<1, 1, 1>};
-  static bool attr_set[5] = {};
+  static bool attr_set[kMaxDevices][5] = {};      // the shared-memory opt-in is per device
+  const int dev_i = current_device_index();
   int ki = 0;
   if (L.kh == 3 && L.MBu == 1 && L.NBJ == 1) ki = 1;
   else if (L.kh == 3 && L.MBu == 2 && L.NBJ == 1) ki = 2;
   else if (L.kh == 3 && L.MBu == 1 && L.NBJ == 2) ki = 3;
   else if (L.kh == 1 && L.MBu == 1 && L.NBJ == 1) ki = 4;
-  if (!attr_set[ki]) {
+  if (!attr_set[dev_i][ki]) {
     CS_CUDA(cudaFuncSetAttribute(kerns[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_CAP));
-    attr_set[ki] = true;
+    attr_set[dev_i][ki] = true;
   }
   kerns[ki]<<<L.ncta, WG_THREADS, L.smemBytes, st>>>(P);
   CS_CUDA(cudaGetLastError());

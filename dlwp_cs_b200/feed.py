@@ -17,17 +17,25 @@ from . import _lib
 
 
 def _indices(sel, n):
+    """Variable indices of a slice / index list over the varlev axis, negative indices normalised, range-checked (the
+    gather kernel reads array[t, idx] unchecked)."""
     if sel is None:
         sel = slice(None)
     if isinstance(sel, slice):
         return list(range(*sel.indices(n)))
-    return [int(v) for v in sel]
+    out = []
+    for v in sel:
+        v = int(v)
+        if v < -n or v >= n:
+            raise IndexError('variable index %d out of range for %d variables' % (v, n))
+        out.append(v % n)
+    return out
 
 
 class DeviceDataFeed(object):
     def __init__(self, array, batch_size=32, input_slice=None, output_slice=None, input_time_steps=1,
                  output_time_steps=1, interval=1, shuffle=False, insolation_array=None, constants=None,
-                 drop_remainder=False, dtype=torch.float32, device='cuda', seed=0, sequence=None):
+                 drop_remainder=False, dtype=torch.float32, device='cuda', seed=0, sequence=None, rank=0, world=1):
         for v, nm in ((input_time_steps, 'input_time_steps'), (output_time_steps, 'output_time_steps'),
                       (batch_size, 'batch_size'), (interval, 'interval')):
             if int(v) <= 0:
@@ -72,6 +80,12 @@ class DeviceDataFeed(object):
         if self._n_sample <= 0:
             raise ValueError('the array is too short for %d + %d time steps at interval %d' % (self.t_in, self.t_out,
                                                                                                 self.interval))
+        # data parallel: every rank shuffles with the SAME seed and takes every world-th sample of the epoch order, so the
+        # ranks see disjoint shards of one global batch (generators.py shuffles once per process; Keras multi_gpu_model
+        # splits each batch across the GPUs, models.py:105-110)
+        self.rank, self.world = int(rank), int(world)
+        if not 0 <= self.rank < self.world:
+            raise ValueError('rank %d outside world of %d' % (self.rank, self.world))
         self._rng = np.random.RandomState(seed)
         self.on_epoch_end()
 
@@ -89,11 +103,15 @@ class DeviceDataFeed(object):
         self._indices = np.arange(self._n_sample)
         if self.shuffle:
             self._rng.shuffle(self._indices)
+        if self.world > 1:           # equal shards: drop the tail that does not divide by the world size
+            usable = (self._n_sample // self.world) * self.world
+            self._indices = self._indices[:usable][self.rank::self.world]
 
-    def __len__(self):                      # generators.py:986-993
+    def __len__(self):                      # generators.py:986-993 (per rank: batch_size samples of this rank's shard)
+        n = len(self._indices)
         if self.drop_remainder:
-            return self._n_sample // self.batch_size
-        return int(np.ceil(self._n_sample / self.batch_size))
+            return n // self.batch_size
+        return int(np.ceil(n / self.batch_size))
 
     def __getitem__(self, index):           # generators.py:995-1011
         if index < 0 or index >= len(self):

@@ -114,12 +114,33 @@ class DataParallelTrainer(object):
             raise _lib.DlwpcsError('DataParallelTrainer needs the model on a CUDA device (no CPU path)')
         self.m = torch.zeros_like(self.flat.param)
         self.v = torch.zeros_like(self.flat.param)
-        self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
+        self._hyper = dict(lr=float(lr), beta1=float(beta1), beta2=float(beta2), eps=float(eps))
         self.group = group
         self.t = 0
         self.step_counter = torch.zeros(1, dtype=torch.int32, device=self.flat.param.device)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.flat.param.device)
         self.flat.broadcast_params(group=group)
+
+    # lr / beta1 / beta2 / eps are baked into the captured launches as scalars: changing one (a learning-rate schedule,
+    # models_torch.py:297-298) drops the cached graphs so that the next step re-captures with the new value
+    def _set_hyper(self, name, value):
+        if self._hyper[name] != float(value):
+            self._hyper[name] = float(value)
+            self._graphs.clear()
+
+    lr = property(lambda self: self._hyper['lr'], lambda self, v: self._set_hyper('lr', v))
+    beta1 = property(lambda self: self._hyper['beta1'], lambda self, v: self._set_hyper('beta1', v))
+    beta2 = property(lambda self: self._hyper['beta2'], lambda self, v: self._set_hyper('beta2', v))
+    eps = property(lambda self: self._hyper['eps'], lambda self, v: self._set_hyper('eps', v))
+
+    def close(self):
+        """Release the captured CUDA graphs (they hold NCCL kernels of the communicator): call before
+        ``torch.distributed.destroy_process_group()``."""
+        torch.cuda.synchronize(self.flat.param.device)
+        self._graphs.clear()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize(self.flat.param.device)
 
     def forward_backward(self, x, target):
         """Gradients of mean((model(x) - target)^2) accumulated into the flat buffer; returns the loss (device scalar)."""
@@ -176,7 +197,12 @@ class DataParallelTrainer(object):
 
     def step(self, x, target):
         """One optimizer step.  With ``use_graph`` the whole step (forward, loss, backward, all-reduce, Adam: ~150
-        launches) is captured once per input shape into a CUDA graph and replayed."""
+        launches) is captured once per input shape into a CUDA graph and replayed.
+
+        Returns the trainer's persistent 1-element loss buffer (no allocation, no synchronisation): it is overwritten by
+        the next step -- ``.clone()`` or ``.item()`` it to keep a history.  Every rank must hold the same number of
+        samples (the gradient of the global-batch mean is the 1/world-scaled sum of the shard means, train_tf.py:166);
+        ``shard_batch`` gives equal shards whenever the global batch is a multiple of the world size."""
         self.t += 1
         return self._graphed('step', [x, target], self._step_body)
 

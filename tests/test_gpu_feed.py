@@ -66,3 +66,22 @@ def test_feed_sequence_vs_reference_golden(golden_dir):
             assert np.array_equal(solars[s - 1].cpu().numpy(), g['solar_%s_%d' % (k, s)])
         for s in range(S):
             assert np.array_equal(targets[s].cpu().numpy(), g['t_%s_%d' % (k, s)])
+
+
+def test_feed_rank_shards_are_disjoint_and_indices_checked():
+    """Data-parallel feed: same seed on every rank, every world-th sample of the shuffled epoch order."""
+    from dlwp_cs_b200.feed import DeviceDataFeed
+    rng = np.random.default_rng(5)
+    array = rng.standard_normal((23, 3, 6, 4, 4)).astype(np.float32)
+    feeds = [DeviceDataFeed(array, batch_size=2, input_time_steps=2, output_time_steps=2, shuffle=True, seed=7,
+                            drop_remainder=True, rank=r, world=4) for r in range(4)]
+    shards = [set(f._indices.tolist()) for f in feeds]
+    assert all(len(s) == feeds[0]._n_sample // 4 for s in shards)
+    assert len(set().union(*shards)) == 4 * len(shards[0])          # disjoint
+    assert len({len(f) for f in feeds}) == 1                         # same number of batches on every rank
+    with pytest.raises(IndexError):
+        DeviceDataFeed(array, input_slice=[0, 3])
+    f = DeviceDataFeed(array, input_slice=[-1, 0], output_slice=[2])
+    assert f.in_idx == [2, 0]
+    with pytest.raises(ValueError):
+        DeviceDataFeed(array, rank=2, world=2)

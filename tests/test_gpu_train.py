@@ -137,3 +137,40 @@ def test_trainer_sequence_step_matches_oracle_autograd(lib):
         np.testing.assert_allclose(p.grad.double().cpu().numpy(), gref, rtol=1e-4,
                                    atol=1e-5 * max(float(np.abs(gref).max()), 1e-30))
     assert int(trainer.step_counter) == 1
+
+
+def test_mse_loss_grad_rejects_mismatched_target(lib):
+    """A float32 target under a bf16 output (or a smaller target) used to be reinterpreted / read out of bounds."""
+    y = torch.randn(2, 6, 8, 8, 8).cuda().bfloat16()
+    loss = torch.zeros(1, device='cuda')
+    with pytest.raises(lib.DlwpcsError):
+        lib.mse_loss_grad(y, torch.randn(2, 6, 8, 8, 8).cuda(), loss)                   # dtype
+    with pytest.raises(lib.DlwpcsError):
+        lib.mse_loss_grad(y, torch.randn(1, 6, 8, 8, 8).cuda().bfloat16(), loss)       # shape
+    with pytest.raises(lib.DlwpcsError):
+        lib.mse_loss_grad(y, y.clone(), torch.zeros(2, device='cuda'))                  # accumulator
+    lib.mse_loss_grad(y, y.clone(), loss)
+    assert float(loss) == 0.0
+
+
+def test_trainer_hyperparameter_change_recaptures(lib):
+    """lr is baked into the captured step: assigning a new one must take effect."""
+    from dlwp_cs_b200.unet import CubeSphereUNet2
+    from dlwp_cs_b200.train import DataParallelTrainer
+    torch.manual_seed(0)
+    model = CubeSphereUNet2(6, 4, base=8).cuda()
+    tr = DataParallelTrainer(model, lr=1e-3)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 6, 8, 8, 6, generator=g).cuda()
+    t = torch.randn(2, 6, 8, 8, 4, generator=g).cuda()
+    tr.step(x, t)
+    p0 = tr.flat.param.clone()
+    tr.lr = 0.0                                  # frozen: the next step must not move the parameters
+    assert not tr._graphs
+    tr.step(x, t)
+    assert torch.equal(tr.flat.param, p0)
+    tr.lr = 1e-2
+    tr.step(x, t)
+    assert not torch.equal(tr.flat.param, p0)
+    tr.close()
+    assert not tr._graphs
