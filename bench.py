@@ -13,6 +13,11 @@ Timing: CUDA events on the launching stream around every bench step, L2 flushed 
 the timed region, barrier + synchronize before and after, max over ranks.
 `--impl reference`: the reference's TensorFlow path cannot run here; its CPU restatement (oracle/cs_oracle.py,
 torch/oneDNN on all host cores, with the per-step host hop of DLWP/model/models.py:446-454) is timed on a bounded sample.
+
+Besides the headline line's keys the JSON carries: `train_*` (BASELINE configs[2]/[3]: data-parallel training step),
+`dp_equivalence` (N > 1: one DP step on N shards == one 1-GPU step on the concatenated batch), and `configs` with the other
+BASELINE configurations -- configs[0] (single 3->3 convolution, batch 1), B = 1 rollout latency, configs[4] (C96, 12
+variables, 1000 steps).
 """
 import argparse
 import json
@@ -28,7 +33,7 @@ if ROOT not in sys.path:
 
 
 def _oracle():
-    """The CPU restatement under oracle/ -- imported by the two CPU legs only (cpu_baseline, --impl reference); the GPU
+    """The CPU restatement under oracle/ -- imported by the CPU legs only (cpu_baseline, --impl reference); the GPU
     arm never touches it."""
     p = os.path.join(ROOT, 'oracle')
     if p not in sys.path:
@@ -39,12 +44,8 @@ def _oracle():
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-N_FACE = 48
-C_PROG = 14       # 7 variables x 2 time steps
 C_FORC = 4        # 2 insolation + 2 constants
 BASE = 32
-# face edge of every unet2 layer relative to the input (two poolings): Azure/train_cs.py:277-305
-EDGE_DIV = {'conv_2d_2': 2, 'conv_2d_2_2': 2, 'conv_2d_5_2': 4, 'conv_2d_5': 4, 'conv_2d_6_2': 2, 'conv_2d_6': 2}
 METRIC = 'forecast steps/sec C48 6-face U-Net rollout'
 UNIT = 'sample-steps/s'
 
@@ -99,25 +100,30 @@ class ClockSampler(object):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def layer_work(name, k, cin, cout, edge, batch, in_bytes, out_bytes):
+def layer_work(k, cin, cout, edge, batch, in_bytes, out_bytes):
     flop = 2.0 * batch * 6 * edge * edge * k * k * cin * cout
     byts = batch * 6 * edge * edge * (cin * in_bytes + cout * out_bytes)   # conv in + out, halo not counted
     return flop, byts
 
 
-def synth_inputs(batch, seed=0):
+def synth_inputs(batch, n_face, c_prog, seed=0):
     g = torch.Generator().manual_seed(seed)
-    state = torch.randn(batch, 6, N_FACE, N_FACE, C_PROG, generator=g).clamp_(-5, 5)
-    forcing = torch.rand(batch, 6, N_FACE, N_FACE, C_FORC, generator=g)
+    state = torch.randn(batch, 6, n_face, n_face, c_prog, generator=g).clamp_(-5, 5)
+    forcing = torch.rand(batch, 6, n_face, n_face, C_FORC, generator=g)
     return state, forcing
 
 
-def cpu_rollout_rate(batch, steps, threads, repeats=1):
+def workload_name(n_face, c_prog, rollout_steps, batch):
+    return ('unet2 (Weyn-2020) C%d rollout, %d vars x 2 tsteps in/out (+2 solar +2 const), ' % (n_face, c_prog // 2) +
+            '%d 6-hr steps, ensemble of %d members per GPU, random-init weights' % (rollout_steps, batch))
+
+
+def cpu_rollout_rate(batch, steps, threads, n_face, c_prog, repeats=1):
     """The reference path's CPU restatement: oracle rollout, oneDNN conv, numpy hop per step.  -> sample-steps/s"""
     O = _oracle()
     torch.set_num_threads(threads)
-    params = O.make_unet2_params(C_PROG + C_FORC, C_PROG, base=BASE, seed=1)
-    state, forcing = synth_inputs(batch)
+    params = O.make_unet2_params(c_prog + C_FORC, c_prog, base=BASE, seed=1)
+    state, forcing = synth_inputs(batch, n_face, c_prog)
     with torch.no_grad():
         O.rollout_fast(params, state, forcing, 1)        # warm-up (oneDNN primitive cache)
         best = None
@@ -129,15 +135,17 @@ def cpu_rollout_rate(batch, steps, threads, repeats=1):
     return batch * steps / best, best
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, n_face, c_prog):
+    """CPU arm: same members per bench step as the GPU arm, a bounded number of 6-hour steps of the same rollout (the CPU
+    cost per sample-step does not depend on how far the rollout has come)."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     b, s = args.ref_batch, args.ref_steps
     O = _oracle()
     torch.set_num_threads(threads)
-    params = O.make_unet2_params(C_PROG + C_FORC, C_PROG, base=BASE, seed=1)
-    state, forcing = synth_inputs(b)
+    params = O.make_unet2_params(c_prog + C_FORC, c_prog, base=BASE, seed=1)
+    state, forcing = synth_inputs(b, n_face, c_prog)
     times = []
     with torch.no_grad():
         for i in range(args.warmup + args.steps):
@@ -147,38 +155,104 @@ def run_reference(args, rank, world):
                 times.append(time.perf_counter() - t0)
     total = sum(times)
     value = b * s * len(times) / total
-    sample = ('oracle/cs_oracle.py rollout_fast (torch-CPU oneDNN restatement of DLWP/custom.py as LUT gather + batched faces, models.py:446-454 host hop), '
-              'fp32, %d members x %d steps per bench step' % (b, s))
+    sample = ('oracle/cs_oracle.py rollout_fast (torch-CPU oneDNN restatement of DLWP/custom.py as LUT gather + batched '
+              'faces, models.py:446-454 host hop), fp32, %d members x %d of the %d steps per bench step'
+              % (b, s, args.rollout_steps))
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'unet2 C48 rollout, 7 vars x 2 tsteps (+2 solar +2 const in), bounded sample of '
-                                   'the %d-step x %d-member job' % (args.rollout_steps, args.batch),
-                       'rollout_steps': s, 'batch': b},
+            'config': {'workload': workload_name(n_face, c_prog, args.rollout_steps, args.batch),
+                       'rollout_steps': args.rollout_steps, 'batch_per_gpu': args.batch, 'face_edge': n_face},
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
 
 
-def time_layers(eng, reps=20):
-    """Per-layer device time of one model step (CUDA events on the current stream, L2-cold-ish: the ensemble's
-    activations are far larger than L2).  -> list of (name, ms)"""
+def time_layers(eng, flush, reps=10):
+    """Per-layer device time of one model step: CUDA events around each single launch, L2 flushed (512 MiB write)
+    before every repetition so that the small layers are not served from a warm L2.  -> list of (name, ms)"""
+    from dlwp_cs_b200 import _lib
     out = []
     for name, d, s0, s1, dst, packed in eng.plan:
-        from dlwp_cs_b200 import _lib
         o = eng.ring[0] if dst == 'out' else eng.buf[dst]
         a, b = eng._src(s0, 0), eng._src(s1, 0)
         for _ in range(3):
             _lib.conv2d_fwd(d, a, b, packed, out=o)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        evs = []
         for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             _lib.conv2d_fwd(d, a, b, packed, out=o)
-        e1.record()
-        e1.synchronize()
-        out.append((name, e0.elapsed_time(e1) / reps))
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        ts = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
+        out.append((name, ts[len(ts) // 2]))           # median
     return out
+
+
+def timed_rollout(eng, flush, steps, warmup):
+    """ms per bench step (one whole rollout) of an engine whose inputs are resident, L2 flushed between steps."""
+    for _ in range(warmup):
+        eng.launch()
+    torch.cuda.synchronize()
+    ev = []
+    for _ in range(steps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        eng.launch()
+        e.record()
+        ev.append((s, e))
+    torch.cuda.synchronize()
+    return sum(s.elapsed_time(e) for s, e in ev) / steps
+
+
+def conv_3to3_record(dev, threads):
+    """BASELINE configs[0]: single CubeSphereConv2D forward, C48, 3 -> 3 channels, batch 1, float32."""
+    from dlwp_cs_b200 import _lib
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 6, 48, 48, 3, generator=g)
+    lim = (6.0 / 54.0) ** 0.5
+    w = [(torch.rand(3, 3, 3, 3, generator=g) * 2 - 1) * lim for _ in range(2)]
+    b = [(torch.rand(3, generator=g) * 2 - 1) * 0.1 for _ in range(2)]
+    d = _lib.make_desc(1, 48, 3, 3, (3, 3), halo=1)
+    xd = x.to(dev)
+    packed = _lib.pack_weights(d, w[0].to(dev), w[1].to(dev), None, b[0].to(dev), b[1].to(dev))
+    for _ in range(5):
+        y = _lib.conv2d_fwd(d, xd, None, packed)
+    reps = 200
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        _lib.conv2d_fwd(d, xd, None, packed, out=y)
+    e1.record()
+    e1.synchronize()
+    gpu_us = 1e3 * e0.elapsed_time(e1) / reps
+    xn, wn, bn = x.numpy(), [t.numpy() for t in w], [t.numpy() for t in b]
+    for _ in range(3):
+        yh = _lib.conv2d_fwd_host(d, xn, wn[0], wn[1], None, bn[0], bn[1])
+    t0 = time.perf_counter()
+    for _ in range(50):
+        yh = _lib.conv2d_fwd_host(d, xn, wn[0], wn[1], None, bn[0], bn[1])
+    host_us = 1e6 * (time.perf_counter() - t0) / 50
+    O = _oracle()
+    torch.set_num_threads(threads)
+    with torch.no_grad():
+        f = lambda: O.cube_sphere_conv2d_fast(O.cube_sphere_pad_fast(x, 1), w[0], w[1], b[0], b[1])
+        for _ in range(5):
+            yc = f()
+        t0 = time.perf_counter()
+        for _ in range(100):
+            yc = f()
+        cpu_us = 1e6 * (time.perf_counter() - t0) / 100
+    err = float((torch.from_numpy(yh) - yc).abs().max() / yc.abs().max())
+    return {'config': 'BASELINE configs[0]: single CubeSphereConv2D fwd (pad 1 fused), C48, 3->3 ch, batch 1, float32',
+            'gpu_us_resident': round(gpu_us, 2), 'gpu_us_host_buffers': round(host_us, 1), 'cpu_us': round(cpu_us, 1),
+            'cpu_cores': threads, 'cpu_kind': 'port (oracle LUT gather + oneDNN conv)', 'max_rel_diff_vs_cpu': err,
+            'note': '2.24 MFLOP / 0.33 MB: launch-latency bound on the GPU; host-buffer call = H2D + pack + kernel + D2H'}
 
 
 def main():
@@ -192,25 +266,27 @@ def main():
     ap.add_argument('--face-edge', type=int, default=48, help='48 = C48 (headline config), 96 = C96 (BASELINE configs[4])')
     ap.add_argument('--variables', type=int, default=7, help='prognostic variables per time step (x2 time steps)')
     ap.add_argument('--dtype', default='auto', choices=['auto', 'bf16', 'fp32'])
-    ap.add_argument('--ref-batch', type=int, default=16)
-    ap.add_argument('--ref-steps', type=int, default=100)
+    ap.add_argument('--ref-batch', type=int, default=None, help='CPU arm: members per bench step (default: --batch)')
+    ap.add_argument('--ref-steps', type=int, default=25, help='CPU arm: 6-hour steps per bench step (bounded sample)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-train', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the configs[0] / B=1 latency / C96 sub-records')
     ap.add_argument('--train-batch', type=int, default=32, help='training samples per GPU per step')
-    ap.add_argument('--train-steps', type=int, default=5)
+    ap.add_argument('--train-steps', type=int, default=10)
     ap.add_argument('--train-dtype', default='bf16', choices=['bf16', 'f32'])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.ref_batch is None:
+        args.ref_batch = args.batch
 
-    global N_FACE, C_PROG
-    N_FACE, C_PROG = args.face_edge, 2 * args.variables
+    n_face, c_prog = args.face_edge, 2 * args.variables
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
 
     if args.impl == 'reference':
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, n_face, c_prog)
         return
 
     from dlwp_cs_b200 import _lib
@@ -232,13 +308,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
     torch.manual_seed(1)                      # random-init weights of the architecture (glorot-uniform kernels, zero biases)
-    model = CubeSphereUNet2(C_PROG + C_FORC, C_PROG, base=BASE).to(dev)
+    model = CubeSphereUNet2(c_prog + C_FORC, c_prog, base=BASE).to(dev)
     dtype = args.dtype
     eng = None
     if dtype in ('auto', 'bf16'):
         try:
-            eng = RolloutEngine(model, args.batch, N_FACE, args.rollout_steps, forcing_channels=C_FORC,
+            eng = RolloutEngine(model, args.batch, n_face, args.rollout_steps, forcing_channels=C_FORC,
                                 dtype=torch.bfloat16, use_graph=not args.no_graph)
             dtype = 'bf16'
         except _lib.DlwpcsError as e:
@@ -246,13 +328,13 @@ def main():
                 raise
             sys.stderr.write('bf16 tensor-core path unavailable (%s); benchmarking the fp32 path\n' % e)
     if eng is None:
-        eng = RolloutEngine(model, args.batch, N_FACE, args.rollout_steps, forcing_channels=C_FORC,
+        eng = RolloutEngine(model, args.batch, n_face, args.rollout_steps, forcing_channels=C_FORC,
                             dtype=torch.float32, use_graph=not args.no_graph)
         dtype = 'fp32'
     tdt = torch.bfloat16 if dtype == 'bf16' else torch.float32
     esz = 2 if dtype == 'bf16' else 4
 
-    state, forcing = synth_inputs(args.batch, seed=rank)
+    state, forcing = synth_inputs(args.batch, n_face, c_prog, seed=rank)
     h_state, h_forcing = state.to(tdt).pin_memory(), forcing.to(tdt).pin_memory()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
@@ -292,10 +374,24 @@ def main():
     clocks = sampler.stop()
     e2e_ms = sum(s.elapsed_time(e) for s, e in ev2)
 
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = t.tolist()
+    # ---------------- the ceiling of the end-to-end arm: the same forecast bytes as a plain device -> pinned-host copy, all
+    # ranks at once (what the host's PCIe / memory system sinks when nothing else is going on)
+    d2h_bytes = h_ring.numel() * esz
+    src = eng.ring.reshape(-1)[:h_ring.numel()]               # a contiguous run of exactly the forecast's byte count
+    h_flat = h_ring.reshape(-1)
+    for _ in range(2):
+        h_flat.copy_(src, non_blocking=True)
+    barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(3):
+        h_flat.copy_(src, non_blocking=True)
+    e.record()
+    barrier()
+    copy_ms = s.elapsed_time(e) / 3
+    del src
+
+    dev_ms, e2e_ms, copy_ms = max_over_ranks([dev_ms, e2e_ms, copy_ms])
     units = float(args.rollout_steps) * args.batch * args.steps * world
     value = units / (dev_ms * 1e-3)
     e2e_value = units / (e2e_ms * 1e-3)
@@ -305,15 +401,14 @@ def main():
     layers = []
     if rank == 0:
         pk = peaks()
-        lt = time_layers(eng)
-        specs = {s[0]: s for s in unet2_layer_specs(C_PROG + C_FORC, C_PROG, BASE)}
+        lt = time_layers(eng, flush)
+        specs = {s[0]: s for s in unet2_layer_specs(c_prog + C_FORC, c_prog, BASE)}
         edges = {name: d.n for name, d, *_ in eng.plan}
         tot = sum(ms for _, ms in lt)
         for name, ms in lt:
             _, k, ci, co = specs[name]
-            flop, byts = layer_work(name, k, ci, co, edges[name], args.batch, esz, esz)
+            flop, byts = layer_work(k, ci, co, edges[name], args.batch, esz, esz)
             tf, gb = flop / ms / 1e9, byts / ms / 1e6
-            tf_peak = pk['tf_sust'] if dtype == 'bf16' else None
             t_c = flop / (pk['tf_sust'] * 1e12) if dtype == 'bf16' else 0.0
             t_m = byts / (pk['hbm'] * 1e9)
             layers.append({'layer': name, 'ms': round(ms, 4), 'share': round(ms / tot, 3), 'tflops': round(tf, 1),
@@ -327,31 +422,85 @@ def main():
             roof = {'bound': 'hbm', 'achieved': top['gbs'], 'peak': pk['hbm'], 'unit': 'GB/s',
                     'frac': round(top['gbs'] / pk['hbm'], 4)}
         traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
-        if dtype == 'bf16' and os.path.exists(tpath):            # DRAM bytes of that launch from the ncu --set full capture
-            tj = json.load(open(tpath))
-            if top['layer'] in tj['dram_bytes_per_launch']:
-                traffic = tj['dram_bytes_per_launch'][top['layer']] * args.batch / tj['batch']
+        for tname in ('r2_traffic.json', 'r1_traffic.json'):     # DRAM bytes of that launch from the ncu --set full capture
+            tpath = os.path.join(ROOT, 'profiles', tname)
+            if dtype == 'bf16' and os.path.exists(tpath):
+                tj = json.load(open(tpath))
+                if top['layer'] in tj['dram_bytes_per_launch']:
+                    traffic = tj['dram_bytes_per_launch'][top['layer']] * args.batch / tj['batch']
+                    break
+        step_ms = dev_ms / args.steps / args.rollout_steps          # one 6-hour model step inside the graph-replayed rollout
+        t_roof = sum(max(layer_work(s[1], s[2], s[3], edges[s[0]], args.batch, esz, esz)[0] / (pk['tf_sust'] * 1e12)
+                         if dtype == 'bf16' else 0.0,
+                         layer_work(s[1], s[2], s[3], edges[s[0]], args.batch, esz, esz)[1] / (pk['hbm'] * 1e9))
+                     for s in specs.values())
         roof.update({'traffic': traffic, 'kernel': 'cs_conv (%s: %s)' % (dtype, top['layer']), 'peak_source': pk['src'],
                      'share_of_step': top['share'],
-                     'whole_step_frac_of_roof': round(sum(r['frac_of_roof'] * r['ms'] for r in layers) / tot, 3)})
+                     'whole_step_frac_of_roof': round(t_roof * 1e3 / step_ms, 3),
+                     'whole_step_us': round(1e3 * step_ms, 1),
+                     'note': 'per-layer times: single launches, L2 flushed before each; whole_step: sum of the per-layer '
+                             'roofline times / the measured 6-hour step inside the rollout graph'})
+
+    # ---------------- the other BASELINE configurations (rank 0, N = 1 only: they are single-GPU records)
+    extra = None
+    threads = os.cpu_count() or 1
+    if rank == 0 and world == 1 and not args.no_extra and dtype == 'bf16':
+        extra = {}
+        extra['conv_3to3_b1'] = conv_3to3_record(dev, threads)
+        # B = 1 latency of the headline rollout (report both B = 1 latency and batched-ensemble throughput)
+        e1 = RolloutEngine(model, 1, n_face, args.rollout_steps, forcing_channels=C_FORC, dtype=tdt)
+        e1.load_inputs(h_state[:1], h_forcing[:1])
+        ms1 = timed_rollout(e1, flush, 5, 3)
+        extra['rollout_b1_latency'] = {'config': 'C%d unet2 rollout, 1 member, %d steps' % (n_face, args.rollout_steps),
+                                       'ms_per_rollout': round(ms1, 3),
+                                       'us_per_6h_step': round(1e3 * ms1 / args.rollout_steps, 1),
+                                       'steps_per_s': round(args.rollout_steps / (ms1 * 1e-3), 1)}
+        del e1
+        if n_face == 48:
+            # BASELINE configs[4]: C96, 12 variables x 2 time steps, 1000-step rollout, 16 members
+            cp96, b96, st96 = 24, 16, 1000
+            torch.manual_seed(1)
+            m96 = CubeSphereUNet2(cp96 + C_FORC, cp96, base=BASE).to(dev)
+            e96 = RolloutEngine(m96, b96, 96, st96, forcing_channels=C_FORC, dtype=tdt)
+            s96, f96 = synth_inputs(b96, 96, cp96)
+            e96.load_inputs(s96.to(tdt).pin_memory(), f96.to(tdt).pin_memory())
+            ms96 = timed_rollout(e96, flush, 3, 3)
+            sp96 = unet2_layer_specs(cp96 + C_FORC, cp96, BASE)
+            div = {'conv_2d_2': 2, 'conv_2d_2_2': 2, 'conv_2d_5_2': 4, 'conv_2d_5': 4, 'conv_2d_6_2': 2, 'conv_2d_6': 2}
+            pk = peaks()
+            t_roof96 = sum(max(layer_work(k, ci, co, 96 // div.get(nm, 1), b96, esz, esz)[0] / (pk['tf_sust'] * 1e12),
+                               layer_work(k, ci, co, 96 // div.get(nm, 1), b96, esz, esz)[1] / (pk['hbm'] * 1e9))
+                           for nm, k, ci, co in sp96)
+            rec = {'config': 'BASELINE configs[4]: C96 unet2, 12 vars x 2 tsteps (+2 +2), %d 6-hr steps, %d members' % (st96, b96),
+                   'value': round(st96 * b96 / (ms96 * 1e-3), 1), 'unit': UNIT, 'ms_per_rollout': round(ms96, 2),
+                   'us_per_6h_step': round(1e3 * ms96 / st96, 1),
+                   'roofline': {'whole_step_frac_of_roof': round(t_roof96 * 1e3 / (ms96 / st96), 3),
+                                'peak_source': pk['src']}}
+            del e96, m96
+            torch.cuda.empty_cache()
+            if not args.no_cpu_baseline:
+                v, secs = cpu_rollout_rate(4, 50, threads, 96, cp96)
+                rec['cpu_baseline'] = {'value': round(v, 2), 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                       'sample': '4 members x 50 of the 1000 steps = %.1f s' % secs}
+            extra['c96_12var_1000steps'] = rec
 
     # ---------------- training step (BASELINE.json configs[2]/[3]): batch-sharded DP, one flat NCCL all-reduce per step
     train = None
+    dp_check = None
     rollout_launches = args.steps * args.rollout_steps * eng.launches_per_step * 2
     if not args.no_train:
         del eng, flush
         torch.cuda.empty_cache()
         from dlwp_cs_b200.train import DataParallelTrainer
         torch.manual_seed(1)
-        tmodel = CubeSphereUNet2(C_PROG + C_FORC, C_PROG, base=BASE).to(dev)
+        tmodel = CubeSphereUNet2(c_prog + C_FORC, c_prog, base=BASE).to(dev)
         trainer = DataParallelTrainer(tmodel, lr=1e-3)
         g = torch.Generator().manual_seed(100 + rank)
         tb = args.train_batch
         ttd = torch.bfloat16 if args.train_dtype == 'bf16' else torch.float32
-        xs = torch.randn(tb, 6, N_FACE, N_FACE, C_PROG + C_FORC, generator=g).to(dev).to(ttd)
-        ts = torch.randn(tb, 6, N_FACE, N_FACE, C_PROG, generator=g).to(dev).to(ttd)
-        for _ in range(2):
+        xs = torch.randn(tb, 6, n_face, n_face, c_prog + C_FORC, generator=g).to(dev).to(ttd)
+        ts = torch.randn(tb, 6, n_face, n_face, c_prog, generator=g).to(dev).to(ttd)
+        for _ in range(3):
             trainer.step(xs, ts)
         barrier()
         s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -360,61 +509,112 @@ def main():
             loss = trainer.step(xs, ts)
         e_ev.record()
         barrier()
-        tt = torch.tensor([s_ev.elapsed_time(e_ev)], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        tms = float(tt.item()) / args.train_steps
-        train = {'metric': 'train samples/sec, unet2 C%d fwd+bwd+Adam' % N_FACE, 'value': tb * world / (tms * 1e-3),
+        tms = max_over_ranks([s_ev.elapsed_time(e_ev)])[0] / args.train_steps
+        div = {'conv_2d_2': 2, 'conv_2d_2_2': 2, 'conv_2d_5_2': 4, 'conv_2d_5': 4, 'conv_2d_6_2': 2, 'conv_2d_6': 2}
+        train = {'metric': 'train samples/sec, unet2 C%d fwd+bwd+Adam' % n_face, 'value': tb * world / (tms * 1e-3),
                  'unit': 'samples/s', 'ms_per_step': tms, 'global_batch': tb * world, 'batch_per_gpu': tb,
                  'dtype': args.train_dtype, 'parallelism': 'dp%d, one flat all-reduce of %d float32 gradients per step'
                                                 % (world, trainer.flat.count),
                  'loss': float(loss.item()),
                  # forward + dgrad + wgrad = 3 x the forward FLOP of every layer
                  'algorithmic_gflop_per_sample': round(3e-9 * sum(
-                     layer_work(s[0], s[1], s[2], s[3], N_FACE // EDGE_DIV.get(s[0], 1), 1, 2, 2)[0]
-                     for s in unet2_layer_specs(C_PROG + C_FORC, C_PROG, BASE)), 3),
+                     layer_work(s[1], s[2], s[3], n_face // div.get(s[0], 1), 1, 2, 2)[0]
+                     for s in unet2_layer_specs(c_prog + C_FORC, c_prog, BASE)), 3),
                  'note': ('bf16 activations: forward, dgrad and wgrad on tcgen05 kernels (fp32 accumulation in tensor '
                           'memory); float32 master weights, fused Adam')
                  if args.train_dtype == 'bf16' else 'float32 CUDA-core kernels (1e-5 parity path)'}
-
-    if train is not None:
         train['tflops'] = round(train['value'] * train['algorithmic_gflop_per_sample'] * 1e-3, 1)
+        trainer.close()
+        del trainer, tmodel
+
+        # ---- data-parallel equivalence (train_tf.py:166): ONE optimizer step on `world` shards ==
+        # one single-GPU step on the concatenated batch; parameters after Adam bitwise identical on every rank
+        if dist is not None:
+            cb = 4                                                     # samples per rank for the check
+            gg = torch.Generator().manual_seed(777)                    # the same global batch on every rank
+            gx = torch.randn(cb * world, 6, n_face, n_face, c_prog + C_FORC, generator=gg).to(dev).to(ttd)
+            gt = torch.randn(cb * world, 6, n_face, n_face, c_prog, generator=gg).to(dev).to(ttd)
+            torch.manual_seed(5)
+            m_dp = CubeSphereUNet2(c_prog + C_FORC, c_prog, base=BASE).to(dev)
+            torch.manual_seed(5)
+            m_one = CubeSphereUNet2(c_prog + C_FORC, c_prog, base=BASE).to(dev)
+            t_dp = DataParallelTrainer(m_dp, lr=1e-3, use_graph=False)
+            t_one = DataParallelTrainer(m_one, lr=1e-3, use_graph=False, distributed=False)
+            l_dp = t_dp.step(gx[rank * cb:(rank + 1) * cb], gt[rank * cb:(rank + 1) * cb]).clone()
+            l_one = t_one.step(gx, gt).clone()
+            torch.cuda.synchronize()
+            g_dp, g_one = t_dp.flat.grad / world, t_one.flat.grad      # summed shard-mean gradients / world vs global mean
+            gscale = float(g_one.abs().max())
+            gdiff = float((g_dp - g_one).abs().max()) / max(gscale, 1e-30)
+            lsum = l_dp.clone()
+            dist.all_reduce(lsum)
+            ldiff = abs(float(lsum) / world - float(l_one)) / max(abs(float(l_one)), 1e-30)
+            plist = [torch.empty_like(t_dp.flat.param) for _ in range(world)]
+            dist.all_gather(plist, t_dp.flat.param)
+            bitwise = all(torch.equal(plist[0], p) for p in plist[1:])
+            pdiff = float((t_dp.flat.param - t_one.flat.param).abs().max())
+            vals = max_over_ranks([gdiff, ldiff, 0.0 if bitwise else 1.0, pdiff])
+            tol = 2e-3 if args.train_dtype == 'bf16' else 1e-4
+            dp_check = {'grad_max_rel_diff_vs_1gpu': vals[0], 'loss_rel_diff_vs_1gpu': vals[1],
+                        'params_bitwise_across_ranks': vals[2] == 0.0, 'param_max_abs_diff_vs_1gpu_after_adam': vals[3],
+                        'tolerance': tol, 'samples_per_rank': cb, 'dtype': args.train_dtype,
+                        'ok': bool(vals[0] <= tol and vals[1] <= tol and vals[2] == 0.0 and vals[3] <= 2.5e-3)}
+            del t_dp, t_one, m_dp, m_one
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        v, secs = cpu_rollout_rate(args.ref_batch, args.ref_steps, threads)
+        v, secs = cpu_rollout_rate(args.ref_batch, args.ref_steps, threads, n_face, c_prog)
         cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-               'sample': 'oracle rollout_fast (torch-CPU oneDNN restatement, LUT-gather halo, fp32, host hop per step), %d members x %d '
-                         'steps = %.1f s' % (args.ref_batch, args.ref_steps, secs)}
+               'sample': 'oracle rollout_fast (torch-CPU oneDNN restatement, LUT-gather halo, fp32, host hop per step), '
+                         '%d members x %d of the %d steps = %.1f s' % (args.ref_batch, args.ref_steps, args.rollout_steps, secs)}
 
     if rank == 0:
         h2d = (h_state.numel() + h_forcing.numel()) * esz
-        d2h = h_ring.numel() * esz
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if dtype == 'bf16' else 'f32',
                 'data': 'synthetic',
-                'config': {'workload': 'unet2 (Weyn-2020) C%d rollout, %d vars x 2 tsteps in/out (+2 solar +2 const), ' % (N_FACE, C_PROG // 2) +
-                                       '%d 6-hr steps, ensemble of %d members per GPU, random-init weights'
-                                       % (args.rollout_steps, args.batch),
-                           'rollout_steps': args.rollout_steps, 'batch_per_gpu': args.batch, 'face_edge': N_FACE,
+                'config': {'workload': workload_name(n_face, c_prog, args.rollout_steps, args.batch),
+                           'rollout_steps': args.rollout_steps, 'batch_per_gpu': args.batch, 'face_edge': n_face,
                            'l2': '512 MiB flush write between bench steps; per-step activation set %.0f MiB > L2'
-                                 % (args.batch * 6 * N_FACE * N_FACE * 32 * esz * 4 / 2 ** 20),
+                                 % (args.batch * 6 * n_face * n_face * 32 * esz * 4 / 2 ** 20),
                            'cuda_graph': not args.no_graph, 'parallelism': 'replicas x%d' % world},
-                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                        'ms_per_step': e2e_ms / args.steps},
+                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h_bytes,
+                        'ms_per_step': e2e_ms / args.steps,
+                        'd2h_ceiling_gbs_per_gpu': round(d2h_bytes / copy_ms / 1e6, 2),
+                        'frac_of_d2h_ceiling': round((copy_ms * args.steps) / e2e_ms, 3),
+                        'note': 'ceiling = the same forecast bytes as a plain device->pinned-host copy issued by all '
+                                'ranks at once (max over ranks): what the host PCIe / memory system sinks'},
                 'gpu_launches': rollout_launches,
-                'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'train': train, 'layers': layers}
+                'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+                'train_value': None if train is None else train['value'],
+                'train_unit': 'samples/s',
+                'train_ms_per_step': None if train is None else train['ms_per_step'],
+                'train_global_batch': None if train is None else train['global_batch'],
+                'train_tflops': None if train is None else train['tflops'],
+                'dp_equivalence': None if dp_check is None else dp_check['ok'],
+                'dp_check': dp_check, 'train': train, 'configs': extra, 'layers': layers}
         print(json.dumps(line), flush=True)
     if dist is not None:
-        # the captured training step holds NCCL kernels: tearing the communicator down under a live CUDA graph can block
-        # (observed: the process hung in destroy_process_group after the result line).  Everything is measured and printed;
-        # synchronise the ranks and leave without the communicator teardown.
+        # the captured graphs that held NCCL kernels were released by trainer.close(); tear the communicator down, guarded by
+        # a watchdog so that a stuck teardown cannot keep the bench line from being delivered
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        done = threading.Event()
+
+        def _teardown():
+            try:
+                dist.destroy_process_group()
+            finally:
+                done.set()
+        th = threading.Thread(target=_teardown, daemon=True)
+        th.start()
+        if not done.wait(30.0):
+            sys.stderr.write('destroy_process_group did not return within 30 s; leaving\n')
+            sys.stderr.flush()
+            os._exit(0)
 
 
 if __name__ == '__main__':

@@ -71,6 +71,7 @@ def load():
         'dlwpcs_feed_gather': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
         'dlwpcs_insolation': (i32, [vp, i32, i32, i64, i32, i32, i32, vp, vp, vp, vp, f32, vp]),
         'dlwpcs_adam_step_dev': (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp]),
+        'dlwpcs_trace_read': (i32, [vp, i32, ctypes.POINTER(ctypes.c_int), i32]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)          # AttributeError here == header and library out of sync
@@ -86,7 +87,7 @@ EXPORTED = ('dlwpcs_version', 'dlwpcs_last_error', 'dlwpcs_conv_out_edge', 'dlwp
             'dlwpcs_dgrad_workspace_bytes', 'dlwpcs_conv2d_dgrad', 'dlwpcs_wgrad_workspace_bytes',
             'dlwpcs_conv2d_wgrad', 'dlwpcs_act_fwd', 'dlwpcs_act_bwd', 'dlwpcs_conv2d_fwd_host',
             'dlwpcs_mse_loss_grad', 'dlwpcs_adam_step', 'dlwpcs_adam_step_dev', 'dlwpcs_insolation', 'dlwpcs_pool2',
-            'dlwpcs_up2cat_fwd', 'dlwpcs_up2cat_bwd', 'dlwpcs_feed_gather')
+            'dlwpcs_up2cat_fwd', 'dlwpcs_up2cat_bwd', 'dlwpcs_feed_gather', 'dlwpcs_trace_read')
 
 
 class DlwpcsError(RuntimeError):
@@ -340,6 +341,15 @@ def insolation(out, c_first, n_sol, sinlat, coslat, lon, days, S=1.0):
     check(load().dlwpcs_insolation(ptr(out), dtype_code(out.dtype), b, npix, c, c_first, n_sol, ptr(sinlat), ptr(coslat),
                                    ptr(lon), ptr(days.contiguous()), S, stream_ptr()))
     return out
+
+
+def trace_read(max_launches=256, reset=True):
+    """Per-CTA %globaltimer records of the last tensor-core conv launches (needs DLWPCS_TC_TRACE=1 in the environment
+    before the library is loaded): uint64 array (launches, 160, 8), see include/dlwpcs.h."""
+    out = np.zeros((max_launches, 160, 8), dtype=np.uint64)
+    n = ctypes.c_int(0)
+    check(load().dlwpcs_trace_read(out.ctypes.data_as(ctypes.c_void_p), max_launches, ctypes.byref(n), int(reset)))
+    return out[:min(n.value, max_launches)]
 
 
 def resample_vec_ok(*tensors):

@@ -821,6 +821,10 @@ __global__ void adam_dev_kernel(float *__restrict__ p, const float *__restrict__
 }
 __global__ void incr_kernel(int32_t *c) { *c += 1; }
 
+int dlwpcs_trace_read(unsigned long long *host_out, int max_launches, int *n_launches, int reset) {
+  return tc_trace_read(host_out, max_launches, n_launches, reset);
+}
+
 int dlwpcs_adam_step_dev(float *param, const float *grad, float *m, float *v, int64_t count, float lr, float beta1,
                          float beta2, float eps, int32_t *step_counter, float grad_scale, void *stream) {
   CS_CHECK(param && grad && m && v && step_counter && count >= 0, "bad arguments to dlwpcs_adam_step_dev");

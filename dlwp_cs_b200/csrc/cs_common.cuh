@@ -78,6 +78,8 @@ bool tc_supported(const dlwpcs_conv_desc *d, const Geometry &g, const char **why
 int tc_conv_dgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *dy, const void *y, const void *packed_t,
                   void *dx, void *workspace, cudaStream_t st);
 
+int tc_trace_read(unsigned long long *host_out, int max_launches, int *n_launches, int reset);
+
 // patch table of a linearised virtual face (width Wv, G entries per face): physical source pixel or -1; cached per device
 const int32_t *get_patch_table(const Geometry &g, int Wv, int G, int n, int halo, int mode);
 

@@ -83,6 +83,7 @@ struct TcP {
   int mask_act;
   float mask_slope, mask_max;
   long long *dbg;               // optional phase timestamps (DLWPCS_TC_TIMING=1)
+  unsigned long long *trace;    // optional per-CTA %globaltimer stamps of this launch (DLWPCS_TC_TRACE=1), [grid][8]
   int knock;                    // bottleneck analysis (DLWPCS_TC_KNOCK): 1 no gathers, 2 no MMAs, 4 no epilogue math/stores, 8 no global stores
   TcPlan pl_;
 };
@@ -92,6 +93,19 @@ constexpr int DBG_K = 6;
 __device__ __forceinline__ void stamp(const TcP &P, int slot, int k, bool who) {
   if (P.dbg && who && blockIdx.x == gridDim.x / 2 && (k == DBG_K || (slot == 11 && k == DBG_K + 1) || slot == 0))
     P.dbg[slot] = clock64();
+}
+
+// cross-kernel timeline (DLWPCS_TC_TRACE=1): nanosecond stamps of every CTA of every launch, read back with
+// dlwpcs_trace_read -- slot 0 kernel entry, 1 prologue done, 2 loaders past the grid dependency, 3 first patch landed,
+// 4 first accumulators complete, 5 last epilogue done, 6 kernel exit, 7 tiles walked by the CTA
+constexpr int TRACE_LAUNCHES = 256, TRACE_CTAS = 160;
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace(const TcP &P, int slot, bool who) {
+  if (P.trace && who) P.trace[blockIdx.x * 8 + slot] = gtime_ns();
 }
 
 // tile id -> (batch, face, tile in face).  Tiles are enumerated face-group-major (equatorial faces of every sample, then
@@ -218,6 +232,7 @@ template <int MBT, int KC16T>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcP P) {
   extern __shared__ uint8_t smem_raw[];
   const TcPlan &L = P.pl_;
+  trace(P, 0, threadIdx.x == 0);
   // carve (1024-byte aligned): [patch stages][weight ring][barriers + tmem slot: 512 B][unit table 2 KB][bias 3*CoutP]
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
@@ -262,6 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(gen + (tmem_slot - base));
   stamp(P, 0, 0, tid == 0);
+  trace(P, 1, tid == 0);
   // programmatic dependent launch: the next kernel of the stream may start its prologue (barriers, tensor-memory
   // allocation, patch-table TMA) on every SM this grid has left.  Whatever may have been written by the previous kernel
   // -- activations (loaders), packed weights (TMA lane 0), bias (epilogue) -- is read behind griddepcontrol.wait; the
@@ -330,6 +346,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_wait(bar_aempty + 8 * sa, pa ^ 1);
       mbar_wait(bar_pfull + 8 * sp, pp);
       tc_fence_after();
+      trace(P, 3, k == 0 && lane == 0 && mw == 0);
       stamp(P, 6, k, lane == 0 && mw == 0);
       stamp(P, 11, k, lane == 0 && mw == 0);
       const uint64_t a_stage = a_fix | ((patch0 + (uint32_t)sp * L.patchBytes) >> 4);
@@ -455,6 +472,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       stamp(P, 8, k, tid == EPI_WARP0 * 32);
       mbar_wait(bar_afull + 8 * sa, pa);
       tc_fence_after();
+      trace(P, 4, k == 0 && tid == EPI_WARP0 * 32);
       stamp(P, 9, k, tid == EPI_WARP0 * 32);
       for (int mb = half; mb < MBc; mb += 2) {
         const int q = (T.tf * L.MB + mb) * 128 + quarter * 32 + lane;
@@ -547,12 +565,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       stamp(P, 10, k, tid == EPI_WARP0 * 32);
       if (++sa == L.AS) { sa = 0; pa ^= 1; }
     }
+    trace(P, 5, tid == EPI_WARP0 * 32);
+    if (P.trace && tid == EPI_WARP0 * 32) P.trace[blockIdx.x * 8 + 7] = (unsigned long long)k;
   } else if (warp < LOAD_WARP0 + 8) {
     // ===== patch loaders =====
     const int lt = tid - LOAD_WARP0 * 32;
     int si = 0, pi = 0, k = 0, ts = 0, tp = 0;
     const int w2_0 = P.n * 2;
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    trace(P, 2, lt == 0);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
       const TileInfo T = decode_tile(tile, P.batch, L.tpf);
       const int MBc = min(L.MB, L.nmb - T.tf * L.MB);
@@ -663,6 +684,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  trace(P, 6, tid == 0);
   if (warp == MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)L.tmemCols);
 }
 
@@ -869,6 +891,9 @@ int num_sms() {
   return sms[dev];
 }
 
+unsigned long long *g_trace = nullptr;      // [TRACE_LAUNCHES][TRACE_CTAS][8]
+int g_trace_launches = 0;
+
 int launch_tc(TcP &P, cudaStream_t st) {
   const TcPlan &L = P.pl_;
   typedef void (*kern_t)(const TcP);
@@ -902,6 +927,15 @@ int launch_tc(TcP &P, cudaStream_t st) {
     CS_CUDA(cudaMemset(dbg, 0, 16 * sizeof(long long)));
     P.dbg = dbg;
   }
+  static const int tracing = env_int("DLWPCS_TC_TRACE", 0);
+  if (tracing && grid <= TRACE_CTAS) {
+    if (!g_trace) {
+      CS_CUDA(cudaMalloc(&g_trace, sizeof(unsigned long long) * TRACE_LAUNCHES * TRACE_CTAS * 8));
+      CS_CUDA(cudaMemset(g_trace, 0, sizeof(unsigned long long) * TRACE_LAUNCHES * TRACE_CTAS * 8));
+    }
+    P.trace = g_trace + (size_t)(g_trace_launches % TRACE_LAUNCHES) * TRACE_CTAS * 8;
+    ++g_trace_launches;
+  }
   static const int pdl = env_int("DLWPCS_TC_PDL", 1);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -931,6 +965,18 @@ int launch_tc(TcP &P, cudaStream_t st) {
 }
 
 }  // namespace
+
+int tc_trace_read(unsigned long long *host_out, int max_launches, int *n_launches, int reset) {
+  const int n = g_trace_launches < TRACE_LAUNCHES ? g_trace_launches : TRACE_LAUNCHES;
+  if (n_launches) *n_launches = n;
+  const int m = n < max_launches ? n : max_launches;
+  if (m > 0 && host_out && g_trace) {
+    CS_CUDA(cudaDeviceSynchronize());
+    CS_CUDA(cudaMemcpy(host_out, g_trace, sizeof(unsigned long long) * (size_t)m * TRACE_CTAS * 8, cudaMemcpyDeviceToHost));
+  }
+  if (reset) g_trace_launches = 0;
+  return 0;
+}
 
 bool tc_supported(const dlwpcs_conv_desc *d, const Geometry &g, const char **why) {
   TcPlan L;

@@ -105,8 +105,9 @@ class DataParallelTrainer(object):
     shards are equal (the reference scales the batch by the GPU count: Azure/train_tf.py:166).
     """
 
-    def __init__(self, model, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, group=None, use_graph=True):
+    def __init__(self, model, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, group=None, use_graph=True, distributed=True):
         self.model = model
+        self.distributed = bool(distributed)      # False: a single-rank step even inside an initialised process group
         self.use_graph = use_graph
         self._graphs = {}
         self.flat = FlatBuffers(model)
@@ -119,7 +120,8 @@ class DataParallelTrainer(object):
         self.t = 0
         self.step_counter = torch.zeros(1, dtype=torch.int32, device=self.flat.param.device)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.flat.param.device)
-        self.flat.broadcast_params(group=group)
+        if self.distributed:
+            self.flat.broadcast_params(group=group)
 
     # lr / beta1 / beta2 / eps are baked into the captured launches as scalars: changing one (a learning-rate schedule,
     # models_torch.py:297-298) drops the cached graphs so that the next step re-captures with the new value
@@ -155,7 +157,7 @@ class DataParallelTrainer(object):
 
     def _step_body(self, x, target):
         loss = self.forward_backward(x, target)
-        world = self.flat.all_reduce(self.group)
+        world = self.flat.all_reduce(self.group) if self.distributed else 1
         # the step counter lives on the device (incremented by the call), so the same launches serve every step
         _lib.adam_step_dev(self.flat.param, self.flat.grad, self.m, self.v, self.lr, self.beta1, self.beta2, self.eps,
                            self.step_counter, 1.0 / world)
@@ -222,7 +224,7 @@ class DataParallelTrainer(object):
         dys = [_lib.mse_loss_grad(y.detach(), t, self.loss, scale=1.0 / n_steps) for y, t in zip(ys, targets)]
         torch.autograd.backward(ys, dys)
         self.flat.collect_grads()
-        world = self.flat.all_reduce(self.group)
+        world = self.flat.all_reduce(self.group) if self.distributed else 1
         _lib.adam_step_dev(self.flat.param, self.flat.grad, self.m, self.v, self.lr, self.beta1, self.beta2, self.eps,
                            self.step_counter, 1.0 / world)
         return self.loss

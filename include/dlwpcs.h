@@ -162,6 +162,13 @@ int dlwpcs_feed_gather(const float *array, const float *insolation, const float 
  * device, runs pad(halo)+conv, copies y back; synchronous.                                                            */
 int dlwpcs_conv2d_fwd_host(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, const void *x_host, void *y_host);
 
+/* Diagnostics (no reference counterpart): with DLWPCS_TC_TRACE=1 in the environment every launch of the tensor-core
+ * convolution kernel records, per CTA, eight %globaltimer values (ns): 0 kernel entry, 1 prologue done, 2 loaders past
+ * the grid dependency, 3 first input patch in shared memory, 4 first accumulators complete, 5 last epilogue done,
+ * 6 kernel exit, 7 = tiles walked.  Copies the records of up to max_launches launches (160 CTAs x 8 values each, launch
+ * order) to host_out, stores the number recorded in *n_launches; reset != 0 restarts the recording.                   */
+int dlwpcs_trace_read(unsigned long long *host_out, int max_launches, int *n_launches, int reset);
+
 #ifdef __cplusplus
 }
 #endif
