@@ -1,9 +1,9 @@
 """
-The Weyn-2020 cubed-sphere U-Net (``unet2`` of the reference's Azure/train_cs.py:196-228, 277-305) on the engine's
-layers, and a device-resident autoregressive rollout (the loop of DLWP/model/models.py:446-454 without the two
-host<->device copies per step).
+The reference's cubed-sphere networks (``basic`` / ``unet`` / ``unet2`` / ``unet3`` / ``unet4`` of Azure/train_cs.py:196-388;
+``unet2`` is the Weyn-2020 U-Net) on the engine's layers, and a device-resident autoregressive rollout (the loop of
+DLWP/model/models.py:446-454 without the two host<->device copies per step).
 
-  * ``CubeSphereUNet2``  -- nn.Module; training / generic forward through the differentiable operators.
+  * ``CubeSphereCNN`` / ``CubeSphereUNet2``  -- nn.Module; training / generic forward through the differentiable operators.
   * ``RolloutEngine``    -- inference: one kernel launch per CubeSphereConv2D (11 per step); the halo exchange, the
     average pooling, the nearest up-sampling, the channel concatenation, bias and the capped leaky ReLU all live in that
     kernel's load stage / epilogue; state, forcing and the forecast ring stay in HBM; the whole multi-step rollout is
@@ -20,13 +20,94 @@ from . import functional as F_cs
 RELU = ('capped_leaky_relu', 0.1, 10.0)      # keras ReLU(negative_slope=0.1, max_value=10.) train_cs.py:199
 
 
+# ---- the reference's cubed-sphere architectures as layer programs (Azure/train_cs.py:209-388) -------------------------
+# Tokens: ('conv', layer name, filters as a multiple of `base` -- or (multiple with skip connections, multiple without)),
+# 'pool' = AveragePooling3D((1,2,2)), 'up' = UpSampling3D((1,2,2)), ('save', tag) keeps the current tensor for a skip
+# connection, ('cat', tag) = concatenate([current, saved], axis=-1).  Every 3x3 conv is preceded by
+# CubeSpherePadding2D(1) and followed by ReLU(0.1, 10); the last token is always the 1x1 'output' convolution.
+# `skip_connections = 'unet' in name` decides the filter counts of conv_2d_4 / _5 / _6 (train_cs.py:208, 218-223).
+ARCHS = {
+    'basic': [('conv', 'conv_2d_1', 1), 'pool', ('conv', 'conv_2d_2', 2), 'pool', ('conv', 'conv_2d_3', 4), 'up',
+              ('conv', 'conv_2d_6', (1, 2)), 'up', ('conv', 'conv_2d_7', 1), ('conv', 'conv_2d_7_2', 1)],
+    'unet': [('conv', 'conv_2d_1', 1), ('save', 'x0'), 'pool', ('conv', 'conv_2d_2', 2), ('save', 'x1'), 'pool',
+             ('conv', 'conv_2d_3', 4), 'up', ('cat', 'x1'), ('conv', 'conv_2d_6', (1, 2)), 'up', ('cat', 'x0'),
+             ('conv', 'conv_2d_7', 1), ('conv', 'conv_2d_7_2', 1)],
+    'unet2': [('conv', 'conv_2d_1', 1), ('conv', 'conv_2d_1_2', 1), ('save', 'x0'), 'pool', ('conv', 'conv_2d_2', 2),
+              ('conv', 'conv_2d_2_2', 2), ('save', 'x1'), 'pool', ('conv', 'conv_2d_5_2', 4), ('conv', 'conv_2d_5', (2, 4)),
+              'up', ('cat', 'x1'), ('conv', 'conv_2d_6_2', 2), ('conv', 'conv_2d_6', (1, 2)), 'up', ('cat', 'x0'),
+              ('conv', 'conv_2d_7', 1), ('conv', 'conv_2d_7_2', 1)],
+    'unet3': [('conv', 'conv_2d_1', 1), ('conv', 'conv_2d_1_2', 1), ('conv', 'conv_2d_1_3', 1), ('save', 'x0'), 'pool',
+              ('conv', 'conv_2d_2', 2), ('conv', 'conv_2d_2_2', 2), ('conv', 'conv_2d_2_3', 2), ('save', 'x1'), 'pool',
+              ('conv', 'conv_2d_5_3', 4), ('conv', 'conv_2d_5_2', 4), ('conv', 'conv_2d_5', (2, 4)), 'up', ('cat', 'x1'),
+              ('conv', 'conv_2d_6_3', 2), ('conv', 'conv_2d_6_2', 2), ('conv', 'conv_2d_6', (1, 2)), 'up', ('cat', 'x0'),
+              ('conv', 'conv_2d_7', 1), ('conv', 'conv_2d_7_2', 1), ('conv', 'conv_2d_7_3', 1)],
+    'unet4': [('conv', 'conv_2d_1', 1), ('conv', 'conv_2d_1_2', 1), ('save', 'x0'), 'pool', ('conv', 'conv_2d_2', 2),
+              ('conv', 'conv_2d_2_2', 2), ('save', 'x1'), 'pool', ('conv', 'conv_2d_3_2', 4), ('conv', 'conv_2d_3', 4),
+              ('save', 'x2'), 'pool', ('conv', 'conv_2d_4_2', 8), ('conv', 'conv_2d_4', (4, 8)), 'up', ('cat', 'x2'),
+              ('conv', 'conv_2d_5_2', 4), ('conv', 'conv_2d_5', (2, 4)), 'up', ('cat', 'x1'), ('conv', 'conv_2d_6_2', 2),
+              ('conv', 'conv_2d_6', (1, 2)), 'up', ('cat', 'x0'), ('conv', 'conv_2d_7', 1), ('conv', 'conv_2d_7_2', 1)],
+}
+# Keras names of the layer objects, in the order Azure/train_cs.py:209-228 creates them (auto-naming by class:
+# cube_sphere_conv2d, cube_sphere_conv2d_1, ...; conv_2d_8 is created with name='output'): the group names of a saved
+# model's weights (util.py:127-193 -> keras `model.save`).
+CREATION_ORDER = ('conv_2d_1', 'conv_2d_1_2', 'conv_2d_1_3', 'conv_2d_2', 'conv_2d_2_2', 'conv_2d_2_3', 'conv_2d_3',
+                  'conv_2d_3_2', 'conv_2d_4', 'conv_2d_4_2', 'conv_2d_5', 'conv_2d_5_2', 'conv_2d_5_3', 'conv_2d_6',
+                  'conv_2d_6_2', 'conv_2d_6_3', 'conv_2d_7', 'conv_2d_7_2', 'conv_2d_7_3')
+
+
+def keras_layer_name(name):
+    """'conv_2d_1' -> 'cube_sphere_conv2d', 'conv_2d_1_2' -> 'cube_sphere_conv2d_1', ..., 'conv_2d_8' -> 'output'."""
+    if name in ('conv_2d_8', 'output'):
+        return 'output'
+    i = CREATION_ORDER.index(name)
+    return 'cube_sphere_conv2d' if i == 0 else 'cube_sphere_conv2d_%d' % i
+
+
+def arch_program(arch, in_channels, out_channels, base=32):
+    """Resolve an architecture into fused convolution steps, in execution order:
+    dict(name, kernel, cin, cout, level, sources=[(tag, channels, mode)], dst, act) with level = number of poolings
+    above the layer (face edge = N >> level), mode in {'same', 'pool', 'up'} = how the source is sampled, tag 'input' =
+    the network input, otherwise the name of the producing layer; dst = own name ('out' for the output layer)."""
+    if arch not in ARCHS:
+        raise ValueError('unknown cubed-sphere architecture %r (one of %s)' % (arch, sorted(ARCHS)))
+    skip = 'unet' in arch
+    cur, mode, level = ('input', in_channels), 'same', 0
+    saved, extra, steps = {}, None, []
+    for tok in list(ARCHS[arch]) + [('conv', 'conv_2d_8', None)]:
+        if tok == 'pool' or tok == 'up':
+            if mode != 'same' or extra is not None:
+                raise ValueError('%s: two resampling steps without a convolution in between cannot be fused' % arch)
+            mode = tok
+            level += 1 if tok == 'pool' else -1
+        elif tok[0] == 'save':
+            saved[tok[1]] = (cur, level)
+        elif tok[0] == 'cat':
+            src, lv = saved[tok[1]]
+            if lv != level:
+                raise ValueError('%s: skip connection %s joins at a different resolution' % (arch, tok[1]))
+            extra = src
+        else:
+            _, name, mult = tok
+            last = name == 'conv_2d_8'
+            if last:
+                cout = out_channels
+            else:
+                m = mult if isinstance(mult, int) else (mult[0] if skip else mult[1])
+                cout = m * base
+            sources = [(cur[0], cur[1], mode)]
+            if extra is not None:
+                sources.append((extra[0], extra[1], 'same'))
+            steps.append(dict(name=name, kernel=1 if last else 3, cin=sum(c for _, c, _ in sources), cout=cout,
+                              level=level, sources=sources, dst='out' if last else name, act=not last))
+            cur, mode, extra = (name, cout), 'same', None
+    if level != 0:
+        raise ValueError('%s: the output is not at the input resolution' % arch)
+    return steps
+
+
 def unet2_layer_specs(in_channels, out_channels, base=32):
     """(name, kernel, Cin, Cout) in execution order -- train_cs.py:209-228 + 277-305."""
-    b = base
-    return [('conv_2d_1', 3, in_channels, b), ('conv_2d_1_2', 3, b, b), ('conv_2d_2', 3, b, 2 * b),
-            ('conv_2d_2_2', 3, 2 * b, 2 * b), ('conv_2d_5_2', 3, 2 * b, 4 * b), ('conv_2d_5', 3, 4 * b, 2 * b),
-            ('conv_2d_6_2', 3, 4 * b, 2 * b), ('conv_2d_6', 3, 2 * b, b), ('conv_2d_7', 3, 2 * b, b),
-            ('conv_2d_7_2', 3, b, b), ('conv_2d_8', 1, b, out_channels)]
+    return [(s['name'], s['kernel'], s['cin'], s['cout']) for s in arch_program('unet2', in_channels, out_channels, base)]
 
 
 def _avg_pool(x):      # AveragePooling3D((1,2,2)), channels_last
@@ -38,24 +119,32 @@ def _upsample(x):      # UpSampling3D((1,2,2))
     return x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
 
 
-class CubeSphereUNet2(nn.Module):
-    """``unet2``: 10 halo-padded 3x3 CubeSphereConv2D + capped leaky ReLU, two 2x2 poolings with skip connections, and a
-    1x1 output convolution.  channels_last (B,6,N,N,C); N divisible by 4."""
+class CubeSphereCNN(nn.Module):
+    """Any of the reference's cubed-sphere networks (``basic``, ``unet``, ``unet2``, ``unet3``, ``unet4`` of
+    Azure/train_cs.py:233-388): halo-padded 3x3 CubeSphereConv2D + ReLU(0.1, 10), 2x2 average pooling, nearest
+    up-sampling, skip connections, and a 1x1 output convolution.  channels_last (B,6,N,N,C); N divisible by
+    2**(number of poolings).  The layer attributes carry the reference's variable names (conv_2d_1, ..., conv_2d_8)."""
 
-    def __init__(self, in_channels, out_channels, base=32, independent_north_pole=False):
+    def __init__(self, arch, in_channels, out_channels, base=32, independent_north_pole=False):
         super().__init__()
+        self.arch = arch
         self.in_channels, self.out_channels, self.base = in_channels, out_channels, base
         self.independent_north_pole = independent_north_pole
-        for name, k, ci, co in unet2_layer_specs(in_channels, out_channels, base):
-            last = name == 'conv_2d_8'
-            setattr(self, name, CubeSphereConv2D(
-                co, k, padding='valid', data_format='channels_last', dilation_rate=1,
+        self.program = arch_program(arch, in_channels, out_channels, base)
+        self.levels = max(s['level'] for s in self.program)
+        for s in self.program:
+            last = s['name'] == 'conv_2d_8'
+            setattr(self, s['name'], CubeSphereConv2D(
+                s['cout'], s['kernel'], padding='valid', data_format='channels_last', dilation_rate=1,
                 activation='linear' if last else RELU, independent_north_pole=independent_north_pole,
                 flip_north_pole=not independent_north_pole,      # train_cs.py:205-206
-                in_channels=ci, fuse_padding=0 if last else 1, name='output' if last else name))
+                in_channels=s['cin'], fuse_padding=0 if last else 1, name='output' if last else s['name']))
+
+    def layer_specs(self):
+        return [(s['name'], s['kernel'], s['cin'], s['cout']) for s in self.program]
 
     def layers_in_order(self):
-        return [getattr(self, s[0]) for s in unet2_layer_specs(self.in_channels, self.out_channels, self.base)]
+        return [getattr(self, s['name']) for s in self.program]
 
     def forward(self, x):
         # pooling / upsampling + concatenation: one 16-byte kernel each way when the channel counts allow it (they do for
@@ -66,17 +155,24 @@ class CubeSphereUNet2(nn.Module):
         def upcat(a, b):
             return F_cs.upsample_concat(a, b) if _lib.resample_vec_ok(a, b) else torch.cat([_upsample(a), b], dim=-1)
 
-        x0 = self.conv_2d_1_2(self.conv_2d_1(x))
-        x1 = self.conv_2d_2_2(self.conv_2d_2(pool(x0)))
-        x2 = self.conv_2d_5(self.conv_2d_5_2(pool(x1)))
-        t = self.conv_2d_6(self.conv_2d_6_2(upcat(x2, x1)))
-        t = self.conv_2d_7_2(self.conv_2d_7(upcat(t, x0)))
-        return self.conv_2d_8(t)
+        vals = {'input': x}
+        for s in self.program:
+            (t0, _, m0) = s['sources'][0]
+            t = vals[t0]
+            if len(s['sources']) == 2:
+                skip = vals[s['sources'][1][0]]
+                t = upcat(t, skip) if m0 == 'up' else torch.cat([pool(t) if m0 == 'pool' else t, skip], dim=-1)
+            elif m0 == 'pool':
+                t = pool(t)
+            elif m0 == 'up':
+                t = _upsample(t)
+            vals[s['name']] = getattr(self, s['name'])(t)
+        return vals['conv_2d_8']
 
     # ---- weight interop with the reference's Keras model ----------------------------------------
     def get_weights(self):
-        """numpy arrays in the order ``keras.Model.get_weights()`` returns them for the reference's ``unet2`` built by
-        Azure/train_cs.py:277-305: layers in creation order (conv_2d_1, conv_2d_1_2, ..., output), each layer in its
+        """numpy arrays in the order ``keras.Model.get_weights()`` returns them for the reference's model built by
+        Azure/train_cs.py:233-409: layers in graph order (conv_2d_1, conv_2d_1_2, ..., output), each layer in its
         ``add_weight`` order (custom.py:882-914: equatorial_kernel, polar_kernel, [north_pole_kernel,] equatorial_bias,
         polar_bias[, north_pole_bias]); kernels HWIO."""
         out = []
@@ -100,11 +196,38 @@ class CubeSphereUNet2(nn.Module):
                 raise ValueError('layer %d: kernel shape %r, expected %r (HWIO)' % (i, tuple(chunk[0].shape), want))
             layer.set_weights(chunk)
 
+    def load_keras_weights(self, path):
+        """Weights of a model saved by the reference (``DLWP.util.save_model`` -> ``<name>.keras``, util.py:127-150: a
+        Keras HDF5 file) into this network, matched by the Keras layer names (``keras_layer_name``) and the
+        ``add_weight`` names of custom.py:882-914.  Pure-Python HDF5 reader: dlwp_cs_b200/h5weights.py."""
+        from .h5weights import read_keras_weights
+        table = read_keras_weights(path)
+        for s in self.program:
+            kname = keras_layer_name(s['name'])
+            if kname not in table:
+                raise KeyError('layer %r (%s) not found in %s; file has %s' % (kname, s['name'], path, sorted(table)))
+            layer, got = getattr(self, s['name']), table[kname]
+            order = [nm for nm in ('equatorial_kernel', 'polar_kernel', 'north_pole_kernel', 'equatorial_bias', 'polar_bias',
+                                   'north_pole_bias') if getattr(layer, nm) is not None]
+            missing = [nm for nm in order if nm not in got]
+            if missing:
+                raise KeyError('layer %r: weights %s missing in %s' % (kname, missing, path))
+            layer.set_weights([got[nm] for nm in order])
+        return self
+
     def load_oracle_params(self, params):
         """params: dict 'layer.equatorial_kernel' -> tensor, as produced by oracle.make_unet2_params (tests / bench)."""
         with torch.no_grad():
             for name, p in self.named_parameters():
                 p.copy_(params[name].to(p.dtype))
+
+
+class CubeSphereUNet2(CubeSphereCNN):
+    """``unet2`` (train_cs.py:277-305), the Weyn-2020 network: 10 halo-padded 3x3 CubeSphereConv2D + capped leaky ReLU,
+    two 2x2 poolings with skip connections, and a 1x1 output convolution."""
+
+    def __init__(self, in_channels, out_channels, base=32, independent_north_pole=False):
+        super().__init__('unet2', in_channels, out_channels, base, independent_north_pole)
 
 
 def reference_input_order(t_in, n_var, n_const, n_sol_per_step=1):
@@ -134,8 +257,8 @@ class RolloutEngine(object):
 
     def __init__(self, model, batch, n, steps, forcing_channels=0, dtype=torch.float32, use_graph=True,
                  per_step_forcing=False, device=None, input_order=None):
-        if n % 4 != 0:
-            raise ValueError('unet2 pools twice: face edge must be divisible by 4')
+        if n % (1 << model.levels) != 0:
+            raise ValueError('%s pools %d times: face edge must be divisible by %d' % (model.arch, model.levels, 1 << model.levels))
         self.model, self.batch, self.n, self.steps = model, batch, n, steps
         self.cf = forcing_channels
         self.cp = model.out_channels
@@ -165,22 +288,28 @@ class RolloutEngine(object):
         fshape = ((steps,) if per_step_forcing else ()) + (b, 6, n, n, max(self.cf_pad, 8))
         self.forcing = torch.zeros(fshape, dtype=dtype, device=self.device)
         self.ring = torch.empty((steps, b, 6, n, n, self.cp_pad), dtype=dtype, device=self.device)
-        self.buf = dict(a=mk(n, base), x0=mk(n, base), b=mk(n // 2, 2 * base), x1=mk(n // 2, 2 * base),
-                        c=mk(n // 4, 4 * base), x2=mk(n // 4, 2 * base), d=mk(n // 2, 2 * base), e=mk(n // 2, base),
-                        f=mk(n, base), g=mk(n, base))
-        S, P, U = _lib.SRC_SAME, _lib.SRC_POOL2, _lib.SRC_UP2
-        # (layer, edge, src0, c0, mode0, src1, c1, mode1, dst)
-        plan = [('conv_2d_1', n, 'state', self.cp_pad, S, 'forcing' if self.cf else None, self.cf_pad, S, 'a'),
-                ('conv_2d_1_2', n, 'a', base, S, None, 0, S, 'x0'),
-                ('conv_2d_2', n // 2, 'x0', base, P, None, 0, S, 'b'),
-                ('conv_2d_2_2', n // 2, 'b', 2 * base, S, None, 0, S, 'x1'),
-                ('conv_2d_5_2', n // 4, 'x1', 2 * base, P, None, 0, S, 'c'),
-                ('conv_2d_5', n // 4, 'c', 4 * base, S, None, 0, S, 'x2'),
-                ('conv_2d_6_2', n // 2, 'x2', 2 * base, U, 'x1', 2 * base, S, 'd'),
-                ('conv_2d_6', n // 2, 'd', 2 * base, S, None, 0, S, 'e'),
-                ('conv_2d_7', n, 'e', base, U, 'x0', base, S, 'f'),
-                ('conv_2d_7_2', n, 'f', base, S, None, 0, S, 'g'),
-                ('conv_2d_8', n, 'g', base, S, None, 0, S, 'out')]
+        # the fused launch plan follows from the architecture's layer program (one launch per CubeSphereConv2D; pooling,
+        # up-sampling and the skip concatenation become the sampling modes of the convolution's one or two sources)
+        modes = {'same': _lib.SRC_SAME, 'pool': _lib.SRC_POOL2, 'up': _lib.SRC_UP2}
+        self.buf = {}
+        plan = []
+        for st in model.program:
+            edge = n >> st['level']
+            srcs = []
+            for tag, c, mode in st['sources']:
+                if tag == 'input':          # [prognostic | pad] from the state / ring, [forcing | pad] as a second source
+                    if len(st['sources']) != 1 or mode != 'same':
+                        raise _lib.DlwpcsError('the network input must feed a plain convolution')
+                    srcs = [('state', self.cp_pad, _lib.SRC_SAME)]
+                    if self.cf:
+                        srcs.append(('forcing', self.cf_pad, _lib.SRC_SAME))
+                else:
+                    srcs.append((tag, c, modes[mode]))
+            if st['dst'] != 'out':
+                self.buf[st['dst']] = mk(edge, st['cout'])
+            (s0, c0, m0), (s1, c1, m1) = srcs[0], (srcs[1] if len(srcs) > 1 else (None, 0, _lib.SRC_SAME))
+            plan.append((st['name'], edge, s0, c0, m0, s1, c1, m1, st['dst']))
+        S = _lib.SRC_SAME
         self.plan = []
         for name, edge, s0, c0, m0, s1, c1, m1, dst in plan:
             layer = getattr(model, name)
@@ -203,7 +332,7 @@ class RolloutEngine(object):
             layer = getattr(self.model, item[0])
             ws = [layer.equatorial_kernel, layer.polar_kernel, layer.north_pole_kernel]
             bs = [layer.equatorial_bias, layer.polar_bias, layer.north_pole_bias]
-            if item[0] == 'conv_2d_1':          # input channels: [prognostic | pad | forcing | pad]
+            if item[2] == 'state':              # input channels: [prognostic | pad | forcing | pad]
                 ws = [None if w is None else self._pad_in(w.detach()) for w in ws]
             if item[4] == 'out':                # output channels: [prognostic | pad]
                 ws = [None if w is None else F.pad(w.detach(), (0, self.cp_pad - self.cp)) for w in ws]

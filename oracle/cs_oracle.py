@@ -9,6 +9,7 @@ A torch-CPU restatement of the one hot path of jweyn/DLWP-CS (reference mounted 
   * ``conv_output_length``   <- DLWP/custom.py:1004-1030  compute_output_shape (keras conv_utils rule)
   * ``capped_leaky_relu`` / ``avg_pool_2x2`` / ``upsample_2x2`` / ``unet2`` <- Azure/train_cs.py:196-228, 277-305
   * ``rollout``              <- DLWP/model/models.py:418-460 predict_timeseries step loop (state fed back each step)
+  * ``cs_network``           <- Azure/train_cs.py:233-388  basic / unet / unet3 / unet4 (same primitives, different depth)
 
 The arithmetic itself lives in an absent third-party dependency (tensorflow==2.1.0, environment.yml:180); its published
 semantics are restated: ``conv2d`` is a cross-correlation with HWIO kernels, 'valid' = no padding, 'same' = asymmetric
@@ -250,6 +251,97 @@ def unet2(params, x, exact=True):
     t = torch.cat([upsample_2x2(t), x0], dim=-1)                                  # train_cs.py:298-299
     t = cs('conv_2d_7_2', cs('conv_2d_7', t))
     return cs('conv_2d_8', t, pad=0, act=False)                                  # train_cs.py:304, 1x1 'output'
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the other architectures of Azure/train_cs.py (233-251 basic, 254-274 unet, 308-346 unet3, 349-388 unet4), restated
+# statement by statement like ``unet2`` above.  Filter counts: train_cs.py:208-228 with skip_connections = 'unet' in name.
+# ----------------------------------------------------------------------------------------------------------------------
+
+def arch_shapes(arch, cin, cout, base=32):
+    """(name, kernel, Cin, Cout) of every CubeSphereConv2D the architecture uses, in execution order."""
+    b = base
+    if arch == 'unet2':
+        return unet2_shapes(cin, cout, base)
+    if arch == 'basic':       # no skip connections: conv_2d_6 has 2b filters (train_cs.py:222)
+        return [('conv_2d_1', 3, cin, b), ('conv_2d_2', 3, b, 2 * b), ('conv_2d_3', 3, 2 * b, 4 * b),
+                ('conv_2d_6', 3, 4 * b, 2 * b), ('conv_2d_7', 3, 2 * b, b), ('conv_2d_7_2', 3, b, b), ('conv_2d_8', 1, b, cout)]
+    if arch == 'unet':
+        return [('conv_2d_1', 3, cin, b), ('conv_2d_2', 3, b, 2 * b), ('conv_2d_3', 3, 2 * b, 4 * b),
+                ('conv_2d_6', 3, 6 * b, b), ('conv_2d_7', 3, 2 * b, b), ('conv_2d_7_2', 3, b, b), ('conv_2d_8', 1, b, cout)]
+    if arch == 'unet3':
+        return [('conv_2d_1', 3, cin, b), ('conv_2d_1_2', 3, b, b), ('conv_2d_1_3', 3, b, b),
+                ('conv_2d_2', 3, b, 2 * b), ('conv_2d_2_2', 3, 2 * b, 2 * b), ('conv_2d_2_3', 3, 2 * b, 2 * b),
+                ('conv_2d_5_3', 3, 2 * b, 4 * b), ('conv_2d_5_2', 3, 4 * b, 4 * b), ('conv_2d_5', 3, 4 * b, 2 * b),
+                ('conv_2d_6_3', 3, 4 * b, 2 * b), ('conv_2d_6_2', 3, 2 * b, 2 * b), ('conv_2d_6', 3, 2 * b, b),
+                ('conv_2d_7', 3, 2 * b, b), ('conv_2d_7_2', 3, b, b), ('conv_2d_7_3', 3, b, b), ('conv_2d_8', 1, b, cout)]
+    if arch == 'unet4':
+        return [('conv_2d_1', 3, cin, b), ('conv_2d_1_2', 3, b, b), ('conv_2d_2', 3, b, 2 * b), ('conv_2d_2_2', 3, 2 * b, 2 * b),
+                ('conv_2d_3_2', 3, 2 * b, 4 * b), ('conv_2d_3', 3, 4 * b, 4 * b), ('conv_2d_4_2', 3, 4 * b, 8 * b),
+                ('conv_2d_4', 3, 8 * b, 4 * b), ('conv_2d_5_2', 3, 8 * b, 4 * b), ('conv_2d_5', 3, 4 * b, 2 * b),
+                ('conv_2d_6_2', 3, 4 * b, 2 * b), ('conv_2d_6', 3, 2 * b, b), ('conv_2d_7', 3, 2 * b, b),
+                ('conv_2d_7_2', 3, b, b), ('conv_2d_8', 1, b, cout)]
+    raise ValueError(arch)
+
+
+def make_arch_params(arch, cin, cout, base=32, seed=1, dtype=torch.float32, bias_scale=0.05):
+    g = torch.Generator().manual_seed(seed)
+    params = {}
+    for name, k, ci, co in arch_shapes(arch, cin, cout, base):
+        limit = math.sqrt(6.0 / (k * k * ci + k * k * co))
+        for kind in ('equatorial', 'polar'):
+            params['%s.%s_kernel' % (name, kind)] = ((torch.rand(k, k, ci, co, generator=g, dtype=torch.float64) * 2 - 1)
+                                                     * limit).to(dtype)
+            params['%s.%s_bias' % (name, kind)] = ((torch.rand(co, generator=g, dtype=torch.float64) * 2 - 1)
+                                                   * bias_scale).to(dtype)
+    return params
+
+
+def cs_network(arch, params, x, exact=True):
+    """``basic`` / ``unet`` / ``unet2`` / ``unet3`` / ``unet4`` of Azure/train_cs.py, channels_last."""
+    def cs(name, t, pad=1, act=True):
+        if pad:
+            t = cube_sphere_pad(t, pad)
+        t = cube_sphere_conv2d(t, params[name + '.equatorial_kernel'], params[name + '.polar_kernel'], None,
+                               params[name + '.equatorial_bias'], params[name + '.polar_bias'], None, exact=exact)
+        return capped_leaky_relu(t) if act else t
+    pool, up = avg_pool_2x2, upsample_2x2
+    cat = lambda a, b: torch.cat([a, b], dim=-1)
+    if arch == 'unet2':
+        return unet2(params, x, exact)
+    if arch == 'basic':                                                         # train_cs.py:233-251
+        t = cs('conv_2d_1', x)
+        t = cs('conv_2d_2', pool(t))
+        t = cs('conv_2d_3', pool(t))
+        t = cs('conv_2d_6', up(t))
+        t = cs('conv_2d_7', up(t))
+        t = cs('conv_2d_7_2', t)
+        return cs('conv_2d_8', t, pad=0, act=False)
+    if arch == 'unet':                                                          # train_cs.py:254-274
+        x0 = cs('conv_2d_1', x)
+        x1 = cs('conv_2d_2', pool(x0))
+        x2 = cs('conv_2d_3', pool(x1))
+        t = cs('conv_2d_6', cat(up(x2), x1))
+        t = cs('conv_2d_7', cat(up(t), x0))
+        t = cs('conv_2d_7_2', t)
+        return cs('conv_2d_8', t, pad=0, act=False)
+    if arch == 'unet3':                                                         # train_cs.py:308-346
+        x0 = cs('conv_2d_1_3', cs('conv_2d_1_2', cs('conv_2d_1', x)))
+        x1 = cs('conv_2d_2_3', cs('conv_2d_2_2', cs('conv_2d_2', pool(x0))))
+        x2 = cs('conv_2d_5', cs('conv_2d_5_2', cs('conv_2d_5_3', pool(x1))))
+        t = cs('conv_2d_6', cs('conv_2d_6_2', cs('conv_2d_6_3', cat(up(x2), x1))))
+        t = cs('conv_2d_7_3', cs('conv_2d_7_2', cs('conv_2d_7', cat(up(t), x0))))
+        return cs('conv_2d_8', t, pad=0, act=False)
+    if arch == 'unet4':                                                         # train_cs.py:349-388
+        x0 = cs('conv_2d_1_2', cs('conv_2d_1', x))
+        x1 = cs('conv_2d_2_2', cs('conv_2d_2', pool(x0)))
+        x2 = cs('conv_2d_3', cs('conv_2d_3_2', pool(x1)))
+        x3 = cs('conv_2d_4', cs('conv_2d_4_2', pool(x2)))
+        t = cs('conv_2d_5', cs('conv_2d_5_2', cat(up(x3), x2)))
+        t = cs('conv_2d_6', cs('conv_2d_6_2', cat(up(t), x1)))
+        t = cs('conv_2d_7_2', cs('conv_2d_7', cat(up(t), x0)))
+        return cs('conv_2d_8', t, pad=0, act=False)
+    raise ValueError(arch)
 
 
 def rollout(params, state, forcing, steps, exact=True, host_hop=False):

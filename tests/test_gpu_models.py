@@ -119,3 +119,34 @@ def test_rollout_c96_12var_multi_step():
     err = _rollout_errors(96, 24, 4, 1, 4)
     assert err[torch.float32].max() <= 1e-4, err[torch.float32]
     assert err[torch.bfloat16].max() <= 1.5e-2, err[torch.bfloat16]
+
+
+@pytest.mark.parametrize('arch', ['basic', 'unet', 'unet3', 'unet4'])
+def test_other_architectures_forward_and_rollout(arch):
+    """The other cubed-sphere networks of Azure/train_cs.py:233-388 through the same layers: module forward (float32) and a
+    2-step device-resident rollout (float32 and bf16), whose fused launch plan is derived from the layer program, against
+    the oracle's statement-by-statement restatement."""
+    from dlwp_cs_b200.unet import CubeSphereCNN, RolloutEngine
+    n, b, cp, cf, base = 16, 2, 6, 2, 8
+    params = O.make_arch_params(arch, cp + cf, cp, base=base, seed=9)
+    model = CubeSphereCNN(arch, cp + cf, cp, base=base).cuda()
+    model.load_oracle_params(params)
+    g = torch.Generator().manual_seed(4)
+    state = torch.randn(b, 6, n, n, cp, generator=g)
+    forcing = torch.rand(b, 6, n, n, cf, generator=g)
+    p64 = {k: v.double() for k, v in params.items()}
+    with torch.no_grad():
+        x = torch.cat([state, forcing], dim=-1)
+        ref1 = O.cs_network(arch, p64, x.double())
+        y = model(x.cuda())
+        scale = float(ref1.abs().max())
+        assert float((y.double().cpu() - ref1).abs().max()) <= 1e-5 * scale
+        ref2 = O.cs_network(arch, p64, torch.cat([ref1, forcing.double()], dim=-1))
+    for dtype, tol in ((torch.float32, 1e-4), (torch.bfloat16, 1.5e-2)):
+        eng = RolloutEngine(model, b, n, 2, forcing_channels=cf, dtype=dtype)
+        assert eng.launches_per_step == len(model.program)
+        out = eng.run(state.cuda(), forcing.cuda()).double().cpu()
+        torch.cuda.synchronize()
+        for t, ref in enumerate((ref1, ref2)):
+            err = float((out[t] - ref).abs().max()) / float(ref.abs().max())
+            assert err <= tol, (arch, dtype, t, err)

@@ -122,3 +122,25 @@ def test_reference_build_model_resolves_engine_layers_by_name():
             sys.modules['DLWP.custom'] = saved
         else:
             sys.modules.pop('DLWP.custom', None)
+
+
+@pytest.mark.parametrize('arch', ['basic', 'unet', 'unet2', 'unet3', 'unet4'])
+def test_architecture_programs_match_the_oracle_restatement(arch):
+    """The layer programs the engine derives its fused launch plan from (dlwp_cs_b200.unet.ARCHS) against the statement-by-
+    statement restatement of Azure/train_cs.py:233-388 in the oracle: same layers, kernel sizes and channel counts."""
+    from dlwp_cs_b200.unet import CubeSphereCNN, arch_program
+    prog = arch_program(arch, 18, 14, 32)
+    assert [(s['name'], s['kernel'], s['cin'], s['cout']) for s in prog] == O.arch_shapes(arch, 18, 14, 32)
+    assert prog[-1]['dst'] == 'out' and prog[-1]['kernel'] == 1 and not prog[-1]['act']
+    for s in prog:                       # at most two sources, only the first one resampled: what one fused launch can read
+        assert 1 <= len(s['sources']) <= 2 and (len(s['sources']) == 1 or s['sources'][1][2] == 'same')
+    m = CubeSphereCNN(arch, 18, 14, 32)
+    assert sum(p.numel() for p in m.parameters()) == sum(2 * (k * k * ci * co + co) for _, k, ci, co in O.arch_shapes(arch, 18, 14, 32))
+    assert m.levels == (3 if arch == 'unet4' else 2)
+
+
+def test_unknown_architecture_and_bad_edge():
+    from dlwp_cs_b200.unet import CubeSphereCNN, arch_program
+    with pytest.raises(ValueError):
+        arch_program('unet5', 4, 4)
+    assert CubeSphereCNN('unet4', 4, 4, base=8).levels == 3
