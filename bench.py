@@ -170,27 +170,30 @@ def run_reference(args, rank, world, n_face, c_prog):
 
 
 def time_layers(eng, flush, reps=10):
-    """Per-layer device time of one model step: CUDA events around each single launch, L2 flushed (512 MiB write)
-    before every repetition so that the small layers are not served from a warm L2.  -> list of (name, ms)"""
+    """Per-layer device time inside one model step: the step's launches are enqueued in order (eagerly, not from the
+    graph) with a CUDA event between consecutive launches, L2 flushed (512 MiB write) before every repetition of the step
+    -- each layer therefore sees the cache state it has in production (whatever part of its predecessor's output the
+    126 MB L2 still holds), not a layer-private warm L2.  Median over the repetitions.  -> list of (name, ms)"""
     from dlwp_cs_b200 import _lib
-    out = []
+    launches = []
     for name, d, s0, s1, dst, packed in eng.plan:
         o = eng.ring[0] if dst == 'out' else eng.buf[dst]
-        a, b = eng._src(s0, 0), eng._src(s1, 0)
-        for _ in range(3):
+        launches.append((name, d, eng._src(s0, 0), eng._src(s1, 0), packed, o))
+    for _ in range(3):
+        for name, d, a, b, packed, o in launches:
             _lib.conv2d_fwd(d, a, b, packed, out=o)
-        evs = []
-        for _ in range(reps):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+    times = {name: [] for name, *_ in launches}
+    for _ in range(reps):
+        flush.zero_()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(launches) + 1)]
+        evs[0].record()
+        for i, (name, d, a, b, packed, o) in enumerate(launches):
             _lib.conv2d_fwd(d, a, b, packed, out=o)
-            e1.record()
-            evs.append((e0, e1))
+            evs[i + 1].record()
         torch.cuda.synchronize()
-        ts = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
-        out.append((name, ts[len(ts) // 2]))           # median
-    return out
+        for i, (name, *_r) in enumerate(launches):
+            times[name].append(evs[i].elapsed_time(evs[i + 1]))
+    return [(name, sorted(times[name])[reps // 2]) for name, *_ in launches]
 
 
 def timed_rollout(eng, flush, steps, warmup):
@@ -438,8 +441,9 @@ def main():
                      'share_of_step': top['share'],
                      'whole_step_frac_of_roof': round(t_roof * 1e3 / step_ms, 3),
                      'whole_step_us': round(1e3 * step_ms, 1),
-                     'note': 'per-layer times: single launches, L2 flushed before each; whole_step: sum of the per-layer '
-                             'roofline times / the measured 6-hour step inside the rollout graph'})
+                     'note': 'per-layer times: CUDA events between the launches of one model step enqueued in order, L2 '
+                             'flushed before every repetition of the step; whole_step: sum of the per-layer roofline '
+                             'times / the measured 6-hour step inside the rollout graph'})
 
     # ---------------- the other BASELINE configurations (rank 0, N = 1 only: they are single-GPU records)
     extra = None

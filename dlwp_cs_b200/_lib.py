@@ -28,6 +28,11 @@ class ConvWeights(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ('w_eq', 'w_pol', 'w_np', 'b_eq', 'b_pol', 'b_np')]
 
 
+class Chain(ctypes.Structure):
+    _fields_ = [('dep', ctypes.c_void_p), ('dep_target', ctypes.c_uint32), ('done', ctypes.c_void_p),
+                ('tile_counter', ctypes.c_void_p), ('error_flag', ctypes.c_void_p)]
+
+
 class ConvWgrads(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ('dw_eq', 'dw_pol', 'dw_np', 'db_eq', 'db_pol', 'db_np')]
 
@@ -72,6 +77,8 @@ def load():
         'dlwpcs_insolation': (i32, [vp, i32, i32, i64, i32, i32, i32, vp, vp, vp, vp, f32, vp]),
         'dlwpcs_adam_step_dev': (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp]),
         'dlwpcs_trace_read': (i32, [vp, i32, ctypes.POINTER(ctypes.c_int), i32]),
+        'dlwpcs_conv2d_fwd_chained': (i32, [dp, vp, vp, vp, vp, ctypes.POINTER(Chain), vp]),
+        'dlwpcs_chain_target': (ctypes.c_uint32, [dp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)          # AttributeError here == header and library out of sync
@@ -87,7 +94,8 @@ EXPORTED = ('dlwpcs_version', 'dlwpcs_last_error', 'dlwpcs_conv_out_edge', 'dlwp
             'dlwpcs_dgrad_workspace_bytes', 'dlwpcs_conv2d_dgrad', 'dlwpcs_wgrad_workspace_bytes',
             'dlwpcs_conv2d_wgrad', 'dlwpcs_act_fwd', 'dlwpcs_act_bwd', 'dlwpcs_conv2d_fwd_host',
             'dlwpcs_mse_loss_grad', 'dlwpcs_adam_step', 'dlwpcs_adam_step_dev', 'dlwpcs_insolation', 'dlwpcs_pool2',
-            'dlwpcs_up2cat_fwd', 'dlwpcs_up2cat_bwd', 'dlwpcs_feed_gather', 'dlwpcs_trace_read')
+            'dlwpcs_up2cat_fwd', 'dlwpcs_up2cat_bwd', 'dlwpcs_feed_gather', 'dlwpcs_trace_read',
+            'dlwpcs_conv2d_fwd_chained', 'dlwpcs_chain_target')
 
 
 class DlwpcsError(RuntimeError):
@@ -204,6 +212,26 @@ def conv2d_fwd(d, x0, x1, packed, out=None):
     y = out if out is not None else torch.empty(shp, dtype=ydt, device=x0.device)
     check(load().dlwpcs_conv2d_fwd(ctypes.byref(d), ptr(x0), ptr(x1), ptr(packed), ptr(y), stream_ptr()))
     return y
+
+
+def chain_target(d):
+    """Value the per-sample completion counters of a chained launch of `d` reach (tiles per sample x epilogue warps)."""
+    v = load().dlwpcs_chain_target(ctypes.byref(d))
+    if v == 0:
+        raise DlwpcsError('chained launches need a bf16 tensor-core configuration')
+    return int(v)
+
+
+def conv2d_fwd_chained(d, x0, x1, packed, out, dep, dep_target, done, tile_counter, error_flag=None):
+    """dlwpcs_conv2d_fwd_chained: dep / done are int32 device tensors of `batch` counters (dep may be None: plain stream
+    order), tile_counter / error_flag 1-element int32 device tensors; all zero before the chain starts."""
+    require_cuda(x0, x1, packed, out, dep, done, tile_counter, error_flag)
+    ch = Chain(dep.data_ptr() if dep is not None else None, int(dep_target) if dep is not None else 0,
+               done.data_ptr() if done is not None else None, tile_counter.data_ptr(),
+               error_flag.data_ptr() if error_flag is not None else None)
+    check(load().dlwpcs_conv2d_fwd_chained(ctypes.byref(d), ptr(x0), ptr(x1), ptr(packed), ptr(out), ctypes.byref(ch),
+                                           stream_ptr()))
+    return out
 
 
 def conv2d_dgrad(d, dy, y, packed_t):

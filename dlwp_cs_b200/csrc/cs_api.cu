@@ -886,11 +886,30 @@ int dlwpcs_conv2d_fwd(const dlwpcs_conv_desc *d, const void *x0, const void *x1,
   if (d->x_dtype == DLWPCS_BF16) {
     const char *why = "";
     CS_CHECK(tc_supported(d, g, &why), "bf16 tensor-core path does not support this configuration: %s", why);
-    return tc_conv_fwd(d, g, x0, x1, packed_w, y, (cudaStream_t)stream);
+    return tc_conv_fwd(d, g, x0, x1, packed_w, y, nullptr, (cudaStream_t)stream);
   }
   CS_CHECK(d->y_dtype == DLWPCS_F32, "float32 input requires float32 output");
   return fp32_conv_fwd(d, g, (const float *)x0, (const float *)x1, (const float *)packed_w, (float *)y,
                        (cudaStream_t)stream);
+}
+
+int dlwpcs_conv2d_fwd_chained(const dlwpcs_conv_desc *d, const void *x0, const void *x1, const void *packed_w, void *y,
+                              const dlwpcs_chain *chain, void *stream) {
+  Geometry g;
+  if (int rc = check_common(d, &g)) return rc;
+  CS_CHECK(chain != nullptr, "null chain descriptor");
+  CS_CHECK(d->x_dtype == DLWPCS_BF16, "chained launches exist on the bf16 tensor-core path only");
+  if (d->batch == 0) return 0;
+  CS_CHECK(x0 && packed_w && y && (d->c1 == 0 || x1), "null tensor pointer");
+  const char *why = "";
+  CS_CHECK(tc_supported(d, g, &why), "bf16 tensor-core path does not support this configuration: %s", why);
+  return tc_conv_fwd(d, g, x0, x1, packed_w, y, chain, (cudaStream_t)stream);
+}
+
+uint32_t dlwpcs_chain_target(const dlwpcs_conv_desc *d) {
+  Geometry g;
+  if (check_common(d, &g) || d->x_dtype != DLWPCS_BF16) return 0;
+  return tc_chain_target(d, g);
 }
 
 static int check_bwd(const dlwpcs_conv_desc *d, Geometry *g) {

@@ -73,7 +73,8 @@ int64_t tc_packed_weight_bytes(const dlwpcs_conv_desc *d, const Geometry &g, int
 int tc_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, int transposed,
                     void *packed, cudaStream_t st);
 int tc_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed,
-                void *y, cudaStream_t st);
+                void *y, const dlwpcs_chain *chain, cudaStream_t st);
+uint32_t tc_chain_target(const dlwpcs_conv_desc *d, const Geometry &g);
 bool tc_supported(const dlwpcs_conv_desc *d, const Geometry &g, const char **why);
 int tc_conv_dgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *dy, const void *y, const void *packed_t,
                   void *dx, void *workspace, cudaStream_t st);

@@ -84,6 +84,14 @@ struct TcP {
   float mask_slope, mask_max;
   long long *dbg;               // optional phase timestamps (DLWPCS_TC_TIMING=1)
   unsigned long long *trace;    // optional per-CTA %globaltimer stamps of this launch (DLWPCS_TC_TRACE=1), [grid][8]
+  // chained launch (dlwpcs_conv2d_fwd_chained): instead of waiting for the whole previous grid, a tile waits until the
+  // launch that produced its input has completed that SAMPLE (per-sample completion counters), and tiles are handed out
+  // by an atomic counter so that CTAs that start early (on SMs the previous layer has already left) take more of them
+  const unsigned *dep;          // [batch] completion counters of the producing launch; nullptr = stream order (classic)
+  unsigned dep_target;          // dep[b] >= dep_target  <=>  sample b of the input is complete
+  unsigned *done;               // [batch] counters this launch raises (once per completed tile); may be nullptr
+  unsigned *tile_ctr;           // dynamic tile scheduler; nullptr = static round-robin over the grid
+  unsigned *chain_err;          // set to 1 if a dependency wait timed out (diagnostics; never hang the GPU)
   int knock;                    // bottleneck analysis (DLWPCS_TC_KNOCK): 1 no gathers, 2 no MMAs, 4 no epilogue math/stores, 8 no global stores
   TcPlan pl_;
 };
@@ -132,6 +140,43 @@ __device__ __forceinline__ TileInfo decode_tile(int id, int batch, int tpf) {
   }
   return t;
 }
+
+// k-th tile of this CTA.  Static schedule: blockIdx.x + k * gridDim.x.  Dynamic schedule (chained launches): lane 1 of the
+// producer warp draws tile ids from a global counter and publishes them in a 16-entry shared-memory ring tagged with
+// k + 1; every role polls its entry (the producer runs at most TS + PS + AS = 7 tiles ahead of the slowest role).
+constexpr int TILE_RING = 16;
+// The poll lives inside one opaque asm statement (like mbar_wait): a spin loop written in C++ makes the compiler treat
+// everything after it as divergent, and the MMA issuers lose their uniform-register descriptors (2x the R2UR count).
+__device__ __forceinline__ int tile_poll(uint32_t ring, int k) {
+  uint32_t lo;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 hi;\n\t"
+      "POLL_TILE:\n\t"
+      "ld.volatile.shared.v2.u32 {%0, hi}, [%1];\n\t"
+      "setp.ne.u32 p, hi, %2;\n\t"
+      "@p bra POLL_TILE;\n\t"
+      "}"
+      : "=r"(lo)
+      : "r"(ring + 8u * (uint32_t)(k & (TILE_RING - 1))), "r"((uint32_t)(k + 1))
+      : "memory");
+  return (int)lo;
+}
+__device__ __forceinline__ void tile_publish(uint32_t ring, int k, int tile) {
+  asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(ring + 8u * (uint32_t)(k & (TILE_RING - 1))),
+               "r"((uint32_t)tile), "r"((uint32_t)(k + 1))
+               : "memory");
+}
+// Loop header over the tiles of a CTA: the static variant is literally the round-robin for-loop of the classic kernel
+// (the compiler's code for it must not change), the dynamic one polls the ring.  K is the running tile index.
+#define TC_TILE_LOOP(K)                                                                                    \
+  for (int tile = DYN ? tile_poll(tile_ring, 0) : (int)blockIdx.x; DYN ? tile >= 0 : tile < ntiles;        \
+       tile = DYN ? tile_poll(tile_ring, K + 1) : tile + (int)gridDim.x, ++K)
+#define TC_TILE_LOOP_UNIFORM(K)                                                                                   \
+  for (int tile = DYN ? __shfl_sync(0xffffffffu, tile_poll(tile_ring, 0), 0) : (int)blockIdx.x;                   \
+       DYN ? tile >= 0 : tile < ntiles;                                                                           \
+       tile = DYN ? __shfl_sync(0xffffffffu, tile_poll(tile_ring, K + 1), 0) : tile + (int)gridDim.x, ++K)
 
 // One 8-channel slab of one patch row through registers: 2x2 mean, activation-derivative mask, or plain copy.
 __device__ __noinline__ uint4 gather_regs(const TcP &P, const __nv_bfloat16 *src, int C, int mode, size_t pix, int cc,
@@ -228,7 +273,7 @@ __device__ __noinline__ void generic_gather(const TcP &P, uint32_t stage, int np
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------
-template <int MBT, int KC16T>
+template <int MBT, int KC16T, bool DYN>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcP P) {
   extern __shared__ uint8_t smem_raw[];
   const TcPlan &L = P.pl_;
@@ -245,6 +290,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t tabring = misc + 512 + MAX_UNITS * 8 + (uint32_t)(3 * L.CoutP * 4);          // TS slots of tabBytes
   const int32_t *s_tab = reinterpret_cast<const int32_t *>(gen + (tabring - base));
   const uint32_t bar_tfull = misc + 256, bar_tempty = misc + 288;
+  const uint32_t tile_ring = misc + 320;                // 16 x {tile id, tag}
+  const uint32_t epi_ctr = misc + 448;                  // epilogue warps that have finished their share of a tile (monotonic)
+  const bool chained = DYN && P.dep != nullptr;
   const uint32_t stg0 = (tabring + (uint32_t)(L.TS * L.tabBytes) + 127u) & ~127u;      // 8 warps x stgBufs x stgBytes
 
   // warp index broadcast from lane 0 (cutlass::canonical_warp_idx_sync): the role branches become provably warp-uniform,
@@ -266,9 +314,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_init(bar_aempty + 8 * i, TC_EPI);
     }
     for (int i = 0; i < L.TS; ++i) {
-      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tfull + 8 * i, chained ? 2 : 1);     // chained: the table copy and the resolved dependency
       mbar_init(bar_tempty + 8 * i, TC_LOADERS);
     }
+    for (int i = 0; i < TILE_RING; ++i) *reinterpret_cast<volatile unsigned long long *>(gen + (tile_ring - base) + 8 * i) = 0ull;
+    *reinterpret_cast<volatile uint32_t *>(gen + (epi_ctr - base)) = 0u;
     fence_mbar_init();
   }
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, (uint32_t)L.tmemCols);
@@ -290,8 +340,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // the loaders' lookups do not queue behind their own DRAM gathers in the L1 pipeline =====
     if (lane == 0) {
       int st = 0, ph = 0, prev_grp = -1;
-      asm volatile("griddepcontrol.wait;" ::: "memory");      // the packed weights may come from the previous kernel
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      // the packed weights may come from the previous kernel (a chained launch's weights are older than its whole chain)
+      if (!chained) asm volatile("griddepcontrol.wait;" ::: "memory");
+      int k = 0;
+      TC_TILE_LOOP(k) {
         const int grp = decode_tile(tile, P.batch, L.tpf).grp;
         if (L.resident && grp == prev_grp) continue;
         prev_grp = grp;
@@ -305,9 +357,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (++st == L.NST) { st = 0; ph ^= 1; }
         }
       }
+    } else if (DYN && lane == 2 && P.done) {
+      // completion signaller: tile k is complete when all epilogue warps have counted it; publish it device-wide
+      int k = 0;
+      TC_TILE_LOOP(k) {
+        const unsigned want = (unsigned)(k + 1) * (unsigned)(TC_EPI / 32);
+        unsigned v;
+        for (;;) {
+          asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(epi_ctr) : "memory");
+          if (v >= want) break;
+          __nanosleep(256);
+        }
+        __threadfence();           // cumulative: the epilogue warps' stores observed through the CTA-scope acquire above
+        atomicAdd(P.done + decode_tile(tile, P.batch, L.tpf).b, 1u);
+      }
     } else if (lane == 1) {
       int ts = 0, tp = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      // dynamic schedule: the draw for tile k+1 is in flight while tile k is processed (the atomic's round trip to L2
+      // would otherwise sit in front of every table copy); a CTA over-draws the counter by one at the end -- harmless
+      // The first tile of a CTA is its own index (148 simultaneous draws on one address would serialise in the L2 slice
+      // for ~2 us at the start of every layer); the counter hands out the tiles from gridDim.x on.
+      unsigned drawn = blockIdx.x;
+      for (int k = 0;; ++k) {
+        int tile;
+        if constexpr (DYN) {
+          tile = drawn < (unsigned)ntiles ? (int)drawn : -1;
+          tile_publish(tile_ring, k, tile);          // to the other roles before anything else
+          if (tile >= 0) drawn = gridDim.x + atomicAdd(P.tile_ctr, 1u);
+        } else {
+          const long long t = (long long)blockIdx.x + (long long)k * gridDim.x;
+          tile = t < ntiles ? (int)t : -1;
+        }
+        if (tile < 0) break;
         const TileInfo T = decode_tile(tile, P.batch, L.tpf);
         const int MBc = min(L.MB, L.nmb - T.tf * L.MB);
         const uint32_t bytes = (uint32_t)((MBc * 128 + L.haloExt + 3) / 4 * 4) * 4u;
@@ -316,6 +397,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         mbar_expect_tx(bar_tfull + 8 * ts, bytes * (1 + L.twoTabs));
         tma_bulk_g2s(tabring + ts * L.tabBytes, P.tab0 + off, bytes, bar_tfull + 8 * ts);
         if (L.twoTabs) tma_bulk_g2s(tabring + ts * L.tabBytes + L.NPIXp * 4, P.tab1 + off, bytes, bar_tfull + 8 * ts);
+        if (++ts == L.TS) { ts = 0; tp ^= 1; }
+      }
+    } else if (DYN && lane == 3 && chained) {
+      // dependency resolver: the table slot of a tile is published (second arrival on its barrier) only when the producing
+      // launch has finished sample T.b -- the loaders start behind that barrier, so every gather of the tile is ordered
+      // after this acquire load.  The table copy itself (static data) does not wait for it.
+      int ts = 0, tp = 0, k = 0, last_b = -1;
+      TC_TILE_LOOP(k) {
+        const int b = decode_tile(tile, P.batch, L.tpf).b;
+        if (b != last_b) {
+          const unsigned *c = P.dep + b;
+          unsigned v;
+          const long long t0 = clock64();
+          for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+            if (v >= P.dep_target) break;
+            if (clock64() - t0 > (1ll << 32)) {        // ~2 s: mis-wired chain -- flag it and go on instead of hanging
+              if (P.chain_err) atomicExch(P.chain_err, 1u);
+              break;
+            }
+            __nanosleep(64);
+          }
+          last_b = b;
+        }
+        mbar_wait(bar_tempty + 8 * ts, tp ^ 1);      // the slot's previous use is over: this arrival counts for tile k
+        mbar_arrive(bar_tfull + 8 * ts);
         if (++ts == L.TS) { ts = 0; tp ^= 1; }
       }
     }
@@ -334,14 +441,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int kh = L.taps / P.kw;
     const uint32_t blk16 = (uint32_t)L.blockBytes >> 4, urow16 = ((uint32_t)(P.dh * L.Wv) * L.RB) >> 4,
                    vcol16 = ((uint32_t)P.dw * L.RB) >> 4;
-    int st = 0, ph = 0, sp = 0, pp = 0, sa = 0, pa = 0, prev_grp = -1, k = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+    int st = 0, ph = 0, sp = 0, pp = 0, sa = 0, pa = 0, prev_grp = -1;
+    int k = 0;
+    // dynamic schedule: the tile id is broadcast from lane 0, which keeps everything derived from it provably
+    // warp-uniform (uniform registers for the MMA descriptors) although it is read from shared memory
+    TC_TILE_LOOP_UNIFORM(k) {
       const TileInfo T = decode_tile(tile, P.batch, L.tpf);
       const int MBc = min(L.MB, L.nmb - T.tf * L.MB);
       const bool load_ev = !(L.resident && T.grp == prev_grp);
       prev_grp = T.grp;
-      const int next = tile + gridDim.x;
-      const bool release_w = !L.resident || next >= ntiles || decode_tile(next, P.batch, L.tpf).grp != T.grp;
+      int next;
+      if constexpr (DYN) {
+        next = L.resident ? __shfl_sync(0xffffffffu, tile_poll(tile_ring, k + 1), 0) : -1;
+      } else {
+        next = tile + (int)gridDim.x;
+        if (next >= ntiles) next = -1;
+      }
+      const bool release_w = !L.resident || next < 0 || decode_tile(next, P.batch, L.tpf).grp != T.grp;
       stamp(P, 5, k, lane == 0 && mw == 0);
       mbar_wait(bar_aempty + 8 * sa, pa ^ 1);
       mbar_wait(bar_pfull + 8 * sp, pp);
@@ -461,10 +577,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int cprLog = (cpr & (cpr - 1)) == 0 ? 31 - __clz(cpr) : -1;          // rows of 2^k chunks: shifts instead of divisions
     const uint32_t smask = (cpr & (cpr - 1)) == 0 ? min(cpr, 8u) - 1u : 0u;    // XOR swizzle of the chunk index by row
     int sa = 0, pa = 0, k = 0;
-    asm volatile("griddepcontrol.wait;" ::: "memory");        // the bias sits behind the packed weights
+    if (!chained) asm volatile("griddepcontrol.wait;" ::: "memory");        // the bias sits behind the packed weights
     for (int i = tid - EPI_WARP0 * 32; i < 3 * L.CoutP; i += TC_EPI) s_bias[i] = P.bias[i];
     asm volatile("bar.sync 2, %0;" ::"n"(TC_EPI) : "memory");
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+    TC_TILE_LOOP(k) {
       const TileInfo T = decode_tile(tile, P.batch, L.tpf);
       const int MBc = min(L.MB, L.nmb - T.tf * L.MB);
       const float *bias = s_bias + T.grp * L.CoutP;
@@ -472,6 +588,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       stamp(P, 8, k, tid == EPI_WARP0 * 32);
       mbar_wait(bar_afull + 8 * sa, pa);
       tc_fence_after();
+      if (DYN && P.done && k > 0) {
+        // count the PREVIOUS tile as stored by this warp (release at CTA scope, after the warp has converged).  Done here,
+        // one tile late and before this tile's first global store, the release finds the old stores already drained and
+        // costs nothing on the epilogue's critical path; lane 2 of the producer warp turns complete tiles into the
+        // device-wide per-sample counter (one device-scope fence per tile per CTA)
+        __syncwarp();
+        if (lane == 0) asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(epi_ctr) : "memory");
+      }
       trace(P, 4, k == 0 && tid == EPI_WARP0 * 32);
       stamp(P, 9, k, tid == EPI_WARP0 * 32);
       for (int mb = half; mb < MBc; mb += 2) {
@@ -565,6 +689,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       stamp(P, 10, k, tid == EPI_WARP0 * 32);
       if (++sa == L.AS) { sa = 0; pa ^= 1; }
     }
+    if (DYN && P.done && k > 0) {                 // the last tile of the CTA
+      __syncwarp();
+      if (lane == 0) asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(epi_ctr) : "memory");
+    }
     trace(P, 5, tid == EPI_WARP0 * 32);
     if (P.trace && tid == EPI_WARP0 * 32) P.trace[blockIdx.x * 8 + 7] = (unsigned long long)k;
   } else if (warp < LOAD_WARP0 + 8) {
@@ -572,9 +700,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int lt = tid - LOAD_WARP0 * 32;
     int si = 0, pi = 0, k = 0, ts = 0, tp = 0;
     const int w2_0 = P.n * 2;
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!chained) asm volatile("griddepcontrol.wait;" ::: "memory");
     trace(P, 2, lt == 0);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+    TC_TILE_LOOP(k) {
       const TileInfo T = decode_tile(tile, P.batch, L.tpf);
       const int MBc = min(L.MB, L.nmb - T.tf * L.MB);
       const int q0 = T.tf * L.MB * 128;
@@ -620,6 +748,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
           }
         } else if (mode == DLWPCS_SRC_POOL2 && !P.mask_y) {
+          // (ld.global.nc stays legal under a chained launch: a sample's pixels are only ever read after the producing
+          // launch has completed that sample, and L1 is invalidated at the start of every kernel, so no line of it can
+          // be cached from before it was final.  ld.global.cg here costs spills across the whole kernel.)
           // 2x2 mean (AveragePooling3D((1,2,2)), train_cs.py:197) through registers: two patch rows = eight 16-byte
           // loads in flight per thread; the mean is rounded to bf16 once, like a stored pooled tensor would be
           for (int i0 = lt >> L.logS; i0 < npix; i0 += 2 * pstep) {
@@ -897,27 +1028,28 @@ int g_trace_launches = 0;
 int launch_tc(TcP &P, cudaStream_t st) {
   const TcPlan &L = P.pl_;
   typedef void (*kern_t)(const TcP);
-  static const kern_t kerns[4][4] = {
-      {conv_tc_kernel<1, 1>, conv_tc_kernel<1, 2>, conv_tc_kernel<1, 3>, conv_tc_kernel<1, 4>},
-      {conv_tc_kernel<2, 1>, conv_tc_kernel<2, 2>, conv_tc_kernel<2, 3>, conv_tc_kernel<2, 4>},
-      {conv_tc_kernel<3, 1>, conv_tc_kernel<3, 2>, conv_tc_kernel<3, 3>, conv_tc_kernel<3, 4>},
-      {conv_tc_kernel<4, 1>, conv_tc_kernel<4, 2>, conv_tc_kernel<4, 3>, conv_tc_kernel<4, 4>}};
-  static bool attr_set[kMaxDevices][4][4] = {};      // the shared-memory opt-in is per device
+#define TC_ROW(MB, D) {conv_tc_kernel<MB, 1, D>, conv_tc_kernel<MB, 2, D>, conv_tc_kernel<MB, 3, D>, conv_tc_kernel<MB, 4, D>}
+  static const kern_t kerns[2][4][4] = {{TC_ROW(1, false), TC_ROW(2, false), TC_ROW(3, false), TC_ROW(4, false)},
+                                        {TC_ROW(1, true), TC_ROW(2, true), TC_ROW(3, true), TC_ROW(4, true)}};
+#undef TC_ROW
+  static bool attr_set[kMaxDevices][2][4][4] = {};      // the shared-memory opt-in is per device
   CS_CHECK(L.MB >= 1 && L.MB <= 4 && L.KC % 16 == 0 && L.KC <= 64, "internal: bad tile plan");
   const int ki = L.MB - 1, kj = L.KC / 16 - 1, dev_i = current_device_index();
-  const kern_t kern = kerns[ki][kj];
-  if (!attr_set[dev_i][ki][kj]) {
+  const int dyn = P.tile_ctr ? 1 : 0;
+  const kern_t kern = kerns[dyn][ki][kj];
+  if (!attr_set[dev_i][dyn][ki][kj]) {
     CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
-    attr_set[dev_i][ki][kj] = true;
+    attr_set[dev_i][dyn][ki][kj] = true;
   }
   const long long ntiles = 6LL * P.batch * L.tpf;
   CS_CHECK(ntiles < (1LL << 30), "batch too large");
   int grid = num_sms();
   if (grid > ntiles) grid = (int)ntiles;
   // CTA c walks tiles c, c + grid, ...: when the tiles of a face differ in size (e.g. 5 m-blocks = 3 + 2) and grid and
-  // tiles-per-face share a factor, some CTAs would only ever see the large tiles -- keep the two coprime
+  // tiles-per-face share a factor, some CTAs would only ever see the large tiles -- keep the two coprime (the dynamic
+  // schedule of a chained launch hands tiles out on demand and uses every SM)
   auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
-  while (grid > 1 && L.nmb % L.MB != 0 && gcd(grid, L.tpf) != 1) --grid;
+  while (!P.tile_ctr && grid > 1 && L.nmb % L.MB != 0 && gcd(grid, L.tpf) != 1) --grid;
   static const int timing = env_int("DLWPCS_TC_TIMING", 0);
   static const int knock = env_int("DLWPCS_TC_KNOCK", 0);
   P.knock = knock;
@@ -1018,13 +1150,28 @@ int tc_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_c
   return 0;
 }
 
+uint32_t tc_chain_target(const dlwpcs_conv_desc *d, const Geometry &g) {
+  TcPlan L;
+  if (make_plan(d, g, d->cin, d->cout, &L)) return 0;
+  return 6u * (uint32_t)L.tpf;      // the counter of a sample moves once per completed tile
+}
+
 int tc_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed,
-                void *y, cudaStream_t st) {
+                void *y, const dlwpcs_chain *chain, cudaStream_t st) {
   TcP P;
   memset(&P, 0, sizeof(P));
   const char *r = make_plan(d, g, d->cin, d->cout, &P.pl_);
   CS_CHECK(r == nullptr, "bf16 tensor-core path does not support this configuration: %s", r);
   TcPlan &L = P.pl_;
+  if (chain) {
+    CS_CHECK(chain->tile_counter != nullptr, "chained launch needs a tile counter");
+    CS_CHECK(chain->dep == nullptr || chain->dep_target > 0, "chained launch: dependency counters without a target");
+    P.dep = chain->dep;
+    P.dep_target = chain->dep_target;
+    P.done = chain->done;
+    P.tile_ctr = chain->tile_counter;
+    P.chain_err = chain->error_flag;
+  }
   P.x0 = (const __nv_bfloat16 *)x0;
   P.x1 = (const __nv_bfloat16 *)x1;
   P.tab0 = get_patch_table(g, L.Wv, L.G, d->n, d->halo, d->mode0);

@@ -9,6 +9,8 @@ DLWP/model/models.py:446-454 without the two host<->device copies per step).
     kernel's load stage / epilogue; state, forcing and the forecast ring stay in HBM; the whole multi-step rollout is
     replayed from one CUDA graph.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -256,7 +258,7 @@ class RolloutEngine(object):
     """
 
     def __init__(self, model, batch, n, steps, forcing_channels=0, dtype=torch.float32, use_graph=True,
-                 per_step_forcing=False, device=None, input_order=None):
+                 per_step_forcing=False, device=None, input_order=None, chain=None):
         if n % (1 << model.levels) != 0:
             raise ValueError('%s pools %d times: face edge must be divisible by %d' % (model.arch, model.levels, 1 << model.levels))
         self.model, self.batch, self.n, self.steps = model, batch, n, steps
@@ -324,7 +326,26 @@ class RolloutEngine(object):
         self.graph_host = None
         self.host_ring = None
         self.host_chunk = 0
+        # chained launches (bf16 tensor-core path, dlwpcs_conv2d_fwd_chained): layer k+1 starts on the SMs layer k has left
+        # as soon as the SAMPLES its tiles read are complete (per-sample completion counters, dynamic tile scheduler)
+        # instead of waiting for the whole previous grid.  One counter block per launch of the rollout, zeroed at the start
+        # of every run.  OFF by default: measured on the B200 (profiles/r2_chain.md) the overlap it buys (~2-3 us per layer)
+        # is eaten by the scheduler / completion-counter overheads (~2.7 us per layer) -- 409 vs 359 us per model step.
+        if chain is None:
+            chain = os.environ.get('DLWPCS_CHAIN', '0') != '0'
+        self.chain = bool(chain) and dtype == torch.bfloat16
+        self._chain_mode = int(os.environ.get('DLWPCS_CHAIN_MODE', '1'))
+        if self.chain:
+            nl = steps * len(self.plan)
+            self._chain_stride = batch + 1
+            self._chain_mem = torch.zeros(nl * self._chain_stride + 1, dtype=torch.int32, device=self.device)
+            self._chain_targets = [_lib.chain_target(item[1]) for item in self.plan]
         self.repack()
+
+    @property
+    def chain_error(self):
+        """True if a chained launch gave up waiting for its producer (never expected; see include/dlwpcs.h)."""
+        return bool(self.chain and int(self._chain_mem[-1].item()) != 0)
 
     def repack(self):
         """(Re)pack the layer weights into the kernels' layouts -- call after the model's parameters change."""
@@ -397,17 +418,35 @@ class RolloutEngine(object):
         self.graph = None
         self.graph_host = None
 
-    def _step(self, t):
+    def _step(self, t, chained=False):
+        """One model step.  chained: the launch follows the previous conv launch of this run directly on the stream (no
+        other kernel in between), so it may depend on that launch's per-sample counters instead of on stream order."""
         if self.solar is not None:
             so = self.solar
             _lib.insolation(self.forcing, 0, so['n'], so['sinlat'], so['coslat'], so['lon'], so['days'][t], so['S'])
-        for name, d, s0, s1, dst, packed in self.plan:
+            chained = False
+        nl = len(self.plan)
+        for i, (name, d, s0, s1, dst, packed) in enumerate(self.plan):
             out = self.ring[t] if dst == 'out' else self.buf[dst]
-            _lib.conv2d_fwd(d, self._src(s0, t), self._src(s1, t), packed, out=out)
+            if not self.chain:
+                _lib.conv2d_fwd(d, self._src(s0, t), self._src(s1, t), packed, out=out)
+                continue
+            li = t * nl + i
+            blk = self._chain_mem[li * self._chain_stride:(li + 1) * self._chain_stride]
+            dep = dep_target = None
+            mode = self._chain_mode          # diagnostics: 1 full chain, 2 dynamic tiles + completion counters, 3 dynamic tiles only
+            if chained and mode == 1:
+                prev = self._chain_mem[(li - 1) * self._chain_stride:li * self._chain_stride]
+                dep, dep_target = prev[:self.batch], self._chain_targets[(i - 1) % nl]
+            _lib.conv2d_fwd_chained(d, self._src(s0, t), self._src(s1, t), packed, out, dep, dep_target,
+                                    blk[:self.batch] if mode < 3 else None, blk[self.batch:], self._chain_mem[-1:])
+            chained = True
 
     def _enqueue_all(self):
+        if self.chain:
+            self._chain_mem.zero_()
         for t in range(self.steps):
-            self._step(t)
+            self._step(t, chained=self.chain and t > 0)
 
     def _ensure_graph(self):
         if self.graph is not None or not self.use_graph:
@@ -416,6 +455,8 @@ class RolloutEngine(object):
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
+            if self.chain:
+                self._chain_mem.zero_()
             self._step(0)
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
@@ -457,10 +498,12 @@ class RolloutEngine(object):
         reference copies every step's result to the host before it starts the next one, models.py:446-454)."""
         main = torch.cuda.current_stream(self.device)
         side = self._side
+        if self.chain:
+            self._chain_mem.zero_()
         for t0 in range(0, self.steps, self.host_chunk):
             t1 = min(self.steps, t0 + self.host_chunk)
             for t in range(t0, t1):
-                self._step(t)
+                self._step(t, chained=self.chain and t > 0)
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 stage = self._stage[(t0 // self.host_chunk) % 2]

@@ -162,6 +162,25 @@ int dlwpcs_feed_gather(const float *array, const float *insolation, const float 
  * device, runs pad(halo)+conv, copies y back; synchronous.                                                            */
 int dlwpcs_conv2d_fwd_host(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, const void *x_host, void *y_host);
 
+/* Chained launch of the forward convolution (bf16 tensor-core path) for back-to-back layers of a network (the layer
+ * sequence of Azure/train_cs.py:233-388 inside the rollout loop of models.py:446-454): instead of waiting for the whole
+ * previous kernel, every tile waits until the launch that produced its input has completed that SAMPLE, and tiles are
+ * handed out on demand, so the pipeline fill of layer k+1 runs on the SMs layer k has already left.  The launches must be
+ * enqueued back to back on one stream; `dep` = the `done` counters handed to the launch that produced x0 (NULL: plain
+ * stream order, e.g. after a non-chained kernel), `dep_target` = dlwpcs_chain_target(desc of that launch).  All counters
+ * are caller-owned device memory, zero before the first launch of a chain replay; error_flag (optional) is set to 1 if a
+ * dependency did not resolve within ~2 s (mis-wired chain) instead of hanging the device.                              */
+typedef struct dlwpcs_chain {
+  const uint32_t *dep;
+  uint32_t dep_target;
+  uint32_t *done;            /* [batch] counters this launch raises, or NULL                                            */
+  uint32_t *tile_counter;    /* one counter: the launch's dynamic tile scheduler                                        */
+  uint32_t *error_flag;
+} dlwpcs_chain;
+int dlwpcs_conv2d_fwd_chained(const dlwpcs_conv_desc *d, const void *x0, const void *x1, const void *packed_w, void *y,
+                              const dlwpcs_chain *chain, void *stream);
+uint32_t dlwpcs_chain_target(const dlwpcs_conv_desc *d);
+
 /* Diagnostics (no reference counterpart): with DLWPCS_TC_TRACE=1 in the environment every launch of the tensor-core
  * convolution kernel records, per CTA, eight %globaltimer values (ns): 0 kernel entry, 1 prologue done, 2 loaders past
  * the grid dependency, 3 first input patch in shared memory, 4 first accumulators complete, 5 last epilogue done,
