@@ -301,8 +301,9 @@ def main():
     dev = torch.device('cuda', local_rank)
     dist = None
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'       # NCCL would print its version banner on stdout, next to the JSON line
+        if os.environ.get('NCCL_DEBUG') and not os.environ.get('NCCL_DEBUG_FILE'):
+            os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'     # NCCL logs (version banner, INFO) go to stdout otherwise: keep
+                                                              # them, but away from the JSON line
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
 

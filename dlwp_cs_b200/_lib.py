@@ -247,8 +247,10 @@ def conv2d_dgrad(d, dy, y, packed_t):
     return dx
 
 
-def conv2d_wgrad(d, x0, dy, y):
-    """Returns (dw_eq, dw_pol, dw_np|None, db_eq|None, db_pol|None, db_np|None), float32 HWIO."""
+def conv2d_wgrad(d, x0, dy, y, outs=None):
+    """Returns (dw_eq, dw_pol, dw_np|None, db_eq|None, db_pol|None, db_np|None), float32 HWIO.  outs: optional tuple of six
+    pre-allocated contiguous float32 tensors (None where the layer has no such parameter) to write into -- e.g. views of a
+    flat gradient buffer."""
     require_cuda(x0, dy, y)
     lib = load()
     nbytes = lib.dlwpcs_wgrad_workspace_bytes(ctypes.byref(d))
@@ -257,13 +259,17 @@ def conv2d_wgrad(d, x0, dy, y):
     dev = x0.device
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
     wshape = (d.kh, d.kw, d.cin, d.cout)
-    mk = lambda shape: torch.empty(shape, dtype=torch.float32, device=dev)
-    dw_eq, dw_pol = mk(wshape), mk(wshape)
-    dw_np = mk(wshape) if d.independent_north_pole else None
-    db_eq = mk((d.cout,)) if d.use_bias else None
-    db_pol = mk((d.cout,)) if d.use_bias else None
-    db_np = mk((d.cout,)) if (d.use_bias and d.independent_north_pole) else None
-    outs = (dw_eq, dw_pol, dw_np, db_eq, db_pol, db_np)
+    inp, bias = bool(d.independent_north_pole), bool(d.use_bias)
+    shapes = (wshape, wshape, wshape if inp else None, (d.cout,) if bias else None, (d.cout,) if bias else None,
+              (d.cout,) if (bias and inp) else None)
+    if outs is not None:
+        for given, shp in zip(outs, shapes):
+            if (given is None) != (shp is None) or (given is not None and (
+                    tuple(given.shape) != tuple(shp) or given.dtype != torch.float32 or not given.is_contiguous())):
+                raise DlwpcsError('conv2d_wgrad: output buffers do not match the layer')
+        require_cuda(*outs)
+    else:
+        outs = tuple(None if shp is None else torch.empty(shp, dtype=torch.float32, device=dev) for shp in shapes)
     g = ConvWgrads(*[t.data_ptr() if t is not None else None for t in outs])
     check(lib.dlwpcs_conv2d_wgrad(ctypes.byref(d), ptr(x0), ptr(dy), ptr(y), ctypes.byref(g), ptr(ws), stream_ptr()))
     return outs

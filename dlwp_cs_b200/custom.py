@@ -208,21 +208,18 @@ class CubeSphereConv2D(nn.modules.lazy.LazyModuleMixin, nn.Module):
         fused = self._fused_act is not None
         kernels = (self.equatorial_kernel, self.polar_kernel, self.north_pole_kernel)
         biases = (self.equatorial_bias, self.polar_bias, self.north_pole_bias)
-        pad_in, pad_out = (-x.shape[-1]) % 8, (-self.filters) % 8
-        if x.dtype == torch.bfloat16 and (pad_in or pad_out):
+        pad_in = pad_out = 0
+        if x.dtype == torch.bfloat16:
             # bf16 tensor-core path: 16-byte gathers / stores need channel counts that are multiples of 8 -- zero input
-            # channels with zero weights and zero-weight output channels leave the result unchanged (autograd slices
-            # the gradients back)
-            fpad = torch.nn.functional.pad
+            # channels with zero weights and zero-weight output channels leave the result unchanged (the operator pads
+            # the packed weights only; the parameters and their gradients keep their shape)
+            pad_in, pad_out = (-x.shape[-1]) % 8, (-self.filters) % 8
             if pad_in:
-                x = fpad(x, (0, pad_in))
-            kernels = tuple(None if w is None else fpad(w, (0, pad_out, 0, pad_in)) for w in kernels)
-            if pad_out:
-                biases = tuple(None if b is None else fpad(b, (0, pad_out)) for b in biases)
+                x = torch.nn.functional.pad(x, (0, pad_in))
         y = F_cs.cube_sphere_conv2d(x, kernels[0], kernels[1], kernels[2], biases[0], biases[1], biases[2], self.strides,
                                     self.padding, self.dilation_rate, self.flip_north_pole, self.fuse_padding,
-                                    self.activation if fused else None)
-        if x.dtype == torch.bfloat16 and pad_out:
+                                    self.activation if fused else None, pad_in=pad_in, pad_out=pad_out)
+        if pad_out:
             y = y[..., :self.filters]
         y = _from_channels_last(y, self.data_format)
         if not fused:

@@ -51,28 +51,57 @@ def cube_sphere_pad(x, p):
     return _CubeSpherePad.apply(x, int(p))
 
 
+# Gradient sink (set by the data-parallel trainer): an object with ``views(params)`` -> the six destination tensors for the
+# weight / bias gradients of a layer whose parameter tensors are `params` (or None if it does not own them) and
+# ``delivered(params)``.  With a sink the weight gradients are written straight into the trainer's flat gradient buffer by
+# the wgrad kernel's second pass -- no per-parameter ``.grad`` tensors, no accumulation or gather kernels -- and the trainer
+# learns when a layer's gradients are complete (to start their all-reduce while backward continues).
+_GRAD_SINK = None
+
+
+def set_grad_sink(sink):
+    global _GRAD_SINK
+    prev, _GRAD_SINK = _GRAD_SINK, sink
+    return prev
+
+
+def _pad_w(w, pad_in, pad_out):
+    return w if (w is None or not (pad_in or pad_out)) else torch.nn.functional.pad(w, (0, pad_out, 0, pad_in))
+
+
+def _pad_b(b, pad_out):
+    return b if (b is None or not pad_out) else torch.nn.functional.pad(b, (0, pad_out))
+
+
 class _CubeSphereConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w_eq, w_pol, w_np, b_eq, b_pol, b_np, cfg):
         x = x.contiguous()
         b, _, n, _, cin = x.shape
+        # zero-weight channel padding of the bf16 path (multiples of 8 channels for 16-byte gathers / stores) happens in
+        # here, on the packed copies only: x arrives padded, the parameters keep their shape
+        pad_in, pad_out = cfg.get('pad_in', 0), cfg.get('pad_out', 0)
         kh, kw, wcin, cout = w_eq.shape
-        if wcin != cin:
-            raise ValueError('input has %d channels, kernel expects %d' % (cin, wcin))
-        d = _lib.make_desc(b, n, cin, cout, (kh, kw), cfg['strides'], cfg['dilation'], cfg['halo'], cfg['same'],
+        if wcin + pad_in != cin:
+            raise ValueError('input has %d channels, kernel expects %d' % (cin, wcin + pad_in))
+        cout_p = cout + pad_out
+        d = _lib.make_desc(b, n, cin, cout_p, (kh, kw), cfg['strides'], cfg['dilation'], cfg['halo'], cfg['same'],
                            cfg['flip_north_pole'], w_np is not None, b_eq is not None, cfg['act'][0], cfg['act'][1],
                            cfg['act'][2], _lib.dtype_code(x.dtype), _lib.dtype_code(cfg.get('out_dtype', x.dtype)))
-        packed = _lib.pack_weights(d, w_eq, w_pol, w_np, b_eq, b_pol, b_np)
+        packed = _lib.pack_weights(d, _pad_w(w_eq, pad_in, pad_out), _pad_w(w_pol, pad_in, pad_out),
+                                   _pad_w(w_np, pad_in, pad_out), _pad_b(b_eq, pad_out), _pad_b(b_pol, pad_out),
+                                   _pad_b(b_np, pad_out))
         y = _lib.conv2d_fwd(d, x, None, packed)
         ctx.d = d
-        ctx.has = (w_np is not None, b_eq is not None, b_np is not None)
-        ctx.save_for_backward(x, y, w_eq, w_pol, w_np)
+        ctx.pads = (pad_in, pad_out)
+        ctx.save_for_backward(x, y, w_eq, w_pol, w_np, b_eq, b_pol, b_np)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, w_eq, w_pol, w_np = ctx.saved_tensors
+        x, y, w_eq, w_pol, w_np, b_eq, b_pol, b_np = ctx.saved_tensors
         d = ctx.d
+        pad_in, pad_out = ctx.pads
         if d.x_dtype != d.y_dtype:
             raise _lib.DlwpcsError('backward needs the output dtype to equal the input dtype')
         dy = dy.contiguous()
@@ -84,17 +113,35 @@ class _CubeSphereConv(torch.autograd.Function):
             y = None
         dx = None
         if ctx.needs_input_grad[0]:
-            packed_t = _lib.pack_weights(d, w_eq, w_pol, w_np, transposed=True)
+            packed_t = _lib.pack_weights(d, _pad_w(w_eq, pad_in, pad_out), _pad_w(w_pol, pad_in, pad_out),
+                                         _pad_w(w_np, pad_in, pad_out), transposed=True)
             dx = _lib.conv2d_dgrad(d, dy, y, packed_t)
-        dw_eq = dw_pol = dw_np = db_eq = db_pol = db_np = None
+        grads = [None] * 6
         if any(ctx.needs_input_grad[1:7]):
-            dw_eq, dw_pol, dw_np, db_eq, db_pol, db_np = _lib.conv2d_wgrad(d, x, dy, y)
-        return dx, dw_eq, dw_pol, dw_np, db_eq, db_pol, db_np, None
+            params = (w_eq, w_pol, w_np, b_eq, b_pol, b_np)
+            sink = _GRAD_SINK
+            views = sink.views(params) if sink is not None else None
+            if views is not None and not (pad_in or pad_out):
+                _lib.conv2d_wgrad(d, x, dy, y, outs=views)          # second pass writes the flat buffer directly
+                sink.delivered(params)
+            else:
+                got = _lib.conv2d_wgrad(d, x, dy, y)
+                if pad_in or pad_out:                                # drop the pad channels' (exactly zero) gradients
+                    cin0, cout0 = w_eq.shape[2], w_eq.shape[3]
+                    got = tuple(None if g is None else (g[:, :, :cin0, :cout0] if g.dim() == 4 else g[:cout0]) for g in got)
+                if views is not None:
+                    for v, g in zip(views, got):
+                        if v is not None:
+                            v.copy_(g)
+                    sink.delivered(params)
+                else:
+                    grads = [g if (g is None or g.is_contiguous()) else g.contiguous() for g in got]
+        return (dx, *grads, None)
 
 
 def cube_sphere_conv2d(x, equatorial_kernel, polar_kernel, north_pole_kernel=None, equatorial_bias=None,
                        polar_bias=None, north_pole_bias=None, strides=(1, 1), padding='valid', dilation_rate=(1, 1),
-                       flip_north_pole=True, halo=0, activation=None, out_dtype=None):
+                       flip_north_pole=True, halo=0, activation=None, out_dtype=None, pad_in=0, pad_out=0):
     """
     CubeSphereConv2D.call on a channels_last tensor.  `halo` > 0 additionally performs CubeSpherePadding2D(halo) inside
     the kernel's load stage (x is then the un-padded tensor).  `activation`: None / 'linear' / 'relu' /
@@ -111,6 +158,9 @@ def cube_sphere_conv2d(x, equatorial_kernel, polar_kernel, north_pole_kernel=Non
                flip_north_pole=bool(flip_north_pole), act=act)
     if out_dtype is not None:
         cfg['out_dtype'] = out_dtype
+    # pad_in / pad_out: x carries pad_in extra zero channels and the result pad_out extra (exactly zero) channels; the
+    # kernels / biases are given un-padded and padded with zeros on their packed copies only
+    cfg['pad_in'], cfg['pad_out'] = int(pad_in), int(pad_out)
     return _CubeSphereConv.apply(x, equatorial_kernel, polar_kernel, north_pole_kernel, equatorial_bias, polar_bias,
                                  north_pole_bias, cfg)
 

@@ -45,13 +45,17 @@ class FlatBuffers(object):
             off += n
         self.params = params
 
-    def collect_grads(self):
+    def collect_grads(self, stop=None):
         """Gather freshly produced per-parameter gradients (``p.grad`` tensors that are not views of the flat buffer) into
         the flat buffer with one multi-tensor copy and re-point ``p.grad`` at the views.  Used by the trainer, which clears
         ``p.grad`` before backward so that autograd hands the gradients over instead of launching one accumulation kernel
-        per parameter."""
+        per parameter.  Parameters from index `stop` on are only re-pointed (their gradients were already copied -- and
+        may be in flight in a collective)."""
         src, dst = [], []
-        for p, v in zip(self.params, self.grad_views):
+        for i, (p, v) in enumerate(zip(self.params, self.grad_views)):
+            if stop is not None and i >= stop:
+                p.grad = v
+                continue
             if p.grad is None:
                 v.zero_()
             elif p.grad.data_ptr() != v.data_ptr():
@@ -64,12 +68,24 @@ class FlatBuffers(object):
     def zero_grad(self):
         self.grad.zero_()
 
-    def all_reduce(self, group=None):
-        """Sum the flat gradient buffer over the ranks: the path's single collective.  Returns the world size."""
+    def all_reduce(self, group=None, lo=0, hi=None):
+        """Sum the flat gradient buffer (or its element range [lo, hi)) over the ranks.  Returns the world size."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+            g = self.grad if (lo == 0 and hi is None) else self.grad[lo:hi]
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
             return dist.get_world_size(group)
         return 1
+
+    def bucket_split(self, min_fraction=0.3):
+        """(parameter index, element offset) where the tail of the flat buffer -- the parameters whose gradients a backward
+        pass produces FIRST (the last layers) -- holds at least `min_fraction` of all elements, cut at a parameter
+        boundary that is a multiple of 4 elements (16-byte aligned float32 ranges for the collective)."""
+        tail = 0
+        for i in range(len(self.sizes) - 1, 0, -1):
+            tail += self.sizes[i]
+            if tail >= min_fraction * self.count and (self.count - tail) % 4 == 0:
+                return i, self.count - tail
+        return 0, 0
 
     def broadcast_params(self, src=0, group=None):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -105,7 +121,8 @@ class DataParallelTrainer(object):
     shards are equal (the reference scales the batch by the GPU count: Azure/train_tf.py:166).
     """
 
-    def __init__(self, model, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, group=None, use_graph=True, distributed=True):
+    def __init__(self, model, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, group=None, use_graph=True, distributed=True,
+                 overlap=True):
         self.model = model
         self.distributed = bool(distributed)      # False: a single-rank step even inside an initialised process group
         self.use_graph = use_graph
@@ -122,6 +139,43 @@ class DataParallelTrainer(object):
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.flat.param.device)
         if self.distributed:
             self.flat.broadcast_params(group=group)
+        # Gradient sink: the layers' backward writes the weight gradients straight into the flat buffer (functional.py) and
+        # reports every delivered layer.  With world > 1 the flat buffer is cut in two buckets in reverse layer order: when
+        # the tail bucket (the decoder layers, whose wgrad runs first) is complete its all-reduce is forked onto a side
+        # stream -- inside the captured graph -- while the encoder's dgrad / wgrad kernels still run; the head bucket
+        # follows on the main stream after backward and Adam waits for both.
+        self._view_of = {p.data_ptr(): i for i, p in enumerate(self.flat.params)}
+        self._overlap = False
+        world = dist.get_world_size(group) if (self.distributed and dist.is_available() and dist.is_initialized()) else 1
+        if overlap and world > 1:
+            k, off = self.flat.bucket_split()
+            if k > 0:
+                self._overlap = True
+                self._bucket_k, self._bucket_off = k, off
+                self._side = torch.cuda.Stream(device=self.flat.param.device)
+        self._delivered = set()
+        self._bucket_fired = False
+        self._main = None
+
+    # ---- gradient sink protocol (dlwp_cs_b200.functional.set_grad_sink) --------------------------------------------------
+    def views(self, params):
+        idx = [None if p is None else self._view_of.get(p.data_ptr()) for p in params]
+        if any(p is not None and i is None for p, i in zip(params, idx)):
+            return None                              # not (all) parameters of this trainer's model
+        return tuple(None if i is None else self.flat.grad_views[i] for i in idx)
+
+    def delivered(self, params):
+        """Called from the layer's backward (autograd thread) once its weight gradients sit in the flat buffer."""
+        for p in params:
+            if p is not None:
+                self._delivered.add(self._view_of[p.data_ptr()])
+        if self._overlap and not self._bucket_fired and \
+                all(i in self._delivered for i in range(self._bucket_k, len(self.flat.params))):
+            self._bucket_fired = True
+            main = self._main          # the stream the step is enqueued on (the autograd thread may have another current)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self.flat.all_reduce(self.group, lo=self._bucket_off)
 
     # lr / beta1 / beta2 / eps are baked into the captured launches as scalars: changing one (a learning-rate schedule,
     # models_torch.py:297-298) drops the cached graphs so that the next step re-captures with the new value
@@ -144,23 +198,58 @@ class DataParallelTrainer(object):
         gc.collect()
         torch.cuda.synchronize(self.flat.param.device)
 
-    def forward_backward(self, x, target):
-        """Gradients of mean((model(x) - target)^2) accumulated into the flat buffer; returns the loss (device scalar)."""
-        self.loss.zero_()
-        for p in self.flat.params:          # every parameter is used exactly once: take the gradients, do not accumulate
+    def _backward_into_flat(self, outputs, grads):
+        """Backward with this trainer as the gradient sink; whatever autograd still hands over as ``p.grad`` (layers outside
+        the sink protocol) is gathered afterwards.  Returns True if the tail bucket's all-reduce is already in flight."""
+        from . import functional as F_cs
+        for p in self.flat.params:          # every parameter is used by one layer: take the gradients, do not accumulate
             p.grad = None
+        self._delivered.clear()
+        self._bucket_fired = False
+        self._main = torch.cuda.current_stream(self.flat.param.device)
+        prev = F_cs.set_grad_sink(self)
+        try:
+            torch.autograd.backward(outputs, grads)
+        finally:
+            F_cs.set_grad_sink(prev)
+        src, dst = [], []
+        for i, (p, v) in enumerate(zip(self.flat.params, self.flat.grad_views)):
+            if i not in self._delivered:
+                if p.grad is None:
+                    v.zero_()
+                elif p.grad.data_ptr() != v.data_ptr():
+                    if self._bucket_fired and i >= self._bucket_k:
+                        raise _lib.DlwpcsError('gradient of a tail-bucket parameter arrived after its all-reduce started')
+                    src.append(p.grad)
+                    dst.append(v)
+            p.grad = v
+        if src:
+            torch._foreach_copy_(dst, src)
+        return self._bucket_fired
+
+    def forward_backward(self, x, target):
+        """Gradients of mean((model(x) - target)^2) in the flat buffer; returns the loss (device scalar)."""
+        self.loss.zero_()
         y = self.model(x)
         dy = _lib.mse_loss_grad(y.detach(), target, self.loss)
-        y.backward(dy)
-        self.flat.collect_grads()
+        self._tail_in_flight = self._backward_into_flat([y], [dy])
         return self.loss
 
-    def _step_body(self, x, target):
-        loss = self.forward_backward(x, target)
-        world = self.flat.all_reduce(self.group) if self.distributed else 1
+    def _reduce_and_update(self):
+        world = 1
+        if self.distributed:
+            if self._tail_in_flight:
+                world = self.flat.all_reduce(self.group, lo=0, hi=self._bucket_off)
+                self._main.wait_stream(self._side)
+            else:
+                world = self.flat.all_reduce(self.group)
         # the step counter lives on the device (incremented by the call), so the same launches serve every step
         _lib.adam_step_dev(self.flat.param, self.flat.grad, self.m, self.v, self.lr, self.beta1, self.beta2, self.eps,
                            self.step_counter, 1.0 / world)
+
+    def _step_body(self, x, target):
+        loss = self.forward_backward(x, target)
+        self._reduce_and_update()
         return loss
 
     def _graphed(self, tag, tensors, body):
@@ -212,8 +301,6 @@ class DataParallelTrainer(object):
     def _sequence_body(self, t_in, n_var, n_steps, x, *rest):
         solars, targets = rest[:n_steps - 1], rest[n_steps - 1:]
         self.loss.zero_()
-        for p in self.flat.params:
-            p.grad = None
         ys, xin = [], x
         for s in range(n_steps):                 # the same layer objects (shared weights) at every step
             y = self.model(xin)
@@ -222,11 +309,14 @@ class DataParallelTrainer(object):
                 xin = repack_reference(y, solars[s], x, t_in, n_var)
         # keras multi-output loss: sum_s w_s * mse(y_s, t_s) with w_s = 1/S (train_cs.py:424-426)
         dys = [_lib.mse_loss_grad(y.detach(), t, self.loss, scale=1.0 / n_steps) for y, t in zip(ys, targets)]
+        # shared layers: every parameter receives one gradient per model step, so the sink (which overwrites) is bypassed
+        # and autograd accumulates them (train_cs.py:391-409 applies the same layer objects S times)
+        for p in self.flat.params:
+            p.grad = None
         torch.autograd.backward(ys, dys)
         self.flat.collect_grads()
-        world = self.flat.all_reduce(self.group) if self.distributed else 1
-        _lib.adam_step_dev(self.flat.param, self.flat.grad, self.m, self.v, self.lr, self.beta1, self.beta2, self.eps,
-                           self.step_counter, 1.0 / world)
+        self._tail_in_flight = False
+        self._reduce_and_update()
         return self.loss
 
     def step_sequence(self, x, solars, targets, t_in, n_var):

@@ -116,3 +116,21 @@ def test_flat_buffers_collect_grads_cpu():
         want = torch.zeros_like(p) if p is unused else next(it)
         assert torch.equal(fb.grad[off:off + n].view(p.shape), want)
         off += n
+
+
+def test_bucket_split_and_partial_collect():
+    """Two gradient buckets in reverse layer order (the tail of the flat buffer = the layers whose gradients backward
+    produces first); collect_grads(stop=k) copies the head only and re-points the tail."""
+    from dlwp_cs_b200.unet import CubeSphereUNet2
+    model = CubeSphereUNet2(18, 14, base=32)
+    flat = FlatBuffers(model)
+    k, off = flat.bucket_split()
+    names = [n for n, _ in model.named_parameters()]
+    assert names[k] == 'conv_2d_6_2.equatorial_kernel' and off == sum(flat.sizes[:k]) and off % 4 == 0
+    assert 0.3 <= (flat.count - off) / flat.count <= 0.5
+    for p in flat.params:
+        p.grad = torch.ones_like(p)                      # fresh tensors, not views of the flat buffer
+    flat.grad.zero_()
+    flat.collect_grads(stop=k)
+    assert float(flat.grad[:off].min()) == 1.0 and float(flat.grad[off:].abs().max()) == 0.0
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(flat.params, flat.grad_views))
