@@ -461,6 +461,21 @@ def main():
                                        'us_per_6h_step': round(1e3 * ms1 / args.rollout_steps, 1),
                                        'steps_per_s': round(args.rollout_steps / (ms1 * 1e-3), 1)}
         del e1
+        # float32 rollout (the reference's arithmetic): float32-accurate tensor-core path (split bf16 x3, float32 accumulation
+        # and storage) next to the CUDA-core float32 parity kernels; same ensemble, same number of steps
+        rec = {'config': 'C%d unet2 rollout in float32, %d members, %d steps' % (n_face, args.batch, args.rollout_steps)}
+        for key, tcflag, reps in (('tensor_core_split_bf16x3', True, 3), ('cuda_core_fp32', False, 1)):
+            ef = RolloutEngine(model, args.batch, n_face, args.rollout_steps, forcing_channels=C_FORC, dtype=torch.float32,
+                               tensor_cores=tcflag)
+            ef.load_inputs(h_state.float(), h_forcing.float())
+            msf = timed_rollout(ef, flush, reps, 1 if not tcflag else 2)
+            rec[key] = {'value': round(args.rollout_steps * args.batch / (msf * 1e-3), 1), 'unit': UNIT,
+                        'ms_per_rollout': round(msf, 2), 'launches_per_6h_step': ef.launches_per_step}
+            del ef
+            torch.cuda.empty_cache()
+        rec['note'] = ('tensor_core: dlwpcs_split3 + bf16 tcgen05 kernel over [hi|lo|hi] x [w_hi;w_hi;w_lo], ~2^-17 per product '
+                       '(tests/test_gpu_tc.py::test_tc32_*); cuda_core: conv_fp32_kernel, the strict 1e-5 parity path')
+        extra['rollout_fp32'] = rec
         if n_face == 48:
             # BASELINE configs[4]: C96, 12 variables x 2 time steps, 1000-step rollout, 16 members
             cp96, b96, st96 = 24, 16, 1000

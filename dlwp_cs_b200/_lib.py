@@ -79,6 +79,7 @@ def load():
         'dlwpcs_trace_read': (i32, [vp, i32, ctypes.POINTER(ctypes.c_int), i32]),
         'dlwpcs_conv2d_fwd_chained': (i32, [dp, vp, vp, vp, vp, ctypes.POINTER(Chain), vp]),
         'dlwpcs_chain_target': (ctypes.c_uint32, [dp]),
+        'dlwpcs_split3': (i32, [vp, i32, i32, vp, i32, vp, i32, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)          # AttributeError here == header and library out of sync
@@ -95,7 +96,7 @@ EXPORTED = ('dlwpcs_version', 'dlwpcs_last_error', 'dlwpcs_conv_out_edge', 'dlwp
             'dlwpcs_conv2d_wgrad', 'dlwpcs_act_fwd', 'dlwpcs_act_bwd', 'dlwpcs_conv2d_fwd_host',
             'dlwpcs_mse_loss_grad', 'dlwpcs_adam_step', 'dlwpcs_adam_step_dev', 'dlwpcs_insolation', 'dlwpcs_pool2',
             'dlwpcs_up2cat_fwd', 'dlwpcs_up2cat_bwd', 'dlwpcs_feed_gather', 'dlwpcs_trace_read',
-            'dlwpcs_conv2d_fwd_chained', 'dlwpcs_chain_target')
+            'dlwpcs_conv2d_fwd_chained', 'dlwpcs_chain_target', 'dlwpcs_split3')
 
 
 class DlwpcsError(RuntimeError):
@@ -212,6 +213,39 @@ def conv2d_fwd(d, x0, x1, packed, out=None):
     y = out if out is not None else torch.empty(shp, dtype=ydt, device=x0.device)
     check(load().dlwpcs_conv2d_fwd(ctypes.byref(d), ptr(x0), ptr(x1), ptr(packed), ptr(y), stream_ptr()))
     return y
+
+
+def split3(a, mode_a=SRC_SAME, b=None, out=None):
+    """float32 (B,6,na,na,Ca) [+ (B,6,n,n,Cb)] -> bf16 (B,6,n,n,3*(Ca+Cb)) in the [hi | lo | hi] layout of the float32-accurate
+    tensor-core convolution; `a` is resampled (2x2 mean / nearest up-sampling) in float32 first.  See include/dlwpcs.h."""
+    require_cuda(a, b, out)
+    if a.dtype != torch.float32 or (b is not None and b.dtype != torch.float32):
+        raise DlwpcsError('split3 takes float32 tensors')
+    a = a.contiguous()
+    b = None if b is None else b.contiguous()
+    bs, _, na, _, ca = a.shape
+    n = na if mode_a == SRC_SAME else (na // 2 if mode_a == SRC_POOL2 else na * 2)
+    cb = 0 if b is None else b.shape[-1]
+    if b is not None and (b.shape[0] != bs or b.shape[2] != n):
+        raise DlwpcsError('split3: second source %r does not match %d x %d faces of batch %d' % (tuple(b.shape), n, n, bs))
+    shape = (bs, 6, n, n, 3 * (ca + cb))
+    if out is None:
+        out = torch.empty(shape, dtype=torch.bfloat16, device=a.device)
+    elif tuple(out.shape) != shape or out.dtype != torch.bfloat16 or not out.is_contiguous():
+        raise DlwpcsError('split3: output buffer must be contiguous bfloat16 of shape %r' % (shape,))
+    check(load().dlwpcs_split3(ptr(a), ca, mode_a, ptr(b), cb, ptr(out), bs, n, stream_ptr()))
+    return out
+
+
+def split3_weights(w, cin_pad=0):
+    """HWIO float32 kernel (kh,kw,Cin,Cout) -> (kh,kw,3*(Cin+cin_pad),Cout) float32 holding [w_hi ; w_hi ; w_lo] along the
+    input-channel axis (all values bf16-representable), the weight side of the [hi | lo | hi] activation layout."""
+    w = w.detach().to(torch.float32)
+    if cin_pad:
+        w = torch.nn.functional.pad(w, (0, 0, 0, cin_pad))
+    hi = w.to(torch.bfloat16).to(torch.float32)
+    lo = (w - hi).to(torch.bfloat16).to(torch.float32)
+    return torch.cat([hi, hi, lo], dim=2).contiguous()
 
 
 def chain_target(d):

@@ -463,6 +463,65 @@ __global__ void up2cat_fwd_kernel(const uint4 *__restrict__ a, const uint4 *__re
   }
 }
 
+// float32 -> three-segment bf16 split for the float32-accurate tensor-core convolution (dlwpcs_split3): every value x is
+// written as hi = bf16(x) and lo = bf16(x - hi) in the channel layout [hi(C) | lo(C) | hi(C)], so that ONE bf16 GEMM with
+// the weights stacked as [w_hi ; w_hi ; w_lo] along K accumulates x_hi*w_hi + x_lo*w_hi + x_hi*w_lo in float32 (the
+// dropped x_lo*w_lo term is 2^-16 relative).  The resampling of the U-Net (2x2 mean / nearest up-sampling of source a,
+// concatenation with source b) is done here in float32, BEFORE the split.  One thread per pixel and 8 channels.
+__global__ void split3_kernel(const float *__restrict__ a, const float *__restrict__ b, uint4 *__restrict__ out, int n,
+                              int ca, int cb, int mode, long long total) {
+  const int C = ca + cb, vc = C >> 3, va = ca >> 3;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int v = (int)(i % vc);
+    long long q = i / vc;
+    const int c = (int)(q % n); q /= n;
+    const int r = (int)(q % n);
+    const long long bf = q / n;
+    float x[8];
+    if (v < va) {
+      if (mode == DLWPCS_SRC_POOL2) {
+        const int w2 = 2 * n;
+        const float *src = a + (((bf * w2 + 2 * r) * w2 + 2 * c) * (long long)ca + 8 * v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const float4 t0 = __ldg(reinterpret_cast<const float4 *>(src + ((long long)dy * w2 + dx) * ca));
+            const float4 t1 = __ldg(reinterpret_cast<const float4 *>(src + ((long long)dy * w2 + dx) * ca) + 1);
+            x[0] += t0.x; x[1] += t0.y; x[2] += t0.z; x[3] += t0.w; x[4] += t1.x; x[5] += t1.y; x[6] += t1.z; x[7] += t1.w;
+          }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] *= 0.25f;
+      } else {
+        const int h = mode == DLWPCS_SRC_UP2 ? n >> 1 : n;
+        const int rr = mode == DLWPCS_SRC_UP2 ? r >> 1 : r, cc = mode == DLWPCS_SRC_UP2 ? c >> 1 : c;
+        const float4 *src = reinterpret_cast<const float4 *>(a + (((bf * h + rr) * h + cc) * (long long)ca + 8 * v));
+        const float4 t0 = __ldg(src), t1 = __ldg(src + 1);
+        x[0] = t0.x; x[1] = t0.y; x[2] = t0.z; x[3] = t0.w; x[4] = t1.x; x[5] = t1.y; x[6] = t1.z; x[7] = t1.w;
+      }
+    } else {
+      const float4 *src = reinterpret_cast<const float4 *>(b + (((bf * n + r) * n + c) * (long long)cb + 8 * (v - va)));
+      const float4 t0 = __ldg(src), t1 = __ldg(src + 1);
+      x[0] = t0.x; x[1] = t0.y; x[2] = t0.z; x[3] = t0.w; x[4] = t1.x; x[5] = t1.y; x[6] = t1.z; x[7] = t1.w;
+    }
+    __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      hi[e] = __float2bfloat16_rn(x[e]);
+      lo[e] = __float2bfloat16_rn(x[e] - __bfloat162float(hi[e]));
+    }
+    uint4 *row = out + (((bf * n + r) * n + c) * 3LL * vc);
+    const uint4 h4 = *reinterpret_cast<const uint4 *>(hi);
+    row[v] = h4;
+    row[vc + v] = *reinterpret_cast<const uint4 *>(lo);
+    row[2 * vc + v] = h4;
+  }
+}
+
 // adjoint: da (BF, n/2, n/2, va) <- sum of the 2x2 blocks of dt[..., :va];  db (BF, n, n, vb) <- dt[..., va:]
 template <typename T>
 __global__ void up2cat_bwd_kernel(const uint4 *__restrict__ dt, uint4 *__restrict__ da, uint4 *__restrict__ db, int n,
@@ -718,6 +777,20 @@ int dlwpcs_up2cat_fwd(const void *a, const void *b, void *t, int batch, int n, i
   else
     up2cat_fwd_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>((const uint4 *)a, (const uint4 *)b, (uint4 *)t, n, va, vb,
                                                                             total);
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dlwpcs_split3(const float *a, int ca, int mode_a, const float *b, int cb, void *out, int batch, int n, void *stream) {
+  CS_CHECK(a && out && batch >= 0 && n > 0 && ca > 0 && cb >= 0 && (cb == 0 || b), "bad arguments to dlwpcs_split3");
+  CS_CHECK(ca % 8 == 0 && cb % 8 == 0, "dlwpcs_split3: channel counts must be multiples of 8 (got %d + %d)", ca, cb);
+  CS_CHECK(mode_a == DLWPCS_SRC_SAME || mode_a == DLWPCS_SRC_POOL2 || (mode_a == DLWPCS_SRC_UP2 && n % 2 == 0),
+           "dlwpcs_split3: bad sampling mode %d for face edge %d", mode_a, n);
+  CS_CHECK(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+           "dlwpcs_split3 needs 16-byte aligned tensors");
+  if (batch == 0) return 0;
+  const long long total = (long long)batch * 6 * n * n * ((ca + cb) / 8);
+  split3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, b, (uint4 *)out, n, ca, cb, mode_a, total);
   CS_CUDA(cudaGetLastError());
   return 0;
 }

@@ -419,24 +419,41 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 // second pass: fixed-order sum of the CTA partials of each (job, face group); un-flip / merge the north-pole share.
 // A block handles 32 consecutive outputs (lanes; consecutive output channels -> coalesced) with 8 warps that each add
 // every 8th CTA partial; the 8 slice sums are then added in slice order (deterministic).
+// V = 4: every thread sums four consecutive output channels with 16-byte loads (cout and the column block are multiples
+// of 4: one quarter of the load instructions for the same bytes -- the pass is a latency-bound sweep over L2); V = 1 for
+// odd channel counts.
+template <int V>
 __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float *__restrict__ ws, const float *__restrict__ ws_b,
                                                               float *dw_eq, float *dw_pol, float *dw_np, float *db_eq,
                                                               float *db_pol, float *db_np, int kh, int kw, int cin,
                                                               int cout, int flip, const WgPlan L) {
-  __shared__ float sh[3][8][32];
+  __shared__ float sh[3][8][32][V];
   const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const long long per = (long long)kh * kw * cin * cout;
-  const long long i = blockIdx.x * 32LL + o;
+  const long long i = (blockIdx.x * 32LL + o) * V;           // first of the V outputs of this thread
   const size_t cta_stride = (size_t)L.nacc * 128 * L.NJ;
   const int gfirst[3] = {0, L.ng[0], L.ng[0] + L.ng[1]};
-  float part[3] = {0.f, 0.f, 0.f};
-  int u = 0;
+  float part[3][V];
+#pragma unroll
+  for (int g = 0; g < 3; ++g)
+#pragma unroll
+    for (int e = 0; e < V; ++e) part[g][e] = 0.f;
+  auto accumulate = [&](const float *src, int n, size_t stride, float *acc) {
+    for (int c = sl; c < n; c += 8) {
+      if constexpr (V == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(src + (size_t)c * stride));
+        acc[0] += t.x; acc[1] += t.y; acc[2] += t.z; acc[3] += t.w;
+      } else {
+        acc[0] += src[(size_t)c * stride];
+      }
+    }
+  };
   if (i < per) {
     const int co = (int)(i % cout);
     long long r = i / cout;
     const int ci = (int)(r % cin); r /= cin;
     const int v = (int)(r % kw);
-    u = (int)(r / kw);
+    const int u = (int)(r / kw);
     const int cbk = ci / L.CinBlk, cil = ci - cbk * L.CinBlk;
     const int ngi = co / L.NJ, col = co - ngi * L.NJ;
     const int job = ngi * L.NCB + cbk;
@@ -445,44 +462,43 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float *__res
     for (int g = 0; g < 3; ++g) {
       const int uu = (g == 2 && flip) ? kh - 1 - u : u;              // packed kernel row that reads source row u
       const size_t off = ((size_t)(uu * L.MBu + mbu) * 128 + lane) * L.NJ + col;
-      const float *src = ws + (size_t)(job * L.nc + gfirst[g]) * cta_stride + off;
-      float acc = 0.f;
-      for (int c = sl; c < L.ng[g]; c += 8) acc += src[(size_t)c * cta_stride];
-      part[g] = acc;
+      accumulate(ws + (size_t)(job * L.nc + gfirst[g]) * cta_stride + off, L.ng[g], cta_stride, part[g]);
     }
   } else if (db_eq && i < per + cout) {
     const int co = (int)(i - per);
     const int ngi = co / L.NJ, col = co - ngi * L.NJ;
     const int job = ngi * L.NCB;
 #pragma unroll
-    for (int g = 0; g < 3; ++g) {
-      const float *src = ws_b + (size_t)(job * L.nc + gfirst[g]) * L.NJ + col;
-      float acc = 0.f;
-      for (int c = sl; c < L.ng[g]; c += 8) acc += src[(size_t)c * L.NJ];
-      part[g] = acc;
-    }
+    for (int g = 0; g < 3; ++g)
+      accumulate(ws_b + (size_t)(job * L.nc + gfirst[g]) * L.NJ + col, L.ng[g], (size_t)L.NJ, part[g]);
   }
 #pragma unroll
-  for (int g = 0; g < 3; ++g) sh[g][sl][o] = part[g];
+  for (int g = 0; g < 3; ++g)
+#pragma unroll
+    for (int e = 0; e < V; ++e) sh[g][sl][o][e] = part[g][e];
   __syncthreads();
   if (sl != 0) return;
-  float tot[3];
 #pragma unroll
-  for (int g = 0; g < 3; ++g) {
-    float acc = 0.f;
+  for (int e = 0; e < V; ++e) {
+    float tot[3];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc += sh[g][k][o];
-    tot[g] = acc;
-  }
-  if (i < per) {
-    dw_eq[i] = tot[0];
-    if (dw_np) { dw_pol[i] = tot[1]; dw_np[i] = tot[2]; }
-    else dw_pol[i] = tot[1] + tot[2];
-  } else if (db_eq && i < per + cout) {
-    const int co = (int)(i - per);
-    db_eq[co] = tot[0];
-    if (db_np) { db_pol[co] = tot[1]; db_np[co] = tot[2]; }
-    else db_pol[co] = tot[1] + tot[2];
+    for (int g = 0; g < 3; ++g) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc += sh[g][k][o][e];
+      tot[g] = acc;
+    }
+    const long long ie = i + e;
+    if (ie < per) {
+      dw_eq[ie] = tot[0];
+      if (dw_np) { dw_pol[ie] = tot[1]; dw_np[ie] = tot[2]; }
+      else dw_pol[ie] = tot[1] + tot[2];
+    } else if (db_eq && ie < per + cout) {
+      const int co = (int)(ie - per);
+      db_eq[co] = tot[0];
+      if (db_np) { db_pol[co] = tot[1]; db_np[co] = tot[2]; }
+      else db_pol[co] = tot[1] + tot[2];
+    }
   }
 }
 
@@ -665,11 +681,22 @@ int tc_conv_wgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, 
   CS_CUDA(cudaGetLastError());
   CS_CUDA(cudaGetLastError());
   const long long total = (long long)g.taps * d->cin * d->cout + d->cout;
-  wgrad_tc_reduce_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(
-      P.ws, P.ws_b, out->dw_eq, out->dw_pol, d->independent_north_pole ? out->dw_np : nullptr,
-      d->use_bias ? out->db_eq : nullptr, d->use_bias ? out->db_pol : nullptr,
-      (d->use_bias && d->independent_north_pole) ? out->db_np : nullptr, d->kh, d->kw, d->cin, d->cout,
-      d->flip_north_pole, L);
+  // four outputs per thread when every group of four consecutive outputs stays inside one column block and one row of
+  // the partials (cout, the column block and the bias offset `per` are multiples of 4) and the partials are 16-byte aligned
+  const bool vec4 = d->cout % 4 == 0 && L.NJ % 4 == 0 && (reinterpret_cast<uintptr_t>(P.ws) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(P.ws_b) & 15) == 0;
+  if (vec4)
+    wgrad_tc_reduce_kernel<4><<<(unsigned)((total + 127) / 128), 256, 0, st>>>(
+        P.ws, P.ws_b, out->dw_eq, out->dw_pol, d->independent_north_pole ? out->dw_np : nullptr,
+        d->use_bias ? out->db_eq : nullptr, d->use_bias ? out->db_pol : nullptr,
+        (d->use_bias && d->independent_north_pole) ? out->db_np : nullptr, d->kh, d->kw, d->cin, d->cout,
+        d->flip_north_pole, L);
+  else
+    wgrad_tc_reduce_kernel<1><<<(unsigned)((total + 31) / 32), 256, 0, st>>>(
+        P.ws, P.ws_b, out->dw_eq, out->dw_pol, d->independent_north_pole ? out->dw_np : nullptr,
+        d->use_bias ? out->db_eq : nullptr, d->use_bias ? out->db_pol : nullptr,
+        (d->use_bias && d->independent_north_pole) ? out->db_np : nullptr, d->kh, d->kw, d->cin, d->cout,
+        d->flip_north_pole, L);
   CS_CUDA(cudaGetLastError());
   return 0;
 }

@@ -165,6 +165,37 @@ def cube_sphere_conv2d(x, equatorial_kernel, polar_kernel, north_pole_kernel=Non
                                  north_pole_bias, cfg)
 
 
+def cube_sphere_conv2d_tc32(x, equatorial_kernel, polar_kernel, north_pole_kernel=None, equatorial_bias=None,
+                            polar_bias=None, north_pole_bias=None, dilation_rate=(1, 1), flip_north_pole=True, halo=0,
+                            activation=None, padding='valid'):
+    """
+    CubeSphereConv2D.call (stride 1) on float32 tensors with float32 ACCURACY on the tensor cores (forward only): x is split
+    into bf16 hi / lo parts laid out [hi | lo | hi] (dlwpcs_split3), the kernels into [w_hi ; w_hi ; w_lo], and the bf16
+    tcgen05 kernel accumulates x_hi*w_hi + x_lo*w_hi + x_hi*w_lo in float32 -- 16 mantissa bits per operand instead of the
+    8 of the plain bf16 path; the result is float32.  Channel counts are padded to multiples of 8 internally.
+    """
+    _check_cl(x)
+    if x.dtype != torch.float32:
+        raise ValueError('cube_sphere_conv2d_tc32 takes float32 tensors')
+    act = resolve_activation(activation)
+    if act is None:
+        raise ValueError('activation %r cannot be fused; apply it to the output instead' % (activation,))
+    b, _, n, _, cin = x.shape
+    kh, kw, wcin, cout = equatorial_kernel.shape
+    if wcin != cin:
+        raise ValueError('input has %d channels, kernel expects %d' % (cin, wcin))
+    pad_in = (-cin) % 8
+    xp = torch.nn.functional.pad(x, (0, pad_in)) if pad_in else x
+    xs = _lib.split3(xp)
+    indep = north_pole_kernel is not None
+    d = _lib.make_desc(b, n, 3 * (cin + pad_in), cout, (kh, kw), (1, 1), tuple(dilation_rate), int(halo),
+                       padding.lower() == 'same', bool(flip_north_pole), indep, equatorial_bias is not None, act[0], act[1],
+                       act[2], _lib.BF16, _lib.F32)
+    ws = [None if w is None else _lib.split3_weights(w, pad_in) for w in (equatorial_kernel, polar_kernel, north_pole_kernel)]
+    packed = _lib.pack_weights(d, ws[0], ws[1], ws[2], equatorial_bias, polar_bias, north_pole_bias)
+    return _lib.conv2d_fwd(d, xs, None, packed)
+
+
 class _Act(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, act):

@@ -64,10 +64,12 @@ class CubeSphereForecaster(object):
     (the plain rollout of models.py:248-302 feeds the output back unchanged; forced models go through
     ``RolloutEngine.set_solar`` / ``forcing=``).  predictors: float array ``(sample, C, 6, N, N)`` for
     data_format='channels_first' (the layout the reference's reshape assumes) or ``(sample, 6, N, N, C)``.
-    dtype: torch.float32 (1e-5 parity kernels) or torch.bfloat16 (tensor-core kernels).
+    dtype: torch.float32 (1e-5 parity: CUDA-core kernels, or with tensor_cores=True the float32-accurate split-bf16
+    tensor-core path) or torch.bfloat16 (tensor-core kernels, bf16-stored activations).
     """
 
-    def __init__(self, model, time_dim=1, data_format='channels_last', dtype=torch.float32, use_graph=True):
+    def __init__(self, model, time_dim=1, data_format='channels_last', dtype=torch.float32, use_graph=True,
+                 tensor_cores=False):
         if int(time_dim) < 1:
             raise ValueError("'time_dim' must be >= 1")
         if data_format not in ('channels_first', 'channels_last'):
@@ -78,6 +80,7 @@ class CubeSphereForecaster(object):
         self.data_format = data_format
         self.dtype = dtype
         self.use_graph = use_graph
+        self.tensor_cores = tensor_cores      # float32 tensors on the float32-accurate tensor-core path (RolloutEngine)
         self.is_recurrent = False
         self.is_convolutional = True
         self._engines = {}
@@ -112,7 +115,7 @@ class CubeSphereForecaster(object):
         key = (batch, n, steps, cf)
         if key not in self._engines:
             self._engines[key] = RolloutEngine(self.model, batch, n, steps, forcing_channels=cf, dtype=self.dtype,
-                                               use_graph=self.use_graph)
+                                               use_graph=self.use_graph, tensor_cores=self.tensor_cores)
         return self._engines[key]
 
     def repack(self):

@@ -80,12 +80,20 @@ class FlatBuffers(object):
         """(parameter index, element offset) where the tail of the flat buffer -- the parameters whose gradients a backward
         pass produces FIRST (the last layers) -- holds at least `min_fraction` of all elements, cut at a parameter
         boundary that is a multiple of 4 elements (16-byte aligned float32 ranges for the collective)."""
-        tail = 0
+        cuts = self.bucket_cuts((min_fraction,))
+        return cuts[0] if cuts else (0, 0)
+
+    def bucket_cuts(self, fractions=(0.3, 0.85)):
+        """Cut points [(parameter index, element offset), ...] walking the flat buffer from its END (reverse layer order =
+        the order in which backward completes the gradients): a cut is made when the elements behind it reach the next
+        cumulative fraction.  n cuts give n + 1 buckets; the head bucket (the first layers) is what is left."""
+        cuts, tail, want = [], 0, list(fractions)
         for i in range(len(self.sizes) - 1, 0, -1):
             tail += self.sizes[i]
-            if tail >= min_fraction * self.count and (self.count - tail) % 4 == 0:
-                return i, self.count - tail
-        return 0, 0
+            if want and tail >= want[0] * self.count and (self.count - tail) % 4 == 0:
+                cuts.append((i, self.count - tail))
+                want.pop(0)
+        return cuts
 
     def broadcast_params(self, src=0, group=None):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -147,14 +155,14 @@ class DataParallelTrainer(object):
         self._view_of = {p.data_ptr(): i for i, p in enumerate(self.flat.params)}
         self._overlap = False
         world = dist.get_world_size(group) if (self.distributed and dist.is_available() and dist.is_initialized()) else 1
+        self._cuts = []
         if overlap and world > 1:
-            k, off = self.flat.bucket_split()
-            if k > 0:
+            self._cuts = self.flat.bucket_cuts()         # [(k_A, off_A), (k_B, off_B)]: tail bucket first
+            if self._cuts:
                 self._overlap = True
-                self._bucket_k, self._bucket_off = k, off
                 self._side = torch.cuda.Stream(device=self.flat.param.device)
         self._delivered = set()
-        self._bucket_fired = False
+        self._fired = 0            # buckets (from the tail) whose all-reduce has been forked in this backward
         self._main = None
 
     # ---- gradient sink protocol (dlwp_cs_b200.functional.set_grad_sink) --------------------------------------------------
@@ -169,13 +177,16 @@ class DataParallelTrainer(object):
         for p in params:
             if p is not None:
                 self._delivered.add(self._view_of[p.data_ptr()])
-        if self._overlap and not self._bucket_fired and \
-                all(i in self._delivered for i in range(self._bucket_k, len(self.flat.params))):
-            self._bucket_fired = True
+        while self._overlap and self._fired < len(self._cuts):
+            k, off = self._cuts[self._fired]
+            k_hi, off_hi = (len(self.flat.params), self.flat.count) if self._fired == 0 else self._cuts[self._fired - 1]
+            if not all(i in self._delivered for i in range(k, k_hi)):
+                break
+            self._fired += 1
             main = self._main          # the stream the step is enqueued on (the autograd thread may have another current)
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
-                self.flat.all_reduce(self.group, lo=self._bucket_off)
+                self.flat.all_reduce(self.group, lo=off, hi=off_hi)
 
     # lr / beta1 / beta2 / eps are baked into the captured launches as scalars: changing one (a learning-rate schedule,
     # models_torch.py:297-298) drops the cached graphs so that the next step re-captures with the new value
@@ -200,12 +211,12 @@ class DataParallelTrainer(object):
 
     def _backward_into_flat(self, outputs, grads):
         """Backward with this trainer as the gradient sink; whatever autograd still hands over as ``p.grad`` (layers outside
-        the sink protocol) is gathered afterwards.  Returns True if the tail bucket's all-reduce is already in flight."""
+        the sink protocol) is gathered afterwards.  Returns the number of buckets whose all-reduce is already in flight."""
         from . import functional as F_cs
         for p in self.flat.params:          # every parameter is used by one layer: take the gradients, do not accumulate
             p.grad = None
         self._delivered.clear()
-        self._bucket_fired = False
+        self._fired = 0
         self._main = torch.cuda.current_stream(self.flat.param.device)
         prev = F_cs.set_grad_sink(self)
         try:
@@ -218,14 +229,14 @@ class DataParallelTrainer(object):
                 if p.grad is None:
                     v.zero_()
                 elif p.grad.data_ptr() != v.data_ptr():
-                    if self._bucket_fired and i >= self._bucket_k:
-                        raise _lib.DlwpcsError('gradient of a tail-bucket parameter arrived after its all-reduce started')
+                    if self._fired and i >= self._cuts[self._fired - 1][0]:
+                        raise _lib.DlwpcsError('gradient of a parameter arrived after the all-reduce of its bucket started')
                     src.append(p.grad)
                     dst.append(v)
             p.grad = v
         if src:
             torch._foreach_copy_(dst, src)
-        return self._bucket_fired
+        return self._fired
 
     def forward_backward(self, x, target):
         """Gradients of mean((model(x) - target)^2) in the flat buffer; returns the loss (device scalar)."""
@@ -238,8 +249,8 @@ class DataParallelTrainer(object):
     def _reduce_and_update(self):
         world = 1
         if self.distributed:
-            if self._tail_in_flight:
-                world = self.flat.all_reduce(self.group, lo=0, hi=self._bucket_off)
+            if self._tail_in_flight:           # the buckets behind this offset are being reduced on the side stream
+                world = self.flat.all_reduce(self.group, lo=0, hi=self._cuts[self._tail_in_flight - 1][1])
                 self._main.wait_stream(self._side)
             else:
                 world = self.flat.all_reduce(self.group)
@@ -315,7 +326,7 @@ class DataParallelTrainer(object):
             p.grad = None
         torch.autograd.backward(ys, dys)
         self.flat.collect_grads()
-        self._tail_in_flight = False
+        self._tail_in_flight = 0
         self._reduce_and_update()
         return self.loss
 

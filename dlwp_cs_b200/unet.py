@@ -258,7 +258,7 @@ class RolloutEngine(object):
     """
 
     def __init__(self, model, batch, n, steps, forcing_channels=0, dtype=torch.float32, use_graph=True,
-                 per_step_forcing=False, device=None, input_order=None, chain=None):
+                 per_step_forcing=False, device=None, input_order=None, chain=None, tensor_cores=False):
         if n % (1 << model.levels) != 0:
             raise ValueError('%s pools %d times: face edge must be divisible by %d' % (model.arch, model.levels, 1 << model.levels))
         self.model, self.batch, self.n, self.steps = model, batch, n, steps
@@ -283,6 +283,11 @@ class RolloutEngine(object):
             raise _lib.DlwpcsError('RolloutEngine needs the model on a CUDA device')
         self.use_graph = use_graph
         self.per_step_forcing = per_step_forcing
+        # tensor_cores=True with float32 tensors: the float32-ACCURATE tensor-core path.  Every layer becomes a float32
+        # split kernel (dlwpcs_split3: x -> [hi | lo | hi] bf16, with the pooling / up-sampling / concatenation done in
+        # float32) followed by one launch of the bf16 tcgen05 kernel over 3x the input channels against [w_hi; w_hi; w_lo],
+        # accumulating x_hi*w_hi + x_lo*w_hi + x_hi*w_lo in float32; activations stay float32 in HBM.
+        self.tc32 = bool(tensor_cores) and dtype == torch.float32
         dt = _lib.dtype_code(dtype)
         b, base = batch, model.base
         mk = lambda edge, c: torch.empty((b, 6, edge, edge, c), dtype=dtype, device=self.device)
@@ -313,15 +318,32 @@ class RolloutEngine(object):
             plan.append((st['name'], edge, s0, c0, m0, s1, c1, m1, st['dst']))
         S = _lib.SRC_SAME
         self.plan = []
+        self._split = {}           # tc32: layer name -> (mode of source 0, bf16 scratch view the conv reads)
+        scratch_elems = 0
         for name, edge, s0, c0, m0, s1, c1, m1, dst in plan:
             layer = getattr(model, name)
             k = layer.kernel_size
             fused = F_cs.resolve_activation(layer.activation)
             cout = self.cp_pad if dst == 'out' else layer.filters
-            d = _lib.make_desc(b, edge, c0 + c1, cout, k, (1, 1), (1, 1), layer.fuse_padding, False,
-                               layer.flip_north_pole, layer.independent_north_pole, layer.use_bias, fused[0], fused[1],
-                               fused[2], dt, dt, c0, m0, c1, m1)
+            if self.tc32:
+                if (c0 % 8) or (c1 % 8):
+                    raise _lib.DlwpcsError('the float32 tensor-core path needs channel counts that are multiples of 8 '
+                                           '(layer %s reads %d + %d)' % (name, c0, c1))
+                d = _lib.make_desc(b, edge, 3 * (c0 + c1), cout, k, (1, 1), (1, 1), layer.fuse_padding, False,
+                                   layer.flip_north_pole, layer.independent_north_pole, layer.use_bias, fused[0],
+                                   fused[1], fused[2], _lib.BF16, _lib.F32)
+                self._split[name] = (m0, (b, 6, edge, edge, 3 * (c0 + c1)))
+                scratch_elems = max(scratch_elems, b * 6 * edge * edge * 3 * (c0 + c1))
+            else:
+                d = _lib.make_desc(b, edge, c0 + c1, cout, k, (1, 1), (1, 1), layer.fuse_padding, False,
+                                   layer.flip_north_pole, layer.independent_north_pole, layer.use_bias, fused[0], fused[1],
+                                   fused[2], dt, dt, c0, m0, c1, m1)
             self.plan.append([name, d, s0, s1, dst, None])
+        if self.tc32:              # the layers run one after the other: one scratch buffer serves every split
+            scratch = torch.empty(scratch_elems, dtype=torch.bfloat16, device=self.device)
+            for name, (m0, shape) in list(self._split.items()):
+                numel = shape[0] * shape[1] * shape[2] * shape[3] * shape[4]
+                self._split[name] = (m0, scratch[:numel].view(shape))
         self.graph = None
         self.graph_host = None
         self.host_ring = None
@@ -358,6 +380,8 @@ class RolloutEngine(object):
             if item[4] == 'out':                # output channels: [prognostic | pad]
                 ws = [None if w is None else F.pad(w.detach(), (0, self.cp_pad - self.cp)) for w in ws]
                 bs = [None if v is None else F.pad(v.detach(), (0, self.cp_pad - self.cp)) for v in bs]
+            if self.tc32:           # [w_hi ; w_hi ; w_lo] along the input channels (see _lib.split3_weights)
+                ws = [None if w is None else _lib.split3_weights(w) for w in ws]
             item[5] = _lib.pack_weights(item[1], ws[0], ws[1], ws[2], bs[0], bs[1], bs[2])
         self.graph = None
         self.graph_host = None
@@ -371,7 +395,7 @@ class RolloutEngine(object):
 
     @property
     def launches_per_step(self):
-        return len(self.plan)
+        return len(self.plan) * (2 if self.tc32 else 1)
 
     def _src(self, key, t):
         if key is None:
@@ -428,6 +452,11 @@ class RolloutEngine(object):
         nl = len(self.plan)
         for i, (name, d, s0, s1, dst, packed) in enumerate(self.plan):
             out = self.ring[t] if dst == 'out' else self.buf[dst]
+            if self.tc32:
+                m0, xs = self._split[name]
+                _lib.split3(self._src(s0, t), m0, self._src(s1, t), out=xs)
+                _lib.conv2d_fwd(d, xs, None, packed, out=out)
+                continue
             if not self.chain:
                 _lib.conv2d_fwd(d, self._src(s0, t), self._src(s1, t), packed, out=out)
                 continue

@@ -162,6 +162,17 @@ int dlwpcs_feed_gather(const float *array, const float *insolation, const float 
  * device, runs pad(halo)+conv, copies y back; synchronous.                                                            */
 int dlwpcs_conv2d_fwd_host(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, const void *x_host, void *y_host);
 
+/* float32-accurate convolution on the tensor cores (the reference's arithmetic is float32: custom.py:928,947,968,979):
+ * a float32 activation x is split into hi = bf16(x), lo = bf16(x - hi) and laid out as [hi(C) | lo(C) | hi(C)] per pixel;
+ * with the weights stacked [w_hi ; w_hi ; w_lo] along the input-channel axis, ONE launch of the bf16 tensor-core kernel
+ * (dlwpcs_conv2d_fwd with x_dtype = BF16, y_dtype = F32, cin = 3C) accumulates x_hi*w_hi + x_lo*w_hi + x_hi*w_lo in float32
+ * in tensor memory -- 16 mantissa bits per operand, the dropped lo*lo term is 2^-16 relative.  dlwpcs_split3 produces that
+ * layout from float32 tensors and performs the U-Net's resampling (Azure/train_cs.py:197-198, 293, 299) in float32 before
+ * the split: source a (batch,6,na,na,ca) sampled with mode_a (DLWPCS_SRC_SAME: na = n, _POOL2: na = 2n, 2x2 mean, _UP2:
+ * na = n/2, nearest), optionally concatenated with b (batch,6,n,n,cb); out (batch,6,n,n,3*(ca+cb)) bf16.  ca, cb multiples
+ * of 8.                                                                                                                */
+int dlwpcs_split3(const float *a, int ca, int mode_a, const float *b, int cb, void *out, int batch, int n, void *stream);
+
 /* Chained launch of the forward convolution (bf16 tensor-core path) for back-to-back layers of a network (the layer
  * sequence of Azure/train_cs.py:233-388 inside the rollout loop of models.py:446-454): instead of waiting for the whole
  * previous kernel, every tile waits until the launch that produced its input has completed that SAMPLE, and tiles are

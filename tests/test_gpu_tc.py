@@ -371,3 +371,74 @@ def test_chained_launches_equal_stream_ordered_launches():
     host = eng.run_to_host(state.cpu().bfloat16().pin_memory(), forcing.cpu().bfloat16().pin_memory(), chunk=2)
     torch.cuda.synchronize()
     assert torch.equal(host, ref.cpu()) and not eng.chain_error
+
+
+# ---- float32-accurate tensor-core path (split bf16 x3: dlwpcs_split3 + [w_hi ; w_hi ; w_lo]) ---------------------------
+@pytest.mark.parametrize('n,cin,cout,k,halo,act,flip,indep', [
+    (48, 3, 3, 3, 1, False, True, False),          # BASELINE configs[0]
+    (12, 32, 32, 3, 1, True, True, False),
+    (24, 64, 32, 3, 1, True, True, False),
+    (12, 128, 64, 3, 1, True, True, False),
+    (8, 18, 32, 3, 1, True, False, True),
+    (16, 32, 14, 1, 0, False, True, False),
+    (12, 16, 24, 5, 2, False, True, False),
+])
+def test_tc32_conv_float32_accuracy(n, cin, cout, k, halo, act, flip, indep):
+    """float32 inputs, float32 weights against the float64 oracle -- on the tensor cores.  Each operand carries 16 mantissa
+    bits (hi + lo bf16) and the lo*lo term is dropped: ~2^-17 relative per product, i.e. <= 1e-5 of the output scale up to
+    K ~ 600 and ~1.6e-5 at the widest layer of the U-Net (K = 9 x 128), where the test allows 2.5e-5."""
+    from dlwp_cs_b200 import functional as F_cs
+    g = torch.Generator().manual_seed(n * 100 + cin)
+    x = torch.randn(2, 6, n, n, cin, generator=g)
+    nw = 3 if indep else 2
+    ws = [torch.randn(k, k, cin, cout, generator=g) * 0.2 for _ in range(nw)]
+    bs = [torch.randn(cout, generator=g) * 0.2 for _ in range(nw)]
+    dd = lambda t: None if t is None else t.double()
+    w_np, b_np = (ws[2], bs[2]) if indep else (None, None)
+    ref = O.cube_sphere_conv2d(O.cube_sphere_pad(x.double(), halo), dd(ws[0]), dd(ws[1]), dd(w_np), dd(bs[0]), dd(bs[1]),
+                               dd(b_np), flip_north_pole=flip)
+    if act:
+        ref = O.capped_leaky_relu(ref)
+    cu = lambda t: None if t is None else t.cuda()
+    y = F_cs.cube_sphere_conv2d_tc32(x.cuda(), cu(ws[0]), cu(ws[1]), cu(w_np), cu(bs[0]), cu(bs[1]), cu(b_np),
+                                     flip_north_pole=flip, halo=halo,
+                                     activation=('capped_leaky_relu', 0.1, 10.0) if act else None)
+    assert y.dtype == torch.float32 and tuple(y.shape) == tuple(ref.shape)
+    a, e = y.double().cpu().numpy(), ref.numpy()
+    scale = float(np.abs(e).max())
+    tol = 1e-5 if k * k * cin <= 600 else 2.5e-5
+    np.testing.assert_allclose(a, e, rtol=tol, atol=tol * scale)
+
+
+def test_tc32_cfg1_vs_reference_golden(golden_dir):
+    """BASELINE configs[0] against the outputs of the reference's OWN call() methods (tests/golden/padconv_cfg1.npz)."""
+    import os
+    from dlwp_cs_b200 import functional as F_cs
+    g = np.load(os.path.join(golden_dir, 'padconv_cfg1.npz'))
+    t = lambda k: torch.from_numpy(g[k]).float().cuda()
+    y = F_cs.cube_sphere_conv2d_tc32(t('x'), t('w_eq'), t('w_pol'), None, t('b_eq'), t('b_pol'), None, halo=1)
+    ref = g['y']
+    np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-5, atol=1e-5 * float(np.abs(ref).max()))
+
+
+def test_tc32_rollout_100_steps_c48():
+    """The float32-accurate tensor-core engine over the 100-step C48 rollout: every step within 1e-4 of the float64 oracle
+    (the CUDA-core float32 engine holds the same bound in tests/test_gpu_models.py), no growth along the rollout."""
+    from dlwp_cs_b200.unet import CubeSphereUNet2, RolloutEngine
+    n, cp, cf, batch, steps = 48, 14, 4, 2, 100
+    params = O.make_unet2_params(cp + cf, cp, base=32, seed=1)
+    model = CubeSphereUNet2(cp + cf, cp, base=32).cuda()
+    model.load_oracle_params(params)
+    g = torch.Generator().manual_seed(0)
+    state = torch.randn(batch, 6, n, n, cp, generator=g).clamp_(-5, 5)
+    forcing = torch.rand(batch, 6, n, n, cf, generator=g)
+    with torch.no_grad():
+        ref = O.rollout({k: v.double() for k, v in params.items()}, state.double(), forcing.double(), steps, exact=False)
+    eng = RolloutEngine(model, batch, n, steps, forcing_channels=cf, dtype=torch.float32, tensor_cores=True)
+    assert eng.tc32 and eng.launches_per_step == 22
+    got = eng.run(state.cuda(), forcing.cuda()).double().cpu()
+    torch.cuda.synchronize()
+    err = ((got - ref).abs().flatten(1).max(dim=1).values / ref.abs().flatten(1).max(dim=1).values).numpy()
+    print('tc32 rel err at steps 1,2,5,10,50,100:', [float('%.2e' % err[i]) for i in (0, 1, 4, 9, 49, 99)])
+    assert err.max() <= 1e-4, err.max()
+    assert err[50:].max() <= 2.0 * err[:5].max() + 1e-5

@@ -128,6 +128,9 @@ def test_bucket_split_and_partial_collect():
     names = [n for n, _ in model.named_parameters()]
     assert names[k] == 'conv_2d_6_2.equatorial_kernel' and off == sum(flat.sizes[:k]) and off % 4 == 0
     assert 0.3 <= (flat.count - off) / flat.count <= 0.5
+    cuts = flat.bucket_cuts()
+    assert cuts[0] == (k, off) and len(cuts) == 2 and names[cuts[1][0]] == 'conv_2d_2_2.equatorial_kernel'
+    assert cuts[1][1] == sum(flat.sizes[:cuts[1][0]]) and cuts[1][1] / flat.count < 0.15       # small exposed head bucket
     for p in flat.params:
         p.grad = torch.ones_like(p)                      # fresh tensors, not views of the flat buffer
     flat.grad.zero_()
