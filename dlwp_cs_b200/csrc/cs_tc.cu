@@ -705,7 +705,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     TC_TILE_LOOP(k) {
       const TileInfo T = decode_tile(tile, P.batch, L.tpf);
       const int MBc = min(L.MB, L.nmb - T.tf * L.MB);
-      const int q0 = T.tf * L.MB * 128;
       const int npix = MBc * 128 + L.haloExt;
       stamp(P, 1, k, lt == 0);
       mbar_wait(bar_pempty + 8 * si, pi ^ 1);
