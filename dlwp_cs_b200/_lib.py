@@ -80,6 +80,9 @@ def load():
         'dlwpcs_conv2d_fwd_chained': (i32, [dp, vp, vp, vp, vp, ctypes.POINTER(Chain), vp]),
         'dlwpcs_chain_target': (ctypes.c_uint32, [dp]),
         'dlwpcs_split3': (i32, [vp, i32, i32, vp, i32, vp, i32, i32, vp]),
+        'dlwpcs_pack_weights2': (i32, [dp, wp, i32, i32, vp, vp, vp]),
+        'dlwpcs_pad_bwd_act': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, i32, vp]),
+        'dlwpcs_conv2d_dgrad_act': (i32, [dp, vp, vp, vp, vp, vp, vp, i32, f32, f32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)          # AttributeError here == header and library out of sync
@@ -96,7 +99,8 @@ EXPORTED = ('dlwpcs_version', 'dlwpcs_last_error', 'dlwpcs_conv_out_edge', 'dlwp
             'dlwpcs_conv2d_wgrad', 'dlwpcs_act_fwd', 'dlwpcs_act_bwd', 'dlwpcs_conv2d_fwd_host',
             'dlwpcs_mse_loss_grad', 'dlwpcs_adam_step', 'dlwpcs_adam_step_dev', 'dlwpcs_insolation', 'dlwpcs_pool2',
             'dlwpcs_up2cat_fwd', 'dlwpcs_up2cat_bwd', 'dlwpcs_feed_gather', 'dlwpcs_trace_read',
-            'dlwpcs_conv2d_fwd_chained', 'dlwpcs_chain_target', 'dlwpcs_split3')
+            'dlwpcs_conv2d_fwd_chained', 'dlwpcs_chain_target', 'dlwpcs_split3',
+            'dlwpcs_pack_weights2', 'dlwpcs_pad_bwd_act', 'dlwpcs_conv2d_dgrad_act')
 
 
 class DlwpcsError(RuntimeError):
@@ -206,6 +210,29 @@ def pack_weights(d, w_eq, w_pol, w_np=None, b_eq=None, b_pol=None, b_np=None, tr
     return packed
 
 
+def pack_weights2(d, w_eq, w_pol, w_np=None, b_eq=None, b_pol=None, b_np=None, forward=True, transposed=True):
+    """bf16 path: (packed, packed_t) in one launch; the kernels may have fewer input / output channels than the descriptor
+    (they are zero-extended, see include/dlwpcs.h)."""
+    lib = load()
+    ws = [w_eq, w_pol, w_np, b_eq, b_pol, b_np]
+    require_cuda(*ws)
+    ws = [None if t is None else (t.detach() if (t.dtype == torch.float32 and t.is_contiguous())
+                                   else t.detach().to(torch.float32).contiguous()) for t in ws]
+    outs = []
+    for want, tr in ((forward, 0), (transposed, 1)):
+        if not want:
+            outs.append(None)
+            continue
+        nbytes = lib.dlwpcs_packed_weight_bytes(ctypes.byref(d), tr)
+        if nbytes < 0:
+            check(1)
+        outs.append(torch.empty(nbytes, dtype=torch.uint8, device=w_eq.device))
+    cw = ConvWeights(*[t.data_ptr() if t is not None else None for t in ws])
+    check(lib.dlwpcs_pack_weights2(ctypes.byref(d), ctypes.byref(cw), int(w_eq.shape[2]), int(w_eq.shape[3]), ptr(outs[0]),
+                                   ptr(outs[1]), stream_ptr()))
+    return outs[0], outs[1]
+
+
 def conv2d_fwd(d, x0, x1, packed, out=None):
     require_cuda(x0, x1, packed)
     shp = out_shape(d)
@@ -268,8 +295,10 @@ def conv2d_fwd_chained(d, x0, x1, packed, out, dep, dep_target, done, tile_count
     return out
 
 
-def conv2d_dgrad(d, dy, y, packed_t):
-    require_cuda(dy, y, packed_t)
+def conv2d_dgrad(d, dy, y, packed_t, x_in=None, in_act=None):
+    """in_act = (code, slope, max) with x_in = the layer's forward input: the result is dL/d(pre-activation of the layer
+    that produced x_in) (dlwpcs_conv2d_dgrad_act)."""
+    require_cuda(dy, y, packed_t, x_in)
     lib = load()
     nbytes = lib.dlwpcs_dgrad_workspace_bytes(ctypes.byref(d))
     if nbytes < 0:
@@ -277,7 +306,11 @@ def conv2d_dgrad(d, dy, y, packed_t):
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dy.device)
     dx = torch.empty((d.batch, 6, d.n, d.n, d.cin), dtype=torch.float32 if d.x_dtype == F32 else torch.bfloat16,
                      device=dy.device)
-    check(lib.dlwpcs_conv2d_dgrad(ctypes.byref(d), ptr(dy), ptr(y), ptr(packed_t), ptr(dx), ptr(ws), stream_ptr()))
+    if in_act is not None and in_act[0] != ACT_NONE:
+        check(lib.dlwpcs_conv2d_dgrad_act(ctypes.byref(d), ptr(dy), ptr(y), ptr(packed_t), ptr(dx), ptr(ws), ptr(x_in),
+                                          int(in_act[0]), float(in_act[1]), float(in_act[2]), stream_ptr()))
+    else:
+        check(lib.dlwpcs_conv2d_dgrad(ctypes.byref(d), ptr(dy), ptr(y), ptr(packed_t), ptr(dx), ptr(ws), stream_ptr()))
     return dx
 
 

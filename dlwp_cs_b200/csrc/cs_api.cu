@@ -217,10 +217,16 @@ __global__ void pad_bwd_kernel(const T *__restrict__ dy, T *__restrict__ dx, con
 
 // 16-byte version (channel count a multiple of 8 bf16 / 4 fp32): one thread sums one 16-byte chunk of a source pixel over
 // the padded positions that read it (1 interior, 2 edge, 3-5 corner: SURVEY.md appendix A), in the table's fixed order
+__device__ __forceinline__ float act_grad_from_y(float y, int act, float slope, float maxv);
+
+// mask_y (optional): the tensor whose halo exchange is being differentiated is the OUTPUT of an activated layer; the
+// gathered gradient is multiplied by that activation's derivative here, which saves the upstream layer's separate
+// act_bwd pass over the same tensor (dlwpcs_conv2d_dgrad_act)
 template <typename T>
 __global__ void pad_bwd_vec_kernel(const uint4 *__restrict__ dy, uint4 *__restrict__ dx,
                                    const int32_t *__restrict__ inv_start, const int32_t *__restrict__ inv_items, int npad,
-                                   int nsrc, int vpp, long long total) {
+                                   int nsrc, int vpp, long long total, const uint4 *__restrict__ mask_y, int act,
+                                   float slope, float maxv) {
   constexpr int E = 16 / sizeof(T);
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -230,7 +236,7 @@ __global__ void pad_bwd_vec_kernel(const uint4 *__restrict__ dy, uint4 *__restri
     const int sp = (int)(s % nsrc);
     const long long b = s / nsrc;
     const int k0 = __ldg(inv_start + sp), k1 = __ldg(inv_start + sp + 1);
-    if (k1 - k0 == 1) {                     // interior pixel: plain copy
+    if (k1 - k0 == 1 && !mask_y) {          // interior pixel: plain copy
       dx[i] = __ldg(dy + (b * npad + __ldg(inv_items + k0)) * vpp + v);
       continue;
     }
@@ -242,6 +248,12 @@ __global__ void pad_bwd_vec_kernel(const uint4 *__restrict__ dy, uint4 *__restri
       const T *t = reinterpret_cast<const T *>(&q);
 #pragma unroll
       for (int e = 0; e < E; ++e) acc[e] += to_f<T>(t[e]);
+    }
+    if (mask_y) {
+      const uint4 m = __ldg(mask_y + i);
+      const T *tm = reinterpret_cast<const T *>(&m);
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[e] *= act_grad_from_y(to_f<T>(tm[e]), act, slope, maxv);
     }
     uint4 o;
     T *t = reinterpret_cast<T *>(&o);
@@ -664,8 +676,14 @@ int dlwpcs_pad_fwd(const void *x, void *y, int batch, int n, int c, int p, int d
 }
 
 int dlwpcs_pad_bwd(const void *dy, void *dx, int batch, int n, int c, int p, int dtype, void *stream) {
+  return dlwpcs_pad_bwd_act(dy, nullptr, dx, batch, n, c, p, DLWPCS_ACT_NONE, 0.f, 0.f, dtype, stream);
+}
+
+int dlwpcs_pad_bwd_act(const void *dy, const void *y_in, void *dx, int batch, int n, int c, int p, int act, float slope,
+                       float maxv, int dtype, void *stream) {
   CS_CHECK(elem_size(dtype) != 0, "unsupported dtype %d", dtype);
   CS_CHECK(batch >= 0 && n > 0 && c > 0 && p >= 0 && p <= n, "bad arguments to dlwpcs_pad_bwd");
+  if (act == DLWPCS_ACT_NONE) y_in = nullptr;
   if (batch == 0) return 0;
   CS_CHECK(dy && dx, "null tensor pointer");
   const HaloTables *t = get_halo_tables(n, p);
@@ -674,15 +692,18 @@ int dlwpcs_pad_bwd(const void *dy, void *dx, int batch, int n, int c, int p, int
   const int H = n + 2 * p, npad = 6 * H * H, nsrc = 6 * n * n;
   const long long total = (long long)batch * nsrc * c;
   const int epv = 16 / (int)elem_size(dtype);       // elements per 16-byte chunk
-  if (c % epv == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
+  if (c % epv == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(y_in) & 15) == 0) {
     const int vpp = c / epv;
     const long long tv = total / epv;
     if (dtype == DLWPCS_F32)
       pad_bwd_vec_kernel<float><<<grid_for(tv, 256), 256, 0, st>>>((const uint4 *)dy, (uint4 *)dx, t->inv_start,
-                                                                     t->inv_items, npad, nsrc, vpp, tv);
+                                                                     t->inv_items, npad, nsrc, vpp, tv, (const uint4 *)y_in,
+                                                                     act, slope, maxv);
     else
       pad_bwd_vec_kernel<__nv_bfloat16><<<grid_for(tv, 256), 256, 0, st>>>((const uint4 *)dy, (uint4 *)dx, t->inv_start,
-                                                                             t->inv_items, npad, nsrc, vpp, tv);
+                                                                             t->inv_items, npad, nsrc, vpp, tv,
+                                                                             (const uint4 *)y_in, act, slope, maxv);
     CS_CUDA(cudaGetLastError());
     return 0;
   }
@@ -693,6 +714,7 @@ int dlwpcs_pad_bwd(const void *dy, void *dx, int batch, int n, int c, int p, int
     pad_bwd_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(
         (const __nv_bfloat16 *)dy, (__nv_bfloat16 *)dx, t->inv_start, t->inv_items, npad, nsrc, c, total);
   CS_CUDA(cudaGetLastError());
+  if (y_in) return dlwpcs_act_bwd(dx, y_in, dx, total, act, slope, maxv, dtype, stream);      // odd channel counts
   return 0;
 }
 
@@ -950,6 +972,18 @@ int dlwpcs_pack_weights(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w,
   return fp32_pack_weights(d, w, transposed, (float *)packed, (cudaStream_t)stream);
 }
 
+int dlwpcs_pack_weights2(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, int src_cin, int src_cout, void *packed,
+                         void *packed_t, void *stream) {
+  Geometry g;
+  if (int rc = check_common(d, &g)) return rc;
+  CS_CHECK(d->x_dtype == DLWPCS_BF16, "dlwpcs_pack_weights2 serves the bf16 tensor-core path");
+  CS_CHECK(w && w->w_eq && w->w_pol && (packed || packed_t), "null weights");
+  CS_CHECK(!d->independent_north_pole || w->w_np, "independent_north_pole needs w_np");
+  CS_CHECK(!packed || !d->use_bias || (w->b_eq && w->b_pol && (!d->independent_north_pole || w->b_np)),
+           "use_bias needs biases");
+  return tc_pack_weights2(d, g, w, src_cin, src_cout, packed, packed_t, (cudaStream_t)stream);
+}
+
 int dlwpcs_conv2d_fwd(const dlwpcs_conv_desc *d, const void *x0, const void *x1, const void *packed_w, void *y,
                       void *stream) {
   Geometry g;
@@ -1007,9 +1041,27 @@ int dlwpcs_conv2d_dgrad(const dlwpcs_conv_desc *d, const void *dy, const void *y
   CS_CHECK(dy && packed_w_t && dx && (d->halo == 0 || workspace), "null pointer");
   CS_CHECK(d->act == DLWPCS_ACT_NONE || y, "activation derivative needs the forward output y");
   if (d->batch == 0) return 0;
-  if (d->x_dtype == DLWPCS_BF16) return tc_conv_dgrad(d, g, dy, y, packed_w_t, dx, workspace, (cudaStream_t)stream);
+  if (d->x_dtype == DLWPCS_BF16)
+    return tc_conv_dgrad(d, g, dy, y, packed_w_t, dx, workspace, nullptr, DLWPCS_ACT_NONE, 0.f, 0.f, (cudaStream_t)stream);
   return fp32_conv_dgrad(d, g, (const float *)dy, (const float *)y, (const float *)packed_w_t, (float *)dx, workspace,
                          (cudaStream_t)stream);
+}
+
+int dlwpcs_conv2d_dgrad_act(const dlwpcs_conv_desc *d, const void *dy, const void *y, const void *packed_w_t, void *dx,
+                            void *workspace, const void *x_in, int in_act, float in_slope, float in_max, void *stream) {
+  Geometry g;
+  if (int rc = check_bwd(d, &g)) return rc;
+  CS_CHECK(in_act == DLWPCS_ACT_NONE || x_in, "the input activation's derivative needs the layer input x_in");
+  if (in_act == DLWPCS_ACT_NONE || d->batch == 0) return dlwpcs_conv2d_dgrad(d, dy, y, packed_w_t, dx, workspace, stream);
+  if (d->x_dtype == DLWPCS_BF16 && d->halo > 0) {
+    CS_CHECK(dy && packed_w_t && dx && workspace, "null pointer");
+    CS_CHECK(d->act == DLWPCS_ACT_NONE || y, "activation derivative needs the forward output y");
+    return tc_conv_dgrad(d, g, dy, y, packed_w_t, dx, workspace, x_in, in_act, in_slope, in_max, (cudaStream_t)stream);
+  }
+  // no halo scatter-add to fuse into (1x1 layers) or the float32 kernels: plain dgrad, then the mask in place
+  if (int rc = dlwpcs_conv2d_dgrad(d, dy, y, packed_w_t, dx, workspace, stream)) return rc;
+  return dlwpcs_act_bwd(dx, x_in, dx, (int64_t)d->batch * 6 * d->n * d->n * d->cin, in_act, in_slope, in_max, d->x_dtype,
+                        stream);
 }
 
 int64_t dlwpcs_wgrad_workspace_bytes(const dlwpcs_conv_desc *d) {

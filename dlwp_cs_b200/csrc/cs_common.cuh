@@ -72,12 +72,14 @@ int64_t fp32_wgrad_workspace_bytes(const dlwpcs_conv_desc *d, const Geometry &g)
 int64_t tc_packed_weight_bytes(const dlwpcs_conv_desc *d, const Geometry &g, int transposed);
 int tc_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, int transposed,
                     void *packed, cudaStream_t st);
+int tc_pack_weights2(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, int src_cin,
+                     int src_cout, void *packed, void *packed_t, cudaStream_t st);
 int tc_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed,
                 void *y, const dlwpcs_chain *chain, cudaStream_t st);
 uint32_t tc_chain_target(const dlwpcs_conv_desc *d, const Geometry &g);
 bool tc_supported(const dlwpcs_conv_desc *d, const Geometry &g, const char **why);
 int tc_conv_dgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *dy, const void *y, const void *packed_t,
-                  void *dx, void *workspace, cudaStream_t st);
+                  void *dx, void *workspace, const void *x_in, int in_act, float in_slope, float in_max, cudaStream_t st);
 
 int tc_trace_read(unsigned long long *host_out, int max_launches, int *n_launches, int reset);
 

@@ -821,11 +821,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 // ---- weight packing -----------------------------------------------------------------------------------------------
 // packed[g][kc][tap][k8][n][8] bf16  (+ fp32 bias[3][CoutP] after the three groups).  transposed (dgrad): the GEMM's
 // K runs over the forward cout, N over the forward cin, taps rotated 180 degrees.
+// One launch packs the forward image (blockIdx.y = 0) and / or the transposed one (blockIdx.y = 1).  The source kernels
+// have the logical shape (kh, kw, scin, scout) and are zero-extended to the descriptor's (cin, cout): the bf16 path's
+// channel padding never materialises padded copies of the parameters.
+struct PackSide {
+  uint8_t *out;
+  int CinP, CoutP, KC;
+  long long groupElems;
+};
 __global__ void pack_tc_kernel(const float *__restrict__ w_eq, const float *__restrict__ w_pol,
                                const float *__restrict__ w_np, const float *__restrict__ b_eq,
-                               const float *__restrict__ b_pol, const float *__restrict__ b_np, uint8_t *__restrict__ out,
-                               int kh, int kw, int cin, int cout, int flip, int transposed, int CinP, int CoutP, int KC,
-                               long long groupElems) {
+                               const float *__restrict__ b_pol, const float *__restrict__ b_np, PackSide fwd, PackSide tr,
+                               int kh, int kw, int cin, int cout, int scin, int scout, int flip, int first_side) {
+  const int transposed = first_side + (int)blockIdx.y;
+  const PackSide S = transposed ? tr : fwd;
+  const long long groupElems = S.groupElems;
+  const int CoutP = S.CoutP, KC = S.KC;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int taps = kh * kw;
   if (i < 3 * groupElems) {
@@ -845,14 +856,14 @@ __global__ void pack_tc_kernel(const float *__restrict__ w_eq, const float *__re
       if (transposed) { u = kh - 1 - u; v = kw - 1 - v; }
       const int us = (g == 2 && flip) ? kh - 1 - u : u;
       const int ci = transposed ? n : k, co = transposed ? k : n;
-      val = src[(((long long)us * kw + v) * cin + ci) * cout + co];
+      if (ci < scin && co < scout) val = src[(((long long)us * kw + v) * scin + ci) * scout + co];
     }
-    reinterpret_cast<__nv_bfloat16 *>(out)[i] = __float2bfloat16_rn(val);
+    reinterpret_cast<__nv_bfloat16 *>(S.out)[i] = __float2bfloat16_rn(val);
   } else if (i < 3 * groupElems + 3LL * CoutP) {
     const int j = (int)(i - 3 * groupElems), g = j / CoutP, co = j % CoutP;
     const float *src = g == 0 ? b_eq : (g == 1 ? b_pol : (b_np ? b_np : b_pol));
-    float *bo = reinterpret_cast<float *>(out + 3 * groupElems * 2);
-    bo[j] = (src && !transposed && co < cout) ? src[co] : 0.f;
+    float *bo = reinterpret_cast<float *>(S.out + 3 * groupElems * 2);
+    bo[j] = (src && !transposed && co < scout) ? src[co] : 0.f;
   }
 }
 
@@ -1133,20 +1144,37 @@ int64_t tc_packed_weight_bytes(const dlwpcs_conv_desc *d, const Geometry &g, int
   return 3 * L.groupBytes + 3LL * L.CoutP * 4;
 }
 
-int tc_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, int transposed,
-                    void *packed, cudaStream_t st) {
-  TcPlan L;
-  const char *r = make_plan(d, g, transposed ? d->cout : d->cin, transposed ? d->cin : d->cout, &L);
-  CS_CHECK(r == nullptr, "bf16 tensor-core path does not support this configuration: %s", r);
-  const long long groupElems = L.groupBytes / 2;
-  const long long total = 3 * groupElems + 3LL * L.CoutP;
-  pack_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+int tc_pack_weights2(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, int src_cin,
+                     int src_cout, void *packed, void *packed_t, cudaStream_t st) {
+  CS_CHECK(packed || packed_t, "nothing to pack");
+  CS_CHECK(src_cin >= 1 && src_cin <= d->cin && src_cout >= 1 && src_cout <= d->cout,
+           "source kernel shape (%d, %d) does not fit the descriptor's (%d, %d)", src_cin, src_cout, d->cin, d->cout);
+  PackSide side[2];
+  long long total = 0;
+  for (int t = 0; t < 2; ++t) {
+    TcPlan L;
+    const char *r = make_plan(d, g, t ? d->cout : d->cin, t ? d->cin : d->cout, &L);
+    CS_CHECK(r == nullptr || !(t ? packed_t : packed), "bf16 tensor-core path does not support this configuration: %s", r);
+    side[t].out = (uint8_t *)(t ? packed_t : packed);
+    side[t].CinP = L.CinP; side[t].CoutP = L.CoutP; side[t].KC = L.KC;
+    side[t].groupElems = L.groupBytes / 2;
+    if (t ? packed_t : packed) {
+      const long long n = 3 * side[t].groupElems + 3LL * L.CoutP;
+      total = n > total ? n : total;
+    }
+  }
+  const int first = packed ? 0 : 1, count = (packed && packed_t) ? 2 : 1;
+  pack_tc_kernel<<<dim3((unsigned)((total + 255) / 256), (unsigned)count), 256, 0, st>>>(
       w->w_eq, w->w_pol, d->independent_north_pole ? w->w_np : nullptr, d->use_bias ? w->b_eq : nullptr,
-      d->use_bias ? w->b_pol : nullptr, (d->use_bias && d->independent_north_pole) ? w->b_np : nullptr,
-      (uint8_t *)packed, d->kh, d->kw, d->cin, d->cout, d->flip_north_pole, transposed, L.CinP, L.CoutP, L.KC,
-      groupElems);
+      d->use_bias ? w->b_pol : nullptr, (d->use_bias && d->independent_north_pole) ? w->b_np : nullptr, side[0], side[1],
+      d->kh, d->kw, d->cin, d->cout, src_cin, src_cout, d->flip_north_pole, first);
   CS_CUDA(cudaGetLastError());
   return 0;
+}
+
+int tc_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, int transposed,
+                    void *packed, cudaStream_t st) {
+  return tc_pack_weights2(d, g, w, d->cin, d->cout, transposed ? nullptr : packed, transposed ? packed : nullptr, st);
 }
 
 uint32_t tc_chain_target(const dlwpcs_conv_desc *d, const Geometry &g) {
@@ -1203,7 +1231,7 @@ int tc_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, co
 // over dy (scaled by the activation derivative taken from the forward output) with the taps rotated 180 degrees and the
 // channels swapped (weights packed with transposed = 1), zero fill outside dy, followed by the adjoint of the halo gather.
 int tc_conv_dgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *dy, const void *y, const void *packed_t,
-                  void *dx, void *workspace, cudaStream_t st) {
+                  void *dx, void *workspace, const void *x_in, int in_act, float in_slope, float in_max, cudaStream_t st) {
   dlwpcs_conv_desc dd = *d;
   dd.cin = d->cout; dd.cout = d->cin; dd.c0 = d->cout; dd.c1 = 0;
   dd.mode0 = dd.mode1 = DLWPCS_SRC_SAME;
@@ -1240,7 +1268,8 @@ int tc_conv_dgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *dy, 
   P.act = DLWPCS_ACT_NONE;
   L.vec = (d->cout % 8 == 0) && aligned16(dy) && (!P.mask_y || aligned16(y));
   if (int rc = launch_tc(P, st)) return rc;
-  if (d->halo > 0) return dlwpcs_pad_bwd(workspace, dx, d->batch, d->n, d->cin, d->halo, DLWPCS_BF16, st);
+  if (d->halo > 0)
+    return dlwpcs_pad_bwd_act(workspace, x_in, dx, d->batch, d->n, d->cin, d->halo, in_act, in_slope, in_max, DLWPCS_BF16, st);
   return 0;
 }
 

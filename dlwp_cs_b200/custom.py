@@ -185,7 +185,7 @@ class CubeSphereConv2D(nn.modules.lazy.LazyModuleMixin, nn.Module):
                 p.materialize((self.filters,))
                 _initialize(p.data, self.bias_initializer)
 
-    def initialize_parameters(self, inputs):          # LazyModuleMixin hook, first call only
+    def initialize_parameters(self, inputs, **_):     # LazyModuleMixin hook, first call only
         if self.has_uninitialized_params():
             ch_axis = 1 if self.data_format == 'channels_first' else -1
             if inputs.dim() != self.rank + 2:
@@ -203,7 +203,9 @@ class CubeSphereConv2D(nn.modules.lazy.LazyModuleMixin, nn.Module):
                 if getattr(self, nm) is not None:
                     _initialize(getattr(self, nm).data, self.bias_initializer)
 
-    def forward(self, inputs):
+    def forward(self, inputs, in_act=None, dy_premasked=False):
+        """in_act / dy_premasked (used by CubeSphereCNN between directly chained layers, see functional.cube_sphere_conv2d):
+        fuse the previous layer's activation derivative into this layer's input gradient."""
         x = _to_channels_last(inputs, self.data_format)
         fused = self._fused_act is not None
         kernels = (self.equatorial_kernel, self.polar_kernel, self.north_pole_kernel)
@@ -218,7 +220,9 @@ class CubeSphereConv2D(nn.modules.lazy.LazyModuleMixin, nn.Module):
                 x = torch.nn.functional.pad(x, (0, pad_in))
         y = F_cs.cube_sphere_conv2d(x, kernels[0], kernels[1], kernels[2], biases[0], biases[1], biases[2], self.strides,
                                     self.padding, self.dilation_rate, self.flip_north_pole, self.fuse_padding,
-                                    self.activation if fused else None, pad_in=pad_in, pad_out=pad_out)
+                                    self.activation if fused else None, pad_in=pad_in, pad_out=pad_out,
+                                    in_act=in_act if not pad_in else None,
+                                    dy_premasked=dy_premasked and fused)
         if pad_out:
             y = y[..., :self.filters]
         y = _from_channels_last(y, self.data_format)

@@ -88,12 +88,21 @@ class _CubeSphereConv(torch.autograd.Function):
         d = _lib.make_desc(b, n, cin, cout_p, (kh, kw), cfg['strides'], cfg['dilation'], cfg['halo'], cfg['same'],
                            cfg['flip_north_pole'], w_np is not None, b_eq is not None, cfg['act'][0], cfg['act'][1],
                            cfg['act'][2], _lib.dtype_code(x.dtype), _lib.dtype_code(cfg.get('out_dtype', x.dtype)))
-        packed = _lib.pack_weights(d, _pad_w(w_eq, pad_in, pad_out), _pad_w(w_pol, pad_in, pad_out),
-                                   _pad_w(w_np, pad_in, pad_out), _pad_b(b_eq, pad_out), _pad_b(b_pol, pad_out),
-                                   _pad_b(b_np, pad_out))
+        ctx.packed_t = None
+        if d.x_dtype == _lib.BF16:
+            # one launch packs the forward image and -- when the input needs a gradient -- the transposed one for dgrad;
+            # the kernels are zero-extended to the padded channel counts inside the pack kernel
+            packed, ctx.packed_t = _lib.pack_weights2(d, w_eq, w_pol, w_np, b_eq, b_pol, b_np, forward=True,
+                                                      transposed=bool(ctx.needs_input_grad[0]))
+        else:
+            packed = _lib.pack_weights(d, _pad_w(w_eq, pad_in, pad_out), _pad_w(w_pol, pad_in, pad_out),
+                                       _pad_w(w_np, pad_in, pad_out), _pad_b(b_eq, pad_out), _pad_b(b_pol, pad_out),
+                                       _pad_b(b_np, pad_out))
         y = _lib.conv2d_fwd(d, x, None, packed)
         ctx.d = d
         ctx.pads = (pad_in, pad_out)
+        ctx.in_act = cfg.get('in_act')
+        ctx.dy_premasked = bool(cfg.get('dy_premasked', False))
         ctx.save_for_backward(x, y, w_eq, w_pol, w_np, b_eq, b_pol, b_np)
         return y
 
@@ -105,7 +114,11 @@ class _CubeSphereConv(torch.autograd.Function):
         if d.x_dtype != d.y_dtype:
             raise _lib.DlwpcsError('backward needs the output dtype to equal the input dtype')
         dy = dy.contiguous()
-        if d.act != _lib.ACT_NONE and d.x_dtype == _lib.BF16:
+        if ctx.dy_premasked:
+            # the consumer's dgrad already multiplied by this layer's activation derivative (dlwpcs_conv2d_dgrad_act)
+            d = _lib.copy_desc(d, act=_lib.ACT_NONE)
+            y = None
+        elif d.act != _lib.ACT_NONE and d.x_dtype == _lib.BF16:
             # bf16 path: the activation derivative is applied once (dgrad and wgrad both need dy * act'(y)); both kernels
             # then stream the product with plain asynchronous 16-byte copies instead of masking in registers
             dy = _lib.act_bwd(dy, y, d.act, d.act_slope, d.act_max)
@@ -113,9 +126,13 @@ class _CubeSphereConv(torch.autograd.Function):
             y = None
         dx = None
         if ctx.needs_input_grad[0]:
-            packed_t = _lib.pack_weights(d, _pad_w(w_eq, pad_in, pad_out), _pad_w(w_pol, pad_in, pad_out),
-                                         _pad_w(w_np, pad_in, pad_out), transposed=True)
-            dx = _lib.conv2d_dgrad(d, dy, y, packed_t)
+            packed_t = ctx.packed_t
+            if packed_t is None:
+                packed_t = _lib.pack_weights(d, _pad_w(w_eq, pad_in, pad_out), _pad_w(w_pol, pad_in, pad_out),
+                                             _pad_w(w_np, pad_in, pad_out), transposed=True)
+            # in_act: x is the output of an activated layer that nothing else reads -- hand that layer
+            # dL/d(pre-activation) directly (the mask is applied inside the halo scatter-add)
+            dx = _lib.conv2d_dgrad(d, dy, y, packed_t, x_in=x, in_act=ctx.in_act)
         grads = [None] * 6
         if any(ctx.needs_input_grad[1:7]):
             params = (w_eq, w_pol, w_np, b_eq, b_pol, b_np)
@@ -141,7 +158,8 @@ class _CubeSphereConv(torch.autograd.Function):
 
 def cube_sphere_conv2d(x, equatorial_kernel, polar_kernel, north_pole_kernel=None, equatorial_bias=None,
                        polar_bias=None, north_pole_bias=None, strides=(1, 1), padding='valid', dilation_rate=(1, 1),
-                       flip_north_pole=True, halo=0, activation=None, out_dtype=None, pad_in=0, pad_out=0):
+                       flip_north_pole=True, halo=0, activation=None, out_dtype=None, pad_in=0, pad_out=0, in_act=None,
+                       dy_premasked=False):
     """
     CubeSphereConv2D.call on a channels_last tensor.  `halo` > 0 additionally performs CubeSpherePadding2D(halo) inside
     the kernel's load stage (x is then the un-padded tensor).  `activation`: None / 'linear' / 'relu' /
@@ -161,6 +179,14 @@ def cube_sphere_conv2d(x, equatorial_kernel, polar_kernel, north_pole_kernel=Non
     # pad_in / pad_out: x carries pad_in extra zero channels and the result pad_out extra (exactly zero) channels; the
     # kernels / biases are given un-padded and padded with zeros on their packed copies only
     cfg['pad_in'], cfg['pad_out'] = int(pad_in), int(pad_out)
+    # in_act / dy_premasked: the producer / consumer halves of the fused activation backward (used by CubeSphereCNN for
+    # directly chained layers): the consumer (in_act = the producer's activation) returns dL/d(pre-activation of the
+    # producer) as its input gradient, the producer (dy_premasked) skips its own derivative
+    if in_act is not None:
+        cfg['in_act'] = resolve_activation(in_act)
+        if pad_in:
+            raise ValueError('in_act cannot be combined with channel padding of the input')
+    cfg['dy_premasked'] = bool(dy_premasked)
     return _CubeSphereConv.apply(x, equatorial_kernel, polar_kernel, north_pole_kernel, equatorial_bias, polar_bias,
                                  north_pole_bias, cfg)
 

@@ -134,6 +134,20 @@ class CubeSphereCNN(nn.Module):
         self.independent_north_pole = independent_north_pole
         self.program = arch_program(arch, in_channels, out_channels, base)
         self.levels = max(s['level'] for s in self.program)
+        # directly chained pairs (consumer reads only the producer's output, un-resampled, and nothing else reads it): the
+        # producer's activation derivative is fused into the consumer's input gradient (dlwpcs_conv2d_dgrad_act)
+        readers = {}
+        for s in self.program:
+            for tag, _, _ in s['sources']:
+                readers[tag] = readers.get(tag, 0) + 1
+        by_name = {s['name']: s for s in self.program}
+        self._fuse_in, self._premasked = {}, set()
+        for s in self.program:
+            if len(s['sources']) == 1:
+                tag, _, mode = s['sources'][0]
+                if tag != 'input' and mode == 'same' and readers[tag] == 1 and by_name[tag]['act']:
+                    self._fuse_in[s['name']] = RELU
+                    self._premasked.add(tag)
         for s in self.program:
             last = s['name'] == 'conv_2d_8'
             setattr(self, s['name'], CubeSphereConv2D(
@@ -168,7 +182,8 @@ class CubeSphereCNN(nn.Module):
                 t = pool(t)
             elif m0 == 'up':
                 t = _upsample(t)
-            vals[s['name']] = getattr(self, s['name'])(t)
+            vals[s['name']] = getattr(self, s['name'])(t, in_act=self._fuse_in.get(s['name']),
+                                                       dy_premasked=s['name'] in self._premasked)
         return vals['conv_2d_8']
 
     # ---- weight interop with the reference's Keras model ----------------------------------------

@@ -72,6 +72,10 @@ int dlwpcs_pad_fwd(const void *x, void *y, int batch, int n, int c, int p, int d
 /* Its adjoint (TF autodiff of the slices/concats): dx[src] = sum of dy over every padded position reading src.
  * Deterministic gather over the inverse table (no float atomics).                                                     */
 int dlwpcs_pad_bwd(const void *dy, void *dx, int batch, int n, int c, int p, int dtype, void *stream);
+/* The same adjoint followed by the derivative of the activation that produced the un-padded tensor (y_in = that tensor,
+ * i.e. the forward input of the halo exchange): dx = scatter_add(dy) * act'(y_in).                                     */
+int dlwpcs_pad_bwd_act(const void *dy, const void *y_in, void *dx, int batch, int n, int c, int p, int act, float slope,
+                       float maxv, int dtype, void *stream);
 
 /* Weight packing: HWIO float32 -> the per-face-group layouts the kernels read.  `packed` must hold
  * dlwpcs_packed_weight_bytes(desc, transposed) bytes.  transposed = 0: forward; 1: dgrad (taps rotated 180 degrees,
@@ -80,6 +84,11 @@ int dlwpcs_pad_bwd(const void *dy, void *dx, int batch, int n, int c, int p, int
 int64_t dlwpcs_packed_weight_bytes(const dlwpcs_conv_desc *d, int transposed);
 int dlwpcs_pack_weights(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, int transposed, void *packed,
                         void *stream);
+/* bf16 path: forward and transposed (dgrad) images in ONE launch (either pointer may be NULL), from kernels of the logical
+ * shape (kh, kw, src_cin, src_cout) zero-extended to the descriptor's (cin, cout) -- the channel padding of the bf16 path
+ * (multiples of 8 for 16-byte gathers) then needs no padded copies of the parameters.                                  */
+int dlwpcs_pack_weights2(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, int src_cin, int src_cout, void *packed,
+                         void *packed_t, void *stream);
 
 /* CubeSphereConv2D.call (+ optional fused padding / sampling / bias / activation).
  *   x0, x1 : the input source(s), dtype d->x_dtype;   y : (B,6,Hout,Wout,cout), dtype d->y_dtype.                     */
@@ -94,6 +103,12 @@ int dlwpcs_conv2d_fwd(const dlwpcs_conv_desc *d, const void *x0, const void *x1,
 int64_t dlwpcs_dgrad_workspace_bytes(const dlwpcs_conv_desc *d);
 int dlwpcs_conv2d_dgrad(const dlwpcs_conv_desc *d, const void *dy, const void *y, const void *packed_w_t, void *dx,
                         void *workspace, void *stream);
+/* dgrad whose result is additionally multiplied by the derivative of the activation that produced the layer's INPUT
+ * (x_in = forward input of this layer = output of the previous ReLU(0.1, 10) layer, Azure/train_cs.py:199): the mask is
+ * applied inside the halo scatter-add, so the previous layer's backward receives dL/d(pre-activation) directly and needs
+ * no pass of its own over the tensor.  in_act = DLWPCS_ACT_NONE: identical to dlwpcs_conv2d_dgrad.                     */
+int dlwpcs_conv2d_dgrad_act(const dlwpcs_conv_desc *d, const void *dy, const void *y, const void *packed_w_t, void *dx,
+                            void *workspace, const void *x_in, int in_act, float in_slope, float in_max, void *stream);
 int64_t dlwpcs_wgrad_workspace_bytes(const dlwpcs_conv_desc *d);
 typedef struct dlwpcs_conv_wgrads {
   float *dw_eq, *dw_pol, *dw_np;

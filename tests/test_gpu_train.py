@@ -174,3 +174,45 @@ def test_trainer_hyperparameter_change_recaptures(lib):
     assert not torch.equal(tr.flat.param, p0)
     tr.close()
     assert not tr._graphs
+
+
+def test_pack_weights2_equals_separate_packs(lib):
+    """One launch for the forward and the transposed image; kernels zero-extended to the padded channel counts == packing
+    explicitly padded copies."""
+    g = torch.Generator().manual_seed(3)
+    cin, cout, cinp, coutp = 18, 14, 24, 16
+    ws = [torch.randn(3, 3, cin, cout, generator=g).cuda() for _ in range(3)]
+    bs = [torch.randn(cout, generator=g).cuda() for _ in range(3)]
+    d = lib.make_desc(2, 8, cinp, coutp, (3, 3), halo=1, independent_north_pole=True, x_dtype=lib.BF16, y_dtype=lib.BF16)
+    fpad = torch.nn.functional.pad
+    wp = [fpad(w, (0, coutp - cout, 0, cinp - cin)) for w in ws]
+    bp = [fpad(b, (0, coutp - cout)) for b in bs]
+    ref_f = lib.pack_weights(d, wp[0], wp[1], wp[2], bp[0], bp[1], bp[2])
+    ref_t = lib.pack_weights(d, wp[0], wp[1], wp[2], transposed=True)
+    got_f, got_t = lib.pack_weights2(d, ws[0], ws[1], ws[2], bs[0], bs[1], bs[2])
+    assert torch.equal(got_f, ref_f) and torch.equal(got_t, ref_t)
+    only_t = lib.pack_weights2(d, ws[0], ws[1], ws[2], forward=False)
+    assert only_t[0] is None and torch.equal(only_t[1], ref_t)
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize('halo,k', [(1, 3), (0, 1)])
+def test_dgrad_act_equals_dgrad_then_activation_derivative(lib, dtype, halo, k):
+    """dlwpcs_conv2d_dgrad_act: the mask of the activation that produced the layer's input, fused into the halo
+    scatter-add (bf16, halo > 0) or applied in place (1x1 layers / float32) == dgrad followed by dlwpcs_act_bwd."""
+    g = torch.Generator().manual_seed(5)
+    b, n, cin, cout = 2, 12, 32, 16
+    code = lib.dtype_code(dtype)
+    x = (torch.randn(b, 6, n, n, cin, generator=g) * 6).to(dtype).cuda()          # values on both sides of 0 and of the cap 10
+    dy = torch.randn(b, 6, n, n, cout, generator=g).to(dtype).cuda()
+    ws = [torch.randn(k, k, cin, cout, generator=g).cuda() * 0.2 for _ in range(2)]
+    d = lib.make_desc(b, n, cin, cout, (k, k), halo=halo, x_dtype=code, y_dtype=code)
+    packed_t = lib.pack_weights(d, ws[0], ws[1], transposed=True)
+    plain = lib.conv2d_dgrad(d, dy, None, packed_t)
+    ref = lib.act_bwd(plain, x, lib.ACT_CAPPED_LEAKY_RELU, 0.1, 10.0)
+    got = lib.conv2d_dgrad(d, dy, None, packed_t, x_in=x, in_act=(lib.ACT_CAPPED_LEAKY_RELU, 0.1, 10.0))
+    if dtype == torch.bfloat16 and halo > 0:
+        # fused: the mask multiplies the float32 sum before the single rounding; the reference rounds twice
+        np.testing.assert_allclose(got.float().cpu().numpy(), ref.float().cpu().numpy(), rtol=2.0 ** -7, atol=1e-6)
+    else:
+        assert torch.equal(got, ref)
