@@ -203,7 +203,7 @@ class CubeSphereConv2D(nn.modules.lazy.LazyModuleMixin, nn.Module):
                 if getattr(self, nm) is not None:
                     _initialize(getattr(self, nm).data, self.bias_initializer)
 
-    def forward(self, inputs, in_act=None, dy_premasked=False):
+    def forward(self, inputs, in_act=None, dy_premasked=False, keep_pad=False):
         """in_act / dy_premasked (used by CubeSphereCNN between directly chained layers, see functional.cube_sphere_conv2d):
         fuse the previous layer's activation derivative into this layer's input gradient."""
         x = _to_channels_last(inputs, self.data_format)
@@ -223,7 +223,7 @@ class CubeSphereConv2D(nn.modules.lazy.LazyModuleMixin, nn.Module):
                                     self.activation if fused else None, pad_in=pad_in, pad_out=pad_out,
                                     in_act=in_act if not pad_in else None,
                                     dy_premasked=dy_premasked and fused)
-        if pad_out:
+        if pad_out and not keep_pad:       # keep_pad: hand out the zero pad channels too (the trainer's loss ignores them)
             y = y[..., :self.filters]
         y = _from_channels_last(y, self.data_format)
         if not fused:

@@ -161,6 +161,8 @@ class DataParallelTrainer(object):
             if self._cuts:
                 self._overlap = True
                 self._side = torch.cuda.Stream(device=self.flat.param.device)
+        import inspect
+        self._keep_pad = 'keep_pad' in inspect.signature(model.forward).parameters
         self._delivered = set()
         self._fired = 0            # buckets (from the tail) whose all-reduce has been forked in this backward
         self._main = None
@@ -241,10 +243,24 @@ class DataParallelTrainer(object):
     def forward_backward(self, x, target):
         """Gradients of mean((model(x) - target)^2) in the flat buffer; returns the loss (device scalar)."""
         self.loss.zero_()
-        y = self.model(x)
-        dy = _lib.mse_loss_grad(y.detach(), target, self.loss)
+        y, target, scale = self._forward_padded(x, target)
+        dy = _lib.mse_loss_grad(y.detach(), target, self.loss, scale=scale)
         self._tail_in_flight = self._backward_into_flat([y], [dy])
         return self.loss
+
+    def _forward_padded(self, x, target):
+        """Forward pass; for a model that supports it the output keeps its zero pad channels (bf16: channel counts are
+        multiples of 8) and the target is zero-padded to match -- the pad channels contribute exactly zero to the squared
+        error, the mean is taken over the real element count through `scale`, and the slice / re-pad copies around the
+        loss disappear.  -> (y, target, loss scale)"""
+        if not self._keep_pad:
+            return self.model(x), target, 1.0
+        y = self.model(x, keep_pad=True)
+        extra = y.shape[-1] - target.shape[-1]
+        if extra == 0:
+            return y, target, 1.0
+        target = torch.nn.functional.pad(target, (0, extra))
+        return y, target, float(y.shape[-1]) / float(y.shape[-1] - extra)
 
     def _reduce_and_update(self):
         world = 1

@@ -162,7 +162,9 @@ class CubeSphereCNN(nn.Module):
     def layers_in_order(self):
         return [getattr(self, s['name']) for s in self.program]
 
-    def forward(self, x):
+    def forward(self, x, keep_pad=False):
+        """keep_pad (bf16 only): return the output layer's result with its zero pad channels (multiple of 8) instead of
+        slicing them off -- the data-parallel trainer computes the loss on the padded tensor and saves three copies."""
         # pooling / upsampling + concatenation: one 16-byte kernel each way when the channel counts allow it (they do for
         # every base that is a multiple of 8), torch ops otherwise
         def pool(t):
@@ -183,7 +185,8 @@ class CubeSphereCNN(nn.Module):
             elif m0 == 'up':
                 t = _upsample(t)
             vals[s['name']] = getattr(self, s['name'])(t, in_act=self._fuse_in.get(s['name']),
-                                                       dy_premasked=s['name'] in self._premasked)
+                                                       dy_premasked=s['name'] in self._premasked,
+                                                       keep_pad=keep_pad and s['name'] == 'conv_2d_8')
         return vals['conv_2d_8']
 
     # ---- weight interop with the reference's Keras model ----------------------------------------
