@@ -1,5 +1,7 @@
-"""Regenerate the tables of profiles/r1_tc_kernels.md and profiles/r1_traffic.json from the ncu artefacts in gpurun_out/
-(r1_tc_final.ncu-rep, r1_wgrad.ncu-rep, r1_launches.csv, r1_train_launches.csv).  Prints the four tables as markdown."""
+"""Regenerate the tables of profiles/r<N>_tc_kernels.md and profiles/r<N>_traffic.json from the ncu artefacts in gpurun_out/
+(r<N>_tc*.ncu-rep, [r<N>_wgrad.ncu-rep,] r<N>_launches.csv, r<N>_train_launches.csv).  Prints the tables as markdown.
+
+    python tools/make_profile_md.py [round, default 2]"""
 import collections, csv, json, os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, 'gpurun_out')
@@ -51,13 +53,18 @@ def shares(path, top=14):
 
 
 if __name__ == '__main__':
-    t1, tr = table(os.path.join(G, 'r1_tc_final.ncu-rep'), NAMES)
-    t2, _ = table(os.path.join(G, 'r1_wgrad.ncu-rep'), list(reversed(NAMES)))
-    json.dump({'source': 'profiles/r1_tc_kernels.md (ncu --set full, batch 64, C48, bf16)', 'batch': 64,
-               'dram_bytes_per_launch': tr}, open(os.path.join(ROOT, 'profiles', 'r1_traffic.json'), 'w'), indent=1)
-    for f in ('r1_launches.csv', 'r1_train_launches.csv'):
+    rnd = sys.argv[1] if len(sys.argv) > 1 else '2'
+    rep = os.path.join(G, 'r%s_tc.ncu-rep' % rnd)
+    if not os.path.exists(rep):
+        rep = os.path.join(G, 'r%s_tc_final.ncu-rep' % rnd)
+    t1, tr = table(rep, NAMES)
+    json.dump({'source': 'profiles/r%s_tc_kernels.md (ncu --set full, batch 64, C48, bf16)' % rnd, 'batch': 64,
+               'dram_bytes_per_launch': tr}, open(os.path.join(ROOT, 'profiles', 'r%s_traffic.json' % rnd), 'w'), indent=1)
+    for f in ('r%s_launches.csv' % rnd, 'r%s_train_launches.csv' % rnd):
         shutil.copy(os.path.join(G, f), os.path.join(ROOT, 'profiles', f))
-    print('## rollout launch list\n' + shares(os.path.join(G, 'r1_launches.csv')))
+    print('## rollout launch list\n' + shares(os.path.join(G, 'r%s_launches.csv' % rnd)))
     print('\n## forward kernel\n' + t1)
-    print('\n## training launch list\n' + shares(os.path.join(G, 'r1_train_launches.csv'), 22))
-    print('\n## wgrad kernel\n' + t2)
+    print('\n## training launch list\n' + shares(os.path.join(G, 'r%s_train_launches.csv' % rnd), 26))
+    wg = os.path.join(G, 'r%s_wgrad.ncu-rep' % rnd)
+    if os.path.exists(wg):
+        print('\n## wgrad kernel\n' + table(wg, list(reversed(NAMES)))[0])
