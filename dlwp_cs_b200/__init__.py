@@ -3,8 +3,10 @@ jweyn/DLWP-CS), hand-written sm_100a CUDA behind the reference's layer API.  See
 
     custom      CubeSpherePadding2D / CubeSphereConv2D with the reference's constructor and call signatures
     functional  the differentiable operators underneath (halo exchange, halo-fused convolution, pooling, upsample+concat)
-    unet        CubeSphereUNet2 (Weyn-2020 unet2), RolloutEngine (device-resident / forced / host-streamed rollout)
-    train       DataParallelTrainer (one flat NCCL all-reduce, fused Adam, CUDA-graph step, multi-step training)
+    unet        CubeSphereCNN (basic / unet / unet2 / unet3 / unet4), RolloutEngine (device-resident / forced / host-streamed)
+    models      CubeSphereForecaster: predict / predict_timeseries with the reference's arguments and array layout
+    h5weights   pure-Python HDF5 reader for the reference's saved Keras models
+    train       DataParallelTrainer (flat gradient buffer, bucketed all-reduce overlapped with backward, fused Adam, graph)
     feed        DeviceDataFeed (ArrayDataGenerator on the device)
 """
 from .custom import CubeSphereConv2D, CubeSpherePadding2D  # noqa: F401
