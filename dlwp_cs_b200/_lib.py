@@ -196,7 +196,8 @@ def out_shape(d):
 
 
 def pack_weights(d, w_eq, w_pol, w_np=None, b_eq=None, b_pol=None, b_np=None, transposed=False):
-    """HWIO float32 parameters -> the packed device buffer the kernels read (uint8 tensor)."""
+    """HWIO float32 parameters -> the packed device buffer the kernels read (uint8 tensor).  transposed: False / 0 forward
+    (for conv2d_fwd), True / 1 dgrad, 2 forward for conv2d_fwd_chained (see include/dlwpcs.h)."""
     lib = load()
     ws = [w_eq, w_pol, w_np, b_eq, b_pol, b_np]
     require_cuda(*ws)

@@ -957,7 +957,7 @@ int64_t dlwpcs_packed_weight_bytes(const dlwpcs_conv_desc *d, int transposed) {
   Geometry g;
   if (check_common(d, &g)) return -1;
   if (d->x_dtype == DLWPCS_BF16) return tc_packed_weight_bytes(d, g, transposed);
-  return fp32_packed_floats(d, transposed) * 4;
+  return fp32_packed_floats(d, transposed == 1) * 4;
 }
 
 int dlwpcs_pack_weights(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, int transposed, void *packed,
@@ -966,10 +966,10 @@ int dlwpcs_pack_weights(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w,
   if (int rc = check_common(d, &g)) return rc;
   CS_CHECK(w && packed && w->w_eq && w->w_pol, "null weights");
   CS_CHECK(!d->independent_north_pole || w->w_np, "independent_north_pole needs w_np");
-  CS_CHECK(transposed || !d->use_bias || (w->b_eq && w->b_pol && (!d->independent_north_pole || w->b_np)),
+  CS_CHECK(transposed == 1 || !d->use_bias || (w->b_eq && w->b_pol && (!d->independent_north_pole || w->b_np)),
            "use_bias needs biases");
   if (d->x_dtype == DLWPCS_BF16) return tc_pack_weights(d, g, w, transposed, packed, (cudaStream_t)stream);
-  return fp32_pack_weights(d, w, transposed, (float *)packed, (cudaStream_t)stream);
+  return fp32_pack_weights(d, w, transposed == 1, (float *)packed, (cudaStream_t)stream);
 }
 
 int dlwpcs_pack_weights2(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, int src_cin, int src_cout, void *packed,

@@ -400,7 +400,9 @@ class RolloutEngine(object):
                 bs = [None if v is None else F.pad(v.detach(), (0, self.cp_pad - self.cp)) for v in bs]
             if self.tc32:           # [w_hi ; w_hi ; w_lo] along the input channels (see _lib.split3_weights)
                 ws = [None if w is None else _lib.split3_weights(w) for w in ws]
-            item[5] = _lib.pack_weights(item[1], ws[0], ws[1], ws[2], bs[0], bs[1], bs[2])
+            # chained launches always run the classic kernel and need its weight image (mode 2)
+            item[5] = _lib.pack_weights(item[1], ws[0], ws[1], ws[2], bs[0], bs[1], bs[2],
+                                        transposed=2 if getattr(self, 'chain', False) else 0)
         self.graph = None
         self.graph_host = None
 
