@@ -78,10 +78,9 @@ int dlwpcs_pad_bwd_act(const void *dy, const void *y_in, void *dx, int batch, in
                        float maxv, int dtype, void *stream);
 
 /* Weight packing: HWIO float32 -> the per-face-group layouts the kernels read.  `packed` must hold
- * dlwpcs_packed_weight_bytes(desc, transposed) bytes.  transposed = 0: forward, in the layout of whichever kernel
- * dlwpcs_conv2d_fwd runs for the descriptor (bf16 layers with <= 32 output channels and 3 kernel columns go to the
- * narrow-layer kernel, whose image stacks the kernel columns along N); 1: dgrad (taps rotated 180 degrees, cin/cout
- * swapped); 2: forward for dlwpcs_conv2d_fwd_chained (always the classic kernel's image).  Group 0 = equatorial, 1 = south pole, 2 = north pole (polar or independent kernel, rows flipped
+ * dlwpcs_packed_weight_bytes(desc, transposed) bytes.  transposed = 0: forward; 1: dgrad (taps rotated 180 degrees,
+ * cin/cout swapped); 2: forward image for dlwpcs_conv2d_fwd_chained (the same image as 0 today; kept distinct so that a
+ * kernel variant with its own weight layout can be dispatched by dlwpcs_conv2d_fwd alone).  Group 0 = equatorial, 1 = south pole, 2 = north pole (polar or independent kernel, rows flipped
  * when flip_north_pole -- equivalent to custom.py:969/995 for every stride).                           */
 int64_t dlwpcs_packed_weight_bytes(const dlwpcs_conv_desc *d, int transposed);
 int dlwpcs_pack_weights(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, int transposed, void *packed,
