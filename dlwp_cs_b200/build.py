@@ -11,13 +11,13 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libdlwpcs.so')
-SOURCES = ['cs_api.cu', 'cs_fp32.cu', 'cs_tc.cu', 'cs_wgrad_tc.cu']
+SOURCES = ['cs_api.cu', 'cs_fp32.cu', 'cs_tc.cu', 'cs_tc_rs.cu', 'cs_wgrad_tc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O3', '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
 # --use_fast_math (flush-to-zero, approximate division / square root) only for the two bf16 tensor-core translation
 # units, whose arithmetic outside the tensor core is fmaf / fminf / fmaxf on values that are rounded to bf16 anyway.  The
 # float32 parity kernels, the Adam update (m / (sqrt(v) + eps)), the loss and the insolation are compiled IEEE.
-FAST_MATH = {'cs_tc.cu', 'cs_wgrad_tc.cu'}
+FAST_MATH = {'cs_tc.cu', 'cs_tc_rs.cu', 'cs_wgrad_tc.cu'}
 
 
 def _nvcc():

@@ -83,6 +83,16 @@ int tc_conv_dgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *dy, 
 
 int tc_trace_read(unsigned long long *host_out, int max_launches, int *n_launches, int reset);
 
+// row-streamed kernel (cs_tc_rs.cu): 3x3, stride 1, bf16 in / out, <= 64 input and <= 80 output channels; the three kernel
+// rows are stacked along N.  Its packed-weight image differs from the classic one; dlwpcs_conv2d_fwd uses it whenever
+// rs_eligible() says so (DLWPCS_RS=0 disables it).
+bool rs_eligible(const dlwpcs_conv_desc *d, const Geometry &g);
+int64_t rs_packed_weight_bytes(const dlwpcs_conv_desc *d, const Geometry &g);
+int rs_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, int src_cin, int src_cout,
+                    void *packed, cudaStream_t st);
+int rs_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed, void *y,
+                cudaStream_t st);
+
 // patch table of a linearised virtual face (width Wv, G entries per face): physical source pixel or -1; cached per device
 const int32_t *get_patch_table(const Geometry &g, int Wv, int G, int n, int halo, int mode);
 

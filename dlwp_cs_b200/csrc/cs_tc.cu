@@ -1135,7 +1135,10 @@ bool tc_supported(const dlwpcs_conv_desc *d, const Geometry &g, const char **why
 }
 
 int64_t tc_packed_weight_bytes(const dlwpcs_conv_desc *d, const Geometry &g, int transposed) {
-  if (transposed == 2) transposed = 0;        // 2 = forward image for chained launches: the same image today
+  // 0: forward image for dlwpcs_conv2d_fwd (the row-streamed kernel's where it applies), 1: transposed (dgrad),
+  // 2: forward image of the classic kernel whatever the layer (chained launches)
+  if (transposed == 0 && rs_eligible(d, g)) return rs_packed_weight_bytes(d, g);
+  if (transposed == 2) transposed = 0;
   TcPlan L;
   const char *r = make_plan(d, g, transposed ? d->cout : d->cin, transposed ? d->cin : d->cout, &L);
   if (r) {
@@ -1148,7 +1151,12 @@ int64_t tc_packed_weight_bytes(const dlwpcs_conv_desc *d, const Geometry &g, int
 int tc_pack_weights2(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, int src_cin,
                      int src_cout, void *packed, void *packed_t, cudaStream_t st, int classic_forward) {
   CS_CHECK(packed || packed_t, "nothing to pack");
-  (void)classic_forward;
+  if (packed && !classic_forward && rs_eligible(d, g)) {
+    // the forward image goes to the row-streamed kernel's layout; the transposed one (if any) stays classic
+    if (int rc = rs_pack_weights(d, g, w, src_cin, src_cout, packed, st)) return rc;
+    if (!packed_t) return 0;
+    packed = nullptr;
+  }
   CS_CHECK(src_cin >= 1 && src_cin <= d->cin && src_cout >= 1 && src_cout <= d->cout,
            "source kernel shape (%d, %d) does not fit the descriptor's (%d, %d)", src_cin, src_cout, d->cin, d->cout);
   PackSide side[2];
@@ -1188,6 +1196,7 @@ uint32_t tc_chain_target(const dlwpcs_conv_desc *d, const Geometry &g) {
 
 int tc_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed,
                 void *y, const dlwpcs_chain *chain, cudaStream_t st) {
+  if (!chain && rs_eligible(d, g)) return rs_conv_fwd(d, g, x0, x1, packed, y, st);
   TcP P;
   memset(&P, 0, sizeof(P));
   const char *r = make_plan(d, g, d->cin, d->cout, &P.pl_);

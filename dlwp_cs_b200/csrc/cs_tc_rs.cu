@@ -1,0 +1,665 @@
+// tcgen05 (sm_100a) bf16 implicit-GEMM kernel of the cubed-sphere convolution, ROW-STREAMED with the three kernel rows
+// stacked along N and the shift-add done by the tensor core itself ("slot ring").
+//
+// Why: an SS-mode tcgen05.mma re-reads its whole A tile from shared memory (tools/umma_probe.cu: M128 K16 costs
+// max(N/2, (4 KB + N*32 B)/128 B) cycles), so the classic kernel (cs_tc.cu: one M128 x N=Cout MMA per tap) is capped at 38 %
+// of the tensor peak for 32 output channels -- nine A reads per output block.  Here one MMA serves the three kernel rows:
+//
+//   geometry   the images (faces) of one weight group are concatenated ROW-WISE: position p = image * Wv + column over the
+//              zero/halo padded width Wv; a *strip* is 128 consecutive positions = the 128 TMEM lanes.  Lanes whose column
+//              is >= Wout (2 of every Wv) or past the last image are computed and dropped.
+//   A          one padded input row y of the strip: 130 positions x Cin, pixel-major with the UMMA 32/64/128-byte swizzle,
+//              gathered through the same patch tables as the classic kernel (halo exchange, pole rotation, pooling,
+//              up-sampling, concatenation); the kernel column v is a +v position offset of the A start address.
+//   B          per (K block, kernel column v): [W[2,v] | W[1,v] | W[0,v]] stacked along N (3 * CoutP columns).
+//   D          a ring of NS = 512 / CoutP accumulator *slots* in tensor memory, one per OUTPUT row.  The MMAs of input row
+//              y accumulate into the three adjacent slots of output rows y-2, y-1, y (kernel rows 2, 1, 0); the MMAs of row
+//              y+1 into y-1, y, y+1; ...  tcgen05.mma instructions execute in issue order also when their accumulator
+//              column ranges overlap only partially (tools/umma_ring_probe.cu, exact on the B200), so the vertical shift-add
+//              costs nothing: a third of the A reads, and the epilogue reads finished sums exactly as before.
+//              A slot is zeroed by one MMA against a zero B operand (accumulate = 0) right before its first real MMA.
+//   pipeline   loaders (8 warps, one input row per stage) -> MMA issuer (1 warp) -> slot ring -> epilogue (8 warps: bias,
+//              capped leaky ReLU, bf16, per-warp compaction in shared memory, coalesced stores), all mbarrier-driven; the
+//              weights of the CTA's face group stay resident in shared memory.
+//   work       every CTA gets a contiguous range of (strip, output row) pairs of equal length (cut at strip boundaries into
+//              units; a unit of h output rows streams h + 2 input rows).
+//
+// Reference semantics: DLWP/custom.py:921-1002 (CubeSphereConv2D.call) with the preceding CubeSpherePadding2D
+// (custom.py:1198-1308) and the U-Net's pool / upsample / concatenate (Azure/train_cs.py:197-199, 282-299) folded into the
+// load stage, bias + capped leaky ReLU in the epilogue.  Same products as cs_tc.cu; the float32 sums associate differently.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "cs_common.cuh"
+#include "cs_ptx.cuh"
+
+namespace dlwpcs {
+
+namespace {
+
+constexpr int RS_THREADS = 576, RS_LOADERS = 256, RS_EPI = 256;
+constexpr int RS_EPI_WARP0 = 8, RS_TMA_WARP = 16, RS_MMA_WARP = 17;
+constexpr int RS_MAXSLOTS = 16, RS_MAXSTAGES = 16;
+constexpr int RS_NPOS = 130;       // 128 lanes + (kw - 1) positions of overhang
+constexpr int RS_NPIXP = 136;      // rows of one stage (multiple of 8)
+constexpr int RS_KP = 5;           // positions per loader thread: ceil(130 / (256 / S)), S = CinP / 8 <= 8
+constexpr int RS_SMEM_CAP = 227 * 1024;
+
+struct RsPlan {
+  int CinP, KC16, S, logS, RB, cprLog, swzMask, layoutType;
+  int CoutP, NT, NS;                 // padded output channels, stacked N = 3 * CoutP, accumulator slots
+  int Wv, Hv, G;                     // padded face, patch-table entries per face
+  int stageBytes, RSn;               // bytes per input-row stage, stages
+  int unitBytes, groupBytes;         // weights of one (kernel column) unit / of one face group
+  int stgBytes;                      // output staging per epilogue warp
+  int off_w, off_zero, off_misc, off_bias, off_pix, off_stg, smemBytes;
+};
+
+struct RsP {
+  const __nv_bfloat16 *x0, *x1;
+  const int32_t *tab0, *tab1;        // [6][G] physical source pixel within one batch element, -1 = zero
+  const uint8_t *wpack;
+  const float *bias;                 // [3][CoutP]
+  __nv_bfloat16 *y;
+  int batch, n, Hout, Wout;
+  int cin, cout, c0, c1, mode0, mode1, ppb0, ppb1;
+  int act;
+  float slope, maxv;
+  int snap;                          // work cuts closer than this to a strip boundary are moved onto it
+  unsigned *err;                     // watchdog flag (a barrier wait that never completes traps instead of hanging the GPU)
+  RsPlan L;
+};
+
+// Bounded barrier wait: ~2^26 polls (seconds) then flag + trap.  A pipeline bug must not hang the GPU box.
+__device__ __forceinline__ void rs_wait(uint32_t bar, uint32_t parity, unsigned *err, int code) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; !done; ++it) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && it > (1u << 26)) {
+      if (err) atomicExch(err, (unsigned)code);
+      __trap();
+    }
+  }
+}
+// Warp-uniform variant for the MMA issuer: the loop lives in one opaque asm statement (a C++ spin loop makes the compiler
+// treat everything after it as divergent and the MMA descriptors leave the uniform registers, see cs_tc.cu).
+__device__ __forceinline__ void rs_wait_uniform(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+
+struct RsWork {
+  long long rho0, rho1;              // this CTA's range of global (strip, output row) indices
+  int ns0, ns1, ns2;                 // strips per face group
+};
+
+__device__ __forceinline__ long long rs_cut(long long c, long long R, int grid, int Hout, int snap) {
+  long long b = c * R / grid;
+  const int r = (int)(b % Hout);
+  if (r < snap) b -= r;
+  else if (r > Hout - snap) b += Hout - r;
+  return b;
+}
+
+struct RsUnit {
+  int grp, sl, y0, y1, Lg;           // face group, strip within the group, output rows [y0, y1), positions in the group
+};
+__device__ __forceinline__ RsUnit rs_unit(const RsWork &W, long long rho, int Hout, int batch, int Wv) {
+  RsUnit u;
+  const int s = (int)(rho / Hout);
+  u.y0 = (int)(rho - (long long)s * Hout);
+  const long long left = W.rho1 - rho;
+  u.y1 = (left < (long long)(Hout - u.y0)) ? u.y0 + (int)left : Hout;
+  if (s < W.ns0) { u.grp = 0; u.sl = s; u.Lg = 4 * batch * Wv; }
+  else if (s < W.ns0 + W.ns1) { u.grp = 1; u.sl = s - W.ns0; u.Lg = batch * Wv; }
+  else { u.grp = 2; u.sl = s - W.ns0 - W.ns1; u.Lg = batch * Wv; }
+  return u;
+}
+// image index within a group -> (batch element, face)
+__device__ __forceinline__ void rs_image(int grp, int i, int &b, int &f) {
+  if (grp == 0) { b = i >> 2; f = i & 3; }
+  else { b = i; f = 3 + grp; }
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------------------------
+template <int KC16T>
+__global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_constant__ RsP P) {
+  extern __shared__ uint8_t smem_raw[];
+  const RsPlan &L = P.L;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t rows0 = base, wbase = base + L.off_w, zbase = base + L.off_zero, misc = base + L.off_misc;
+  // barriers (8 bytes each): rfull[16] rempty[16] sfull[16] sempty[16] wfull wempty; tensor-memory slot
+  const uint32_t bar_rfull = misc, bar_rempty = misc + 128, bar_sfull = misc + 256, bar_sempty = misc + 384,
+                 bar_wfull = misc + 512, bar_wempty = misc + 520, tmem_slot = misc + 528;
+  float *s_bias = reinterpret_cast<float *>(gen + L.off_bias);
+  int *s_pix = reinterpret_cast<int *>(gen + L.off_pix);
+  const uint32_t stg0 = base + L.off_stg;
+
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+
+  RsWork W;
+  W.ns0 = (4 * P.batch * L.Wv + 127) >> 7;
+  W.ns1 = (P.batch * L.Wv + 127) >> 7;
+  W.ns2 = W.ns1;
+  {
+    const long long R = (long long)(W.ns0 + W.ns1 + W.ns2) * P.Hout;
+    W.rho0 = rs_cut(blockIdx.x, R, gridDim.x, P.Hout, P.snap);
+    W.rho1 = rs_cut(blockIdx.x + 1, R, gridDim.x, P.Hout, P.snap);
+  }
+
+  if (tid == 0) {
+    for (int i = 0; i < L.RSn; ++i) {
+      mbar_init(bar_rfull + 8 * i, RS_LOADERS);
+      mbar_init(bar_rempty + 8 * i, 1);
+    }
+    for (int i = 0; i < L.NS; ++i) {
+      mbar_init(bar_sfull + 8 * i, 1);
+      mbar_init(bar_sempty + 8 * i, 128);
+    }
+    mbar_init(bar_wfull, 1);
+    mbar_init(bar_wempty, 1);
+    fence_mbar_init();
+  }
+  // the zero B operand of the slot-clearing MMA
+  for (int i = tid; i < 2 * L.CoutP * 16 / 16; i += RS_THREADS) st_shared16(zbase + 16u * (uint32_t)i, make_uint4(0, 0, 0, 0));
+  fence_proxy_async();
+  if (warp == RS_MMA_WARP) tmem_alloc(tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(gen + (tmem_slot - base));
+  // programmatic dependent launch (see cs_tc.cu): whatever a previous kernel may have written -- activations (loaders),
+  // packed weights (TMA lane), bias (epilogue) -- is read behind griddepcontrol.wait
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp == RS_TMA_WARP) {
+    // ===== weight producer: the whole stacked weight set of a face group, once per group change =====
+    if (lane == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      int prev = -1, eph = 0;
+      for (long long rho = W.rho0; rho < W.rho1;) {
+        const RsUnit u = rs_unit(W, rho, P.Hout, P.batch, L.Wv);
+        if (u.grp != prev) {
+          if (prev >= 0) { rs_wait(bar_wempty, eph, P.err, 1); eph ^= 1; }
+          prev = u.grp;
+          const uint8_t *wg = P.wpack + (size_t)u.grp * L.groupBytes;
+          mbar_expect_tx(bar_wfull, (uint32_t)L.groupBytes);
+          for (int o = 0; o < L.groupBytes; o += 32768) {
+            const int bytes = min(32768, L.groupBytes - o);
+            tma_bulk_g2s(wbase + (uint32_t)o, wg + o, (uint32_t)bytes, bar_wfull);
+          }
+        }
+        rho += u.y1 - u.y0;
+      }
+    }
+  } else if (warp == RS_MMA_WARP) {
+    // ===== MMA issuer: whole-warp uniform loops, one elected lane per instruction =====
+    const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (8u << 24);
+    const uint32_t coutp = (uint32_t)L.CoutP, NS = (uint32_t)L.NS;
+    // A: swizzled K-major rows of RB bytes: SBO = 8 rows, LBO unused (1), layout code in bits 61..63, version 1
+    const uint64_t a_fix = ((uint64_t)(((uint32_t)(8 * L.RB) >> 4) | (1u << 14) | ((uint32_t)L.layoutType << 29)) << 32) |
+                           (1ull << 16);
+    // B: un-swizzled K-major core matrices [k8][n][8]: SBO = 128 B (next 8 columns), LBO = NT*16 B (next k8)
+    const uint64_t b_fix = ((uint64_t)((128u >> 4) | (1u << 14)) << 32) | ((uint64_t)((uint32_t)L.NT & 0x3FFFu) << 16);
+    const uint64_t z_desc = (((uint64_t)((128u >> 4) | (1u << 14)) << 32) | ((uint64_t)(coutp & 0x3FFFu) << 16)) | (zbase >> 4);
+    const uint32_t rb16 = (uint32_t)L.RB >> 4, unit16 = (uint32_t)L.unitBytes >> 4, b_jstep = (uint32_t)(2 * L.NT * 16) >> 4;
+    const uint64_t b_w = b_fix | (wbase >> 4);
+    // ring positions kept incrementally (no divisions in the row loop): row stage + parity; slot of the output row that is
+    // first touched by the current input row (zs, with the parity its "drained" barrier is waited with) and slot of the
+    // output row that the current input row completes (cs)
+    uint32_t stage = 0, sph = 0, zs = 0, zp = 1, cs = 0;
+    int prev = -1, fph = 0;
+    for (long long rho = W.rho0; rho < W.rho1;) {
+      const RsUnit u = rs_unit(W, rho, P.Hout, P.batch, L.Wv);
+      const int H = u.y1 - u.y0;
+      if (u.grp != prev) {
+        rs_wait_uniform(bar_wfull, fph);
+        fph ^= 1;
+        prev = u.grp;
+      }
+      const uint32_t s0 = zs;              // slot of the unit's first output row
+      cs = zs;
+#pragma unroll 1
+      for (int yi = 0; yi < H + 2; ++yi) {
+        rs_wait_uniform(bar_rfull + 8 * stage, sph);
+        if (yi < H) rs_wait_uniform(bar_sempty + 8 * zs, zp);   // first touch of this slot: it must have been drained
+        tc_fence_after();
+        const uint64_t a_row = a_fix | ((rows0 + stage * (uint32_t)L.stageBytes) >> 4);
+        if (yi < H) umma_bf16_elect(tmem_base + zs * coutp, a_row, z_desc, idesc0 | ((coutp >> 3) << 17), 0u);
+        // parts j = 0..2 of the stacked N (kernel rows 2, 1, 0) -> output rows yi - 2 + j, those inside [0, H)
+        const int jlo = yi >= 2 ? 0 : 2 - yi, jhi = (H + 1 - yi) < 2 ? (H + 1 - yi) : 2;
+        const uint32_t t0 = yi >= 2 ? cs : s0;
+        const int np = jhi - jlo + 1;
+        const int np1 = (int)(NS - t0) < np ? (int)(NS - t0) : np;
+#pragma unroll 1
+        for (int seg = 0; seg < 2; ++seg) {
+          const int j0 = seg == 0 ? jlo : jlo + np1, cnt = seg == 0 ? np1 : np - np1;
+          if (cnt <= 0) break;
+          const uint32_t d = tmem_base + (seg == 0 ? t0 : 0u) * coutp;
+          const uint32_t idesc = idesc0 | ((((uint32_t)cnt * coutp) >> 3) << 17);
+          const uint64_t b_seg = b_w + (uint64_t)(((uint32_t)j0 * coutp * 16u) >> 4);
+#pragma unroll
+          for (int v = 0; v < 3; ++v)
+#pragma unroll
+            for (int j = 0; j < KC16T; ++j)
+              umma_bf16_elect(d, a_row + (uint64_t)((uint32_t)v * rb16 + (uint32_t)j * 2u),
+                              b_seg + (uint64_t)((uint32_t)v * unit16 + (uint32_t)j * b_jstep), idesc, 1u);
+        }
+        umma_commit_elect(bar_rempty + 8 * stage);                      // the row stage may be refilled
+        if (++stage == (uint32_t)L.RSn) { stage = 0; sph ^= 1u; }
+        if (yi >= 2) {                                                  // output row yi - 2 is complete
+          umma_commit_elect(bar_sfull + 8 * cs);
+          if (++cs == NS) cs = 0;
+        }
+        if (yi < H && ++zs == NS) { zs = 0; zp ^= 1u; }
+      }
+      rho += H;
+      if (rho < W.rho1 && rs_unit(W, rho, P.Hout, P.batch, L.Wv).grp != u.grp) umma_commit_elect(bar_wempty);
+    }
+  } else if (warp >= RS_EPI_WARP0 && warp < RS_EPI_WARP0 + 8) {
+    // ===== epilogue: slot -> registers -> bias / activation -> bf16 -> per-warp compaction -> coalesced stores.  Warp w
+    // reads TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter take alternate output rows. =====
+    const int quarter = warp & 3, half = (warp - RS_EPI_WARP0) >> 2;
+    const uint32_t stg = stg0 + (uint32_t)(warp - RS_EPI_WARP0) * L.stgBytes;
+    int *pixw = s_pix + (warp - RS_EPI_WARP0) * 32;
+    const uint32_t rowB = (uint32_t)P.cout * 2u;
+    const bool act_fast = P.act == DLWPCS_ACT_CAPPED_LEAKY_RELU && P.slope >= 0.f && P.slope <= 1.f;
+    const uint32_t cpr = rowB >> 4;
+    const int cprLog = (cpr & (cpr - 1)) == 0 ? 31 - __clz(cpr) : -1;
+    const uint32_t smask = (cpr & (cpr - 1)) == 0 ? min(cpr, 8u) - 1u : 0u;
+    const uint32_t NS = (uint32_t)L.NS;
+    asm volatile("griddepcontrol.wait;" ::: "memory");        // the bias sits behind the packed weights
+    for (int i = tid - RS_EPI_WARP0 * 32; i < 3 * L.CoutP; i += RS_EPI) s_bias[i] = P.bias[i];
+    asm volatile("bar.sync 2, %0;" ::"n"(RS_EPI) : "memory");
+    uint32_t slot = 0, eph = 0, odd = 0;      // slot / barrier parity / row parity of the next output row of this CTA
+    for (long long rho = W.rho0; rho < W.rho1;) {
+      const RsUnit u = rs_unit(W, rho, P.Hout, P.batch, L.Wv);
+      const int H = u.y1 - u.y0;
+      const float *bias = s_bias + u.grp * L.CoutP;
+      // this lane's position: image and column
+      const int p = u.sl * 128 + quarter * 32 + lane;
+      const int img = p / L.Wv, cv = p - img * L.Wv;
+      const bool ok = p < u.Lg && cv < P.Wout;
+      int b, f;
+      rs_image(u.grp, img, b, f);
+      const int opix0 = ((b * 6 + f) * P.Hout + u.y0) * P.Wout + cv;       // output pixel of this lane in the unit's first row
+      const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+      const int nvalid = __popc(okmask);
+      const uint32_t prow = (uint32_t)__popc(okmask & ((1u << lane) - 1u));   // compacted row of this lane
+      __syncwarp();
+      if (ok) pixw[prow] = opix0;
+      __syncwarp();
+      const uint32_t srow = stg + prow * rowB;
+      const uint32_t total = (uint32_t)nvalid * rowB;
+#pragma unroll 1
+      for (int o = 0; o < H; ++o) {
+        const uint32_t slot_o = slot, eph_o = eph, mine = ((int)odd == half);
+        odd ^= 1u;
+        if (++slot == NS) { slot = 0; eph ^= 1u; }
+        if (!mine) continue;
+        rs_wait(bar_sfull + 8 * slot_o, eph_o, P.err, 2);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot_o * (uint32_t)L.CoutP;
+        for (int n0 = 0; n0 < L.CoutP; n0 += 32) {
+          uint32_t v[32];
+          const bool two = n0 + 16 < L.CoutP;
+          tmem_ld16(trow + (uint32_t)n0, v);
+          if (two) tmem_ld16(trow + (uint32_t)n0 + 16u, v + 16);
+          tmem_ld_wait();
+          if (n0 + 32 >= L.CoutP) {          // everything of the slot is in registers: hand it back to the MMA issuer
+            tc_fence_before();
+            mbar_arrive(bar_sempty + 8 * slot_o);
+          }
+          if (!ok) continue;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !two) break;
+            const int nb = n0 + 16 * h;
+            float r[16];
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const float4 bv = *reinterpret_cast<const float4 *>(bias + nb + 4 * k4);
+              r[4 * k4 + 0] = __uint_as_float(v[16 * h + 4 * k4 + 0]) + bv.x;
+              r[4 * k4 + 1] = __uint_as_float(v[16 * h + 4 * k4 + 1]) + bv.y;
+              r[4 * k4 + 2] = __uint_as_float(v[16 * h + 4 * k4 + 2]) + bv.z;
+              r[4 * k4 + 3] = __uint_as_float(v[16 * h + 4 * k4 + 3]) + bv.w;
+            }
+            if (act_fast) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) r[e] = fminf(fmaxf(r[e], P.slope * r[e]), P.maxv);
+            } else if (P.act != DLWPCS_ACT_NONE) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) r[e] = act_apply(r[e], P.act, P.slope, P.maxv);
+            }
+            if (nb + 8 <= P.cout)
+              st_shared16(srow + ((((uint32_t)nb >> 3) ^ (prow & smask)) << 4),
+                          make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7])));
+            if (nb + 16 <= P.cout)
+              st_shared16(srow + (((((uint32_t)nb >> 3) + 1u) ^ (prow & smask)) << 4),
+                          make_uint4(pack_bf16x2(r[8], r[9]), pack_bf16x2(r[10], r[11]), pack_bf16x2(r[12], r[13]), pack_bf16x2(r[14], r[15])));
+          }
+        }
+        __syncwarp();
+        // rows of one image are contiguous in HBM; consecutive lanes copy consecutive 16-byte chunks
+        const uint32_t rowoff = (uint32_t)(o * P.Wout);
+        for (uint32_t off = (uint32_t)lane * 16u; off < total; off += 512u) {
+          uint32_t row, ch;
+          if (cprLog >= 0) { row = off >> (4 + cprLog); ch = (off >> 4) & (cpr - 1u); }
+          else { row = off / rowB; ch = (off - row * rowB) >> 4; }
+          uint4 q;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                       : "r"(stg + row * rowB + ((ch ^ (row & smask)) << 4)));
+          uint8_t *gdst = reinterpret_cast<uint8_t *>(P.y) + ((size_t)((uint32_t)pixw[row] + rowoff)) * rowB + (ch << 4);
+          *reinterpret_cast<uint4 *>(gdst) = q;
+        }
+        __syncwarp();                                 // the staging buffer is rewritten by this warp's next row
+      }
+      rho += H;
+    }
+  } else if (warp < 8) {
+    // ===== loaders: one padded input row of the strip per stage; every thread owns one 16-byte channel chunk of up to
+    // RS_KP fixed positions =====
+    const int lt = tid;
+    const int chunk = lt & (L.S - 1), c = chunk * 8;
+    const bool first = c < P.c0;
+    const __nv_bfloat16 *src = first ? P.x0 : P.x1;
+    const int C = first ? P.c0 : P.c1, cc = first ? c : c - P.c0, mode = first ? P.mode0 : P.mode1;
+    const int32_t *tab = first ? P.tab0 : P.tab1;
+    const int ppb = first ? P.ppb0 : P.ppb1;
+    const bool chan_ok = c < P.cin;
+    const int pstep = RS_LOADERS >> L.logS, l0 = lt >> L.logS;
+    const uint32_t cw = (uint32_t)chunk & ((1u << L.cprLog) - 1u);
+    const bool pooled = mode == DLWPCS_SRC_POOL2;
+    const int w2 = P.n * 2;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    uint32_t stage = 0, sph = 0;
+    for (long long rho = W.rho0; rho < W.rho1;) {
+      const RsUnit u = rs_unit(W, rho, P.Hout, P.batch, L.Wv);
+      const int H = u.y1 - u.y0;
+      int tabofs[RS_KP], pixb[RS_KP];
+      uint32_t dsto[RS_KP];
+#pragma unroll
+      for (int k = 0; k < RS_KP; ++k) {
+        const int l = l0 + k * pstep;
+        const int p = u.sl * 128 + l;
+        const int img = p / L.Wv, cv = p - img * L.Wv;
+        int b, f;
+        rs_image(u.grp, img, b, f);
+        const bool inb = l < RS_NPOS;
+        tabofs[k] = (inb && p < u.Lg && chan_ok) ? f * L.G + cv : -1;
+        pixb[k] = b * ppb;
+        const uint32_t ro = (uint32_t)l * (uint32_t)L.RB;
+        dsto[k] = inb ? ro + ((cw ^ ((ro >> 7) & (uint32_t)L.swzMask)) << 4) : 0xFFFFFFFFu;
+      }
+      int pxn[RS_KP];
+#pragma unroll
+      for (int k = 0; k < RS_KP; ++k) pxn[k] = tabofs[k] >= 0 ? __ldg(tab + tabofs[k] + u.y0 * L.Wv) : -1;
+#pragma unroll 1
+      for (int yi = 0; yi < H + 2; ++yi) {
+        int px[RS_KP];
+#pragma unroll
+        for (int k = 0; k < RS_KP; ++k) px[k] = pxn[k];
+        if (yi + 1 < H + 2) {
+#pragma unroll
+          for (int k = 0; k < RS_KP; ++k) pxn[k] = tabofs[k] >= 0 ? __ldg(tab + tabofs[k] + (u.y0 + yi + 1) * L.Wv) : -1;
+        }
+        rs_wait(bar_rempty + 8 * stage, sph ^ 1u, P.err, 3);
+        const uint32_t sbase = rows0 + stage * (uint32_t)L.stageBytes;
+        if (!pooled) {
+#pragma unroll
+          for (int k = 0; k < RS_KP; ++k) {
+            if (dsto[k] != 0xFFFFFFFFu) {
+              const __nv_bfloat16 *g = px[k] >= 0 ? src + ((size_t)(pixb[k] + px[k]) * C + cc) : P.x0;
+              cp_async16(sbase + dsto[k], g, px[k] >= 0 ? 16u : 0u);
+            }
+          }
+          fence_proxy_async();
+          cp_async_mbar_arrive(bar_rfull + 8 * stage);
+        } else {
+          // 2x2 mean (AveragePooling3D((1,2,2)), train_cs.py:197) through registers; rounded to bf16 once, like a stored
+          // pooled tensor
+#pragma unroll
+          for (int k = 0; k < RS_KP; ++k) {
+            if (dsto[k] != 0xFFFFFFFFu) {
+              uint4 o4 = make_uint4(0, 0, 0, 0);
+              if (px[k] >= 0) {
+                const __nv_bfloat16 *g = src + ((size_t)(pixb[k] + px[k]) * C + cc);
+                const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(g));
+                const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(g + C));
+                const uint4 v2 = __ldg(reinterpret_cast<const uint4 *>(g + (size_t)w2 * C));
+                const uint4 v3 = __ldg(reinterpret_cast<const uint4 *>(g + (size_t)(w2 + 1) * C));
+                float a[8], t[8];
+                unpack_bf16x8(v0, a);
+                unpack_bf16x8(v1, t);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] += t[e];
+                unpack_bf16x8(v2, t);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] += t[e];
+                unpack_bf16x8(v3, t);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] += t[e];
+                o4 = make_uint4(pack_bf16x2(0.25f * a[0], 0.25f * a[1]), pack_bf16x2(0.25f * a[2], 0.25f * a[3]),
+                                pack_bf16x2(0.25f * a[4], 0.25f * a[5]), pack_bf16x2(0.25f * a[6], 0.25f * a[7]));
+              }
+              st_shared16(sbase + dsto[k], o4);
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(bar_rfull + 8 * stage);
+        }
+        if (++stage == (uint32_t)L.RSn) { stage = 0; sph ^= 1u; }
+      }
+      rho += H;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == RS_MMA_WARP) tmem_dealloc(tmem_base, 512u);
+}
+
+// ---- weight packing: packed[g][v][k8][n = j*CoutP + o][8] bf16, part j = kernel row 2 - j; + fp32 bias[3][CoutP] ----
+__global__ void pack_rs_kernel(const float *__restrict__ w_eq, const float *__restrict__ w_pol, const float *__restrict__ w_np,
+                               const float *__restrict__ b_eq, const float *__restrict__ b_pol, const float *__restrict__ b_np,
+                               uint8_t *out, int CinP, int CoutP, long long groupElems, int cin, int cout, int scin, int scout,
+                               int flip) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int NT = 3 * CoutP;
+  if (i < 3 * groupElems) {
+    const int g = (int)(i / groupElems);
+    long long r = i % groupElems;
+    const int e = (int)(r % 8); r /= 8;
+    const int n = (int)(r % NT); r /= NT;
+    const int k8 = (int)(r % (CinP / 8));
+    const int v = (int)(r / (CinP / 8));
+    const int j = n / CoutP, o = n - j * CoutP, k = k8 * 8 + e, u = 2 - j;
+    float val = 0.f;
+    if (k < cin && o < cout && k < scin && o < scout) {
+      const float *src = g == 0 ? w_eq : (g == 1 ? w_pol : (w_np ? w_np : w_pol));
+      const int us = (g == 2 && flip) ? 2 - u : u;
+      val = src[(((long long)us * 3 + v) * scin + k) * scout + o];
+    }
+    reinterpret_cast<__nv_bfloat16 *>(out)[i] = __float2bfloat16_rn(val);
+  } else if (i < 3 * groupElems + 3LL * CoutP) {
+    const int jj = (int)(i - 3 * groupElems), g = jj / CoutP, co = jj % CoutP;
+    const float *src = g == 0 ? b_eq : (g == 1 ? b_pol : (b_np ? b_np : b_pol));
+    float *bo = reinterpret_cast<float *>(out + 3 * groupElems * 2);
+    bo[jj] = (src && co < scout) ? src[co] : 0.f;
+  }
+}
+
+int rs_env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return s && *s ? atoi(s) : dflt;
+}
+
+// nullptr when the row-streamed kernel serves the layer, otherwise the reason it does not
+const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L) {
+  if (d->kh != 3 || d->kw != 3) return "3x3 kernels only";
+  if (d->stride_h != 1 || d->stride_w != 1 || d->dil_h != 1 || d->dil_w != 1) return "stride / dilation 1 only";
+  if (d->x_dtype != DLWPCS_BF16 || d->y_dtype != DLWPCS_BF16) return "bf16 in, bf16 out";
+  if (d->cout % 8 || d->c0 % 8 || d->c1 % 8) return "channel counts must be multiples of 8";
+  L->CinP = (d->cin + 15) / 16 * 16;
+  if (L->CinP > 32) L->CinP = (d->cin + 63) / 64 * 64;
+  if (L->CinP > 64) return "more than 64 input channels";
+  L->KC16 = L->CinP / 16;
+  L->S = L->CinP / 8;
+  L->logS = L->S == 2 ? 1 : (L->S == 4 ? 2 : 3);
+  L->RB = L->CinP * 2;
+  L->cprLog = L->RB == 128 ? 3 : (L->RB == 64 ? 2 : 1);
+  L->swzMask = (1 << L->cprLog) - 1;
+  L->layoutType = L->RB == 128 ? 2 : (L->RB == 64 ? 4 : 6);
+  L->CoutP = (d->cout + 15) / 16 * 16;
+  if (L->CoutP < 32) L->CoutP = 32;
+  L->NT = 3 * L->CoutP;
+  if (L->NT > 256) return "more than 80 output channels";
+  L->NS = 512 / L->CoutP;
+  if (L->NS > RS_MAXSLOTS) L->NS = RS_MAXSLOTS;
+  L->Wv = g.Wout + 2;
+  L->Hv = g.Hout + 2;
+  L->G = (L->Hv * L->Wv + 3) / 4 * 4;
+  L->stageBytes = (RS_NPIXP * L->RB + 1023) / 1024 * 1024;
+  L->unitBytes = L->CinP * L->NT * 2;
+  L->groupBytes = 3 * L->unitBytes;
+  L->stgBytes = 32 * d->cout * 2;
+  int off = 0;
+  L->off_w = 0;        // filled below, after the row stages
+  const int wB = (L->groupBytes + 1023) / 1024 * 1024;
+  const int zeroB = 2 * L->CoutP * 16;
+  const int fixed = wB + (zeroB + 127) / 128 * 128 + 1024 + (3 * L->CoutP * 4 + 127) / 128 * 128 + 8 * 32 * 4 +
+                    8 * L->stgBytes + 1024 /* alignment slack */;
+  int rsn = (RS_SMEM_CAP - fixed) / L->stageBytes;
+  const int want = rs_env_int("DLWPCS_RS_STAGES", RS_MAXSTAGES);
+  if (rsn > want) rsn = want;
+  if (rsn > RS_MAXSTAGES) rsn = RS_MAXSTAGES;
+  if (rsn < 4) return "stacked weights leave no room for the input-row ring";
+  L->RSn = rsn;
+  off = rsn * L->stageBytes;
+  L->off_w = off; off += wB;
+  L->off_zero = off; off += (zeroB + 127) / 128 * 128;
+  L->off_misc = off; off += 1024;
+  L->off_bias = off; off += (3 * L->CoutP * 4 + 127) / 128 * 128;
+  L->off_pix = off; off += 8 * 32 * 4;
+  L->off_stg = off; off += 8 * L->stgBytes;
+  L->smemBytes = off + 1024;
+  return nullptr;
+}
+
+bool rs_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int rs_num_sms() {
+  static int sms[kMaxDevices] = {};
+  const int dev = current_device_index();
+  if (!sms[dev] && (cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms[dev] <= 0))
+    sms[dev] = 148;
+  return sms[dev];
+}
+
+unsigned *g_rs_err[kMaxDevices] = {};
+
+}  // namespace
+
+bool rs_eligible(const dlwpcs_conv_desc *d, const Geometry &g) {
+  static const int enabled = rs_env_int("DLWPCS_RS", 1);
+  if (!enabled) return false;
+  RsPlan L;
+  return rs_make_plan(d, g, &L) == nullptr;
+}
+
+int64_t rs_packed_weight_bytes(const dlwpcs_conv_desc *d, const Geometry &g) {
+  RsPlan L;
+  if (rs_make_plan(d, g, &L)) return -1;
+  return 3LL * L.groupBytes + 3LL * L.CoutP * 4;
+}
+
+int rs_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, int src_cin, int src_cout,
+                    void *packed, cudaStream_t st) {
+  RsPlan L;
+  const char *r = rs_make_plan(d, g, &L);
+  CS_CHECK(r == nullptr, "row-streamed kernel does not support this configuration: %s", r);
+  const long long groupElems = L.groupBytes / 2, total = 3 * groupElems + 3LL * L.CoutP;
+  pack_rs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      w->w_eq, w->w_pol, d->independent_north_pole ? w->w_np : nullptr, d->use_bias ? w->b_eq : nullptr,
+      d->use_bias ? w->b_pol : nullptr, (d->use_bias && d->independent_north_pole) ? w->b_np : nullptr, (uint8_t *)packed,
+      L.CinP, L.CoutP, groupElems, d->cin, d->cout, src_cin, src_cout, d->flip_north_pole);
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int rs_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed, void *y,
+                cudaStream_t st) {
+  RsP P;
+  memset(&P, 0, sizeof(P));
+  const char *r = rs_make_plan(d, g, &P.L);
+  CS_CHECK(r == nullptr, "row-streamed kernel does not support this configuration: %s", r);
+  const RsPlan &L = P.L;
+  CS_CHECK(rs_aligned16(x0) && (d->c1 == 0 || rs_aligned16(x1)) && rs_aligned16(y) && rs_aligned16(packed),
+           "bf16 tensors must be 16-byte aligned");
+  P.x0 = (const __nv_bfloat16 *)x0;
+  P.x1 = (const __nv_bfloat16 *)x1;
+  P.tab0 = get_patch_table(g, L.Wv, L.G, d->n, d->halo, d->mode0);
+  if (!P.tab0) return 3;
+  P.tab1 = P.tab0;
+  if (d->c1 > 0) {
+    P.tab1 = get_patch_table(g, L.Wv, L.G, d->n, d->halo, d->mode1);
+    if (!P.tab1) return 3;
+  }
+  auto ppb = [&](int mode) {
+    const int e = mode == DLWPCS_SRC_SAME ? d->n : (mode == DLWPCS_SRC_UP2 ? d->n / 2 : d->n * 2);
+    return 6 * e * e;
+  };
+  P.ppb0 = ppb(d->mode0);
+  P.ppb1 = ppb(d->mode1);
+  P.wpack = (const uint8_t *)packed;
+  P.bias = reinterpret_cast<const float *>(P.wpack + 3LL * L.groupBytes);
+  P.y = (__nv_bfloat16 *)y;
+  P.batch = d->batch; P.n = d->n; P.Hout = g.Hout; P.Wout = g.Wout;
+  P.cin = d->cin; P.cout = d->cout; P.c0 = d->c0; P.c1 = d->c1; P.mode0 = d->mode0; P.mode1 = d->mode1;
+  P.act = d->act; P.slope = d->act_slope; P.maxv = d->act_max;
+  if (d->batch == 0) return 0;
+  const int dev_i = current_device_index();
+  if (!g_rs_err[dev_i]) {
+    CS_CUDA(cudaMalloc(&g_rs_err[dev_i], sizeof(unsigned)));
+    CS_CUDA(cudaMemset(g_rs_err[dev_i], 0, sizeof(unsigned)));
+  }
+  P.err = g_rs_err[dev_i];
+  typedef void (*kern_t)(const RsP);
+  static const kern_t kerns[4] = {conv_rs_kernel<1>, conv_rs_kernel<2>, nullptr, conv_rs_kernel<4>};
+  static bool attr_set[kMaxDevices][4] = {};
+  const kern_t kern = kerns[L.KC16 - 1];
+  CS_CHECK(kern != nullptr, "internal: bad K block");
+  if (!attr_set[dev_i][L.KC16 - 1]) {
+    CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_CAP));
+    attr_set[dev_i][L.KC16 - 1] = true;
+  }
+  const long long strips = (4LL * d->batch * L.Wv + 127) / 128 + 2 * ((1LL * d->batch * L.Wv + 127) / 128);
+  const long long R = strips * g.Hout;
+  CS_CHECK(R < (1LL << 40), "batch too large");
+  P.snap = g.Hout >= 16 ? 4 : (g.Hout >= 8 ? 2 : 1);
+  int grid = rs_num_sms();
+  const long long min_rows = 4;
+  if ((long long)grid * min_rows > R) grid = (int)((R + min_rows - 1) / min_rows);
+  if (grid < 1) grid = 1;
+  static const int pdl = rs_env_int("DLWPCS_TC_PDL", 1);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(RS_THREADS);
+  cfg.dynamicSmemBytes = (size_t)L.smemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  CS_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+  return 0;
+}
+
+}  // namespace dlwpcs
