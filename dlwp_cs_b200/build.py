@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(LIB_DIR, src.replace('.cu', '.o'))
         cmd = [nvcc] + NVCC_FLAGS + (['--use_fast_math'] if src in FAST_MATH else []) + \
-            (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+            (['-Xptxas', '-v'] if verbose else []) + (['-DRS_DEBUG_WAITS'] if os.environ.get('DLWPCS_RS_DEBUG') else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

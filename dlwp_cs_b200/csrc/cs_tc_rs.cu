@@ -42,8 +42,9 @@ constexpr int RS_EPI_WARP0 = 8, RS_TMA_WARP = 16, RS_MMA_WARP = 17;
 constexpr int RS_MAXSLOTS = 16, RS_MAXSTAGES = 16;
 constexpr int RS_NPOS = 130;       // 128 lanes + (kw - 1) positions of overhang
 constexpr int RS_NPIXP = 136;      // rows of one stage (multiple of 8)
-constexpr int RS_KP = 5;           // positions per loader thread: ceil(130 / (256 / S)), S = CinP / 8 <= 8
+//          // positions per loader lane and batch of table lookups (S = 4: the whole row in one batch)
 constexpr int RS_SMEM_CAP = 227 * 1024;
+constexpr int RS_MAXGRID = 160;
 
 struct RsPlan {
   int CinP, KC16, S, logS, RB, cprLog, swzMask, layoutType;
@@ -52,7 +53,7 @@ struct RsPlan {
   int stageBytes, RSn;               // bytes per input-row stage, stages
   int unitBytes, groupBytes;         // weights of one (kernel column) unit / of one face group
   int stgBytes;                      // output staging per epilogue warp
-  int off_w, off_zero, off_misc, off_bias, off_pix, off_stg, smemBytes;
+  int off_w, off_zero, off_misc, off_bias, off_pix, off_pos, off_px, off_stg, smemBytes;
 };
 
 struct RsP {
@@ -65,7 +66,8 @@ struct RsP {
   int cin, cout, c0, c1, mode0, mode1, ppb0, ppb1;
   int act;
   float slope, maxv;
-  int snap;                          // work cuts closer than this to a strip boundary are moved onto it
+  int knock;                         // bottleneck analysis (DLWPCS_RS_KNOCK): 1 no gathers, 2 no MMAs, 4 no epilogue math / stores
+  int cut_s[RS_MAXGRID + 1], cut_y[RS_MAXGRID + 1];     // CTA c works on [(cut_s[c], cut_y[c]), (cut_s[c+1], cut_y[c+1]))
   unsigned *err;                     // watchdog flag (a barrier wait that never completes traps instead of hanging the GPU)
   RsPlan L;
 };
@@ -83,8 +85,11 @@ __device__ __forceinline__ void rs_wait(uint32_t bar, uint32_t parity, unsigned 
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (!done && it > (1u << 26)) {
-      if (err) atomicExch(err, (unsigned)code);
+    if (!done && it > (1u << 24)) {
+      if (err) {
+        atomicCAS(err, 0u, (unsigned)code | (parity << 4) | ((bar & 0xFFFu) << 8) | (blockIdx.x << 20));
+        __threadfence_system();
+      }
       __trap();
     }
   }
@@ -92,33 +97,37 @@ __device__ __forceinline__ void rs_wait(uint32_t bar, uint32_t parity, unsigned 
 // Warp-uniform variant for the MMA issuer: the loop lives in one opaque asm statement (a C++ spin loop makes the compiler
 // treat everything after it as divergent and the MMA descriptors leave the uniform registers, see cs_tc.cu).
 __device__ __forceinline__ void rs_wait_uniform(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+#ifdef RS_DEBUG_WAITS
+#define RS_WAIT_MMA(bar, parity, code) rs_wait(bar, parity, P.err, code)
+#else
+#define RS_WAIT_MMA(bar, parity, code) rs_wait_uniform(bar, parity)
+#endif
 
+// Work of a CTA: a contiguous range of (strip, output row) pairs, [ (s0, y0), (s1, y1) ), cut on the host (rs_conv_fwd) and
+// passed in the kernel parameters, so that everything the MMA issuer derives from it is provably warp-uniform (constant
+// bank + blockIdx): its descriptors then live in uniform registers instead of being converted for every instruction.
 struct RsWork {
-  long long rho0, rho1;              // this CTA's range of global (strip, output row) indices
-  int ns0, ns1, ns2;                 // strips per face group
+  int s, y0;                         // current unit: strip, first output row
+  int s_end, y_end;                  // end of the range
+  int ns0, ns01;                     // strips of group 0, of groups 0 + 1
+  int Hout, eqL, polL;               // output rows per strip, positions of the equatorial / of a polar group
 };
-
-__device__ __forceinline__ long long rs_cut(long long c, long long R, int grid, int Hout, int snap) {
-  long long b = c * R / grid;
-  const int r = (int)(b % Hout);
-  if (r < snap) b -= r;
-  else if (r > Hout - snap) b += Hout - r;
-  return b;
-}
-
 struct RsUnit {
   int grp, sl, y0, y1, Lg;           // face group, strip within the group, output rows [y0, y1), positions in the group
 };
-__device__ __forceinline__ RsUnit rs_unit(const RsWork &W, long long rho, int Hout, int batch, int Wv) {
+__device__ __forceinline__ bool rs_more(const RsWork &W) { return W.s < W.s_end || (W.s == W.s_end && W.y0 < W.y_end); }
+__device__ __forceinline__ RsUnit rs_unit(const RsWork &W) {
   RsUnit u;
-  const int s = (int)(rho / Hout);
-  u.y0 = (int)(rho - (long long)s * Hout);
-  const long long left = W.rho1 - rho;
-  u.y1 = (left < (long long)(Hout - u.y0)) ? u.y0 + (int)left : Hout;
-  if (s < W.ns0) { u.grp = 0; u.sl = s; u.Lg = 4 * batch * Wv; }
-  else if (s < W.ns0 + W.ns1) { u.grp = 1; u.sl = s - W.ns0; u.Lg = batch * Wv; }
-  else { u.grp = 2; u.sl = s - W.ns0 - W.ns1; u.Lg = batch * Wv; }
+  u.y0 = W.y0;
+  u.y1 = W.s == W.s_end ? W.y_end : W.Hout;
+  if (W.s < W.ns0) { u.grp = 0; u.sl = W.s; u.Lg = W.eqL; }
+  else if (W.s < W.ns01) { u.grp = 1; u.sl = W.s - W.ns0; u.Lg = W.polL; }
+  else { u.grp = 2; u.sl = W.s - W.ns01; u.Lg = W.polL; }
   return u;
+}
+__device__ __forceinline__ void rs_advance(RsWork &W, const RsUnit &u) {
+  if (u.y1 == W.Hout) { ++W.s; W.y0 = 0; }
+  else W.y0 = u.y1;
 }
 // image index within a group -> (batch element, face)
 __device__ __forceinline__ void rs_image(int grp, int i, int &b, int &f) {
@@ -143,24 +152,21 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
 
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
 
-  RsWork W;
-  W.ns0 = (4 * P.batch * L.Wv + 127) >> 7;
-  W.ns1 = (P.batch * L.Wv + 127) >> 7;
-  W.ns2 = W.ns1;
-  {
-    const long long R = (long long)(W.ns0 + W.ns1 + W.ns2) * P.Hout;
-    W.rho0 = rs_cut(blockIdx.x, R, gridDim.x, P.Hout, P.snap);
-    W.rho1 = rs_cut(blockIdx.x + 1, R, gridDim.x, P.Hout, P.snap);
-  }
+  RsWork W0;
+  W0.s = P.cut_s[blockIdx.x]; W0.y0 = P.cut_y[blockIdx.x];
+  W0.s_end = P.cut_s[blockIdx.x + 1]; W0.y_end = P.cut_y[blockIdx.x + 1];
+  W0.ns0 = (4 * P.batch * L.Wv + 127) >> 7;
+  W0.ns01 = W0.ns0 + ((P.batch * L.Wv + 127) >> 7);
+  W0.Hout = P.Hout; W0.eqL = 4 * P.batch * L.Wv; W0.polL = P.batch * L.Wv;
 
   if (tid == 0) {
     for (int i = 0; i < L.RSn; ++i) {
-      mbar_init(bar_rfull + 8 * i, RS_LOADERS);
+      mbar_init(bar_rfull + 8 * i, 32);                   // the 32 lanes of the loader warp that owns the row
       mbar_init(bar_rempty + 8 * i, 1);
     }
     for (int i = 0; i < L.NS; ++i) {
       mbar_init(bar_sfull + 8 * i, 1);
-      mbar_init(bar_sempty + 8 * i, 128);
+      mbar_init(bar_sempty + 8 * i, 4);                   // one arrival per epilogue warp of the row (4 lane quarters)
     }
     mbar_init(bar_wfull, 1);
     mbar_init(bar_wempty, 1);
@@ -183,8 +189,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     if (lane == 0) {
       asm volatile("griddepcontrol.wait;" ::: "memory");
       int prev = -1, eph = 0;
-      for (long long rho = W.rho0; rho < W.rho1;) {
-        const RsUnit u = rs_unit(W, rho, P.Hout, P.batch, L.Wv);
+      for (RsWork W = W0; rs_more(W);) {
+        const RsUnit u = rs_unit(W);
         if (u.grp != prev) {
           if (prev >= 0) { rs_wait(bar_wempty, eph, P.err, 1); eph ^= 1; }
           prev = u.grp;
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
             tma_bulk_g2s(wbase + (uint32_t)o, wg + o, (uint32_t)bytes, bar_wfull);
           }
         }
-        rho += u.y1 - u.y0;
+        rs_advance(W, u);
       }
     }
   } else if (warp == RS_MMA_WARP) {
@@ -215,23 +221,24 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     // output row that the current input row completes (cs)
     uint32_t stage = 0, sph = 0, zs = 0, zp = 1, cs = 0;
     int prev = -1, fph = 0;
-    for (long long rho = W.rho0; rho < W.rho1;) {
-      const RsUnit u = rs_unit(W, rho, P.Hout, P.batch, L.Wv);
-      const int H = u.y1 - u.y0;
-      if (u.grp != prev) {
-        rs_wait_uniform(bar_wfull, fph);
+    for (RsWork W = W0; rs_more(W);) {
+      const RsUnit u = rs_unit(W);
+      const int H = u.y1 - u.y0, grp = u.grp;
+      if (grp != prev) {
+        RS_WAIT_MMA(bar_wfull, fph, 4);
         fph ^= 1;
-        prev = u.grp;
+        prev = grp;
       }
       const uint32_t s0 = zs;              // slot of the unit's first output row
       cs = zs;
 #pragma unroll 1
       for (int yi = 0; yi < H + 2; ++yi) {
-        rs_wait_uniform(bar_rfull + 8 * stage, sph);
-        if (yi < H) rs_wait_uniform(bar_sempty + 8 * zs, zp);   // first touch of this slot: it must have been drained
+        if (!(P.knock & 16)) RS_WAIT_MMA(bar_rfull + 8 * stage, sph, 5);
+        if (yi < H && !(P.knock & 8)) RS_WAIT_MMA(bar_sempty + 8 * zs, zp, 6);   // first touch of this slot: it must have been drained
         tc_fence_after();
+        fence_proxy_async();               // the loaders' generic-proxy writes, acquired through the barrier, before the MMAs' reads
         const uint64_t a_row = a_fix | ((rows0 + stage * (uint32_t)L.stageBytes) >> 4);
-        if (yi < H) umma_bf16_elect(tmem_base + zs * coutp, a_row, z_desc, idesc0 | ((coutp >> 3) << 17), 0u);
+        if (yi < H && !(P.knock & 2)) umma_bf16_elect(tmem_base + zs * coutp, a_row, z_desc, idesc0 | ((coutp >> 3) << 17), 0u);
         // parts j = 0..2 of the stacked N (kernel rows 2, 1, 0) -> output rows yi - 2 + j, those inside [0, H)
         const int jlo = yi >= 2 ? 0 : 2 - yi, jhi = (H + 1 - yi) < 2 ? (H + 1 - yi) : 2;
         const uint32_t t0 = yi >= 2 ? cs : s0;
@@ -240,7 +247,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
 #pragma unroll 1
         for (int seg = 0; seg < 2; ++seg) {
           const int j0 = seg == 0 ? jlo : jlo + np1, cnt = seg == 0 ? np1 : np - np1;
-          if (cnt <= 0) break;
+          if (cnt <= 0 || (P.knock & 2)) break;
           const uint32_t d = tmem_base + (seg == 0 ? t0 : 0u) * coutp;
           const uint32_t idesc = idesc0 | ((((uint32_t)cnt * coutp) >> 3) << 17);
           const uint64_t b_seg = b_w + (uint64_t)(((uint32_t)j0 * coutp * 16u) >> 4);
@@ -251,16 +258,16 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
               umma_bf16_elect(d, a_row + (uint64_t)((uint32_t)v * rb16 + (uint32_t)j * 2u),
                               b_seg + (uint64_t)((uint32_t)v * unit16 + (uint32_t)j * b_jstep), idesc, 1u);
         }
-        umma_commit_elect(bar_rempty + 8 * stage);                      // the row stage may be refilled
+        if (!(P.knock & 16)) umma_commit_elect(bar_rempty + 8 * stage);                      // the row stage may be refilled
         if (++stage == (uint32_t)L.RSn) { stage = 0; sph ^= 1u; }
         if (yi >= 2) {                                                  // output row yi - 2 is complete
-          umma_commit_elect(bar_sfull + 8 * cs);
+          if (!(P.knock & 8)) umma_commit_elect(bar_sfull + 8 * cs);
           if (++cs == NS) cs = 0;
         }
         if (yi < H && ++zs == NS) { zs = 0; zp ^= 1u; }
       }
-      rho += H;
-      if (rho < W.rho1 && rs_unit(W, rho, P.Hout, P.batch, L.Wv).grp != u.grp) umma_commit_elect(bar_wempty);
+      rs_advance(W, u);
+      if (rs_more(W) && rs_unit(W).grp != grp) umma_commit_elect(bar_wempty);
     }
   } else if (warp >= RS_EPI_WARP0 && warp < RS_EPI_WARP0 + 8) {
     // ===== epilogue: slot -> registers -> bias / activation -> bf16 -> per-warp compaction -> coalesced stores.  Warp w
@@ -278,8 +285,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     for (int i = tid - RS_EPI_WARP0 * 32; i < 3 * L.CoutP; i += RS_EPI) s_bias[i] = P.bias[i];
     asm volatile("bar.sync 2, %0;" ::"n"(RS_EPI) : "memory");
     uint32_t slot = 0, eph = 0, odd = 0;      // slot / barrier parity / row parity of the next output row of this CTA
-    for (long long rho = W.rho0; rho < W.rho1;) {
-      const RsUnit u = rs_unit(W, rho, P.Hout, P.batch, L.Wv);
+    for (RsWork W = W0; rs_more(W) && !(P.knock & 8);) {
+      const RsUnit u = rs_unit(W);
       const int H = u.y1 - u.y0;
       const float *bias = s_bias + u.grp * L.CoutP;
       // this lane's position: image and column
@@ -314,9 +321,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
           tmem_ld_wait();
           if (n0 + 32 >= L.CoutP) {          // everything of the slot is in registers: hand it back to the MMA issuer
             tc_fence_before();
-            mbar_arrive(bar_sempty + 8 * slot_o);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_sempty + 8 * slot_o);
           }
-          if (!ok) continue;
+          if (!ok || (P.knock & 4)) continue;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (h == 1 && !two) break;
@@ -348,7 +356,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
         __syncwarp();
         // rows of one image are contiguous in HBM; consecutive lanes copy consecutive 16-byte chunks
         const uint32_t rowoff = (uint32_t)(o * P.Wout);
-        for (uint32_t off = (uint32_t)lane * 16u; off < total; off += 512u) {
+        for (uint32_t off = (uint32_t)lane * 16u; off < total && !(P.knock & 4); off += 512u) {
           uint32_t row, ch;
           if (cprLog >= 0) { row = off >> (4 + cprLog); ch = (off >> 4) & (cpr - 1u); }
           else { row = off / rowB; ch = (off - row * rowB) >> 4; }
@@ -360,76 +368,93 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
         }
         __syncwarp();                                 // the staging buffer is rewritten by this warp's next row
       }
-      rho += H;
+      rs_advance(W, u);
     }
   } else if (warp < 8) {
-    // ===== loaders: one padded input row of the strip per stage; every thread owns one 16-byte channel chunk of up to
-    // RS_KP fixed positions =====
-    const int lt = tid;
-    const int chunk = lt & (L.S - 1), c = chunk * 8;
+    // ===== loaders: loader warp w gathers the input rows m = w (mod NW) of this CTA's row sequence, one whole row (130
+    // positions x Cin) per turn: consecutive lanes copy consecutive 16-byte chunks of consecutive positions.  Every lane owns
+    // a fixed channel chunk (32 % S == 0), i.e. a fixed source tensor / sampling mode.  NW = min(8, stages): with fewer than
+    // 8 stages every stage belongs to ONE warp, so a waiter is never more than one barrier phase ahead (parity waits). =====
+    const int NW = L.RSn < 8 ? L.RSn : 8;
+    const int chunk = lane & (L.S - 1), c = chunk * 8;
     const bool first = c < P.c0;
     const __nv_bfloat16 *src = first ? P.x0 : P.x1;
     const int C = first ? P.c0 : P.c1, cc = first ? c : c - P.c0, mode = first ? P.mode0 : P.mode1;
     const int32_t *tab = first ? P.tab0 : P.tab1;
     const int ppb = first ? P.ppb0 : P.ppb1;
     const bool chan_ok = c < P.cin;
-    const int pstep = RS_LOADERS >> L.logS, l0 = lt >> L.logS;
+    const int pstep = 32 >> L.logS, l0 = lane >> L.logS;
     const uint32_t cw = (uint32_t)chunk & ((1u << L.cprLog) - 1u);
     const bool pooled = mode == DLWPCS_SRC_POOL2;
     const int w2 = P.n * 2;
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    uint32_t stage = 0, sph = 0;
-    for (long long rho = W.rho0; rho < W.rho1;) {
-      const RsUnit u = rs_unit(W, rho, P.Hout, P.batch, L.Wv);
-      const int H = u.y1 - u.y0;
-      int tabofs[RS_KP], pixb[RS_KP];
-      uint32_t dsto[RS_KP];
-#pragma unroll
-      for (int k = 0; k < RS_KP; ++k) {
-        const int l = l0 + k * pstep;
-        const int p = u.sl * 128 + l;
-        const int img = p / L.Wv, cv = p - img * L.Wv;
-        int b, f;
-        rs_image(u.grp, img, b, f);
-        const bool inb = l < RS_NPOS;
-        tabofs[k] = (inb && p < u.Lg && chan_ok) ? f * L.G + cv : -1;
-        pixb[k] = b * ppb;
-        const uint32_t ro = (uint32_t)l * (uint32_t)L.RB;
-        dsto[k] = inb ? ro + ((cw ^ ((ro >> 7) & (uint32_t)L.swzMask)) << 4) : 0xFFFFFFFFu;
-      }
-      int pxn[RS_KP];
-#pragma unroll
-      for (int k = 0; k < RS_KP; ++k) pxn[k] = tabofs[k] >= 0 ? __ldg(tab + tabofs[k] + u.y0 * L.Wv) : -1;
-#pragma unroll 1
-      for (int yi = 0; yi < H + 2; ++yi) {
-        int px[RS_KP];
-#pragma unroll
-        for (int k = 0; k < RS_KP; ++k) px[k] = pxn[k];
-        if (yi + 1 < H + 2) {
-#pragma unroll
-          for (int k = 0; k < RS_KP; ++k) pxn[k] = tabofs[k] >= 0 ? __ldg(tab + tabofs[k] + (u.y0 + yi + 1) * L.Wv) : -1;
+    int2 *ptab = reinterpret_cast<int2 *>(gen + L.off_pos) + warp * RS_NPIXP;       // this warp's copy: {table offset, batch element}
+    // The patch-table entries of a row (source pixel of every position, for each of the two sources' sampling modes) are
+    // prefetched into shared memory one turn ahead with 4-byte asynchronous copies: no L2 round trip in front of the gathers.
+    const bool two_tabs = P.tab1 != P.tab0;
+    const uint32_t pxb = base + (uint32_t)L.off_px + (uint32_t)warp * (4u * RS_NPIXP * 4u);     // [2 buffers][2 tables][136]
+    const int *pxg = reinterpret_cast<const int *>(gen + L.off_px) + warp * (4 * RS_NPIXP);
+    const int mysel = (first || !two_tabs) ? 0 : RS_NPIXP;
+    auto prefetch = [&](int y, int bufi) {
+      for (int l = lane; l < RS_NPOS; l += 32) {
+        const int to = ptab[l].x;
+        const uint32_t dst = pxb + (uint32_t)(bufi * 2 * RS_NPIXP + l) * 4u;
+        if (to >= 0) {
+          cp_async4(dst, P.tab0 + to + y * L.Wv);
+          if (two_tabs) cp_async4(dst + RS_NPIXP * 4u, P.tab1 + to + y * L.Wv);
+        } else {
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(-1) : "memory");
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + RS_NPIXP * 4u), "r"(-1) : "memory");
         }
+      }
+      cp_async_commit();
+    };
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    uint32_t m = 0;                       // rows of this CTA's sequence before the current unit
+    for (RsWork W = W0; rs_more(W) && !(P.knock & 16) && warp < NW;) {
+      const RsUnit u = rs_unit(W);
+      const int H = u.y1 - u.y0;
+      // first row of the unit that is this warp's
+      int yi = (warp + NW - (int)(m % (uint32_t)NW)) % NW;
+      int cur = 0;
+      if (yi < H + 2) {
+        __syncwarp();
+        for (int l = lane; l < RS_NPOS; l += 32) {
+          const int p = u.sl * 128 + l;
+          const int img = p / L.Wv, cv = p - img * L.Wv;
+          int b, f;
+          rs_image(u.grp, img, b, f);
+          ptab[l] = make_int2(p < u.Lg ? f * L.G + cv : -1, b);
+        }
+        __syncwarp();
+        prefetch(u.y0 + yi, 0);
+      }
+#pragma unroll 1
+      for (; yi < H + 2; yi += NW) {
+        const uint32_t mm = m + (uint32_t)yi, stage = mm % (uint32_t)L.RSn, sph = (mm / (uint32_t)L.RSn) & 1u;
+        __syncwarp();                                     // everybody has finished reading the buffer that is refilled now
+        if (yi + NW < H + 2) prefetch(u.y0 + yi + NW, cur ^ 1);
+        else cp_async_commit();
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
         rs_wait(bar_rempty + 8 * stage, sph ^ 1u, P.err, 3);
         const uint32_t sbase = rows0 + stage * (uint32_t)L.stageBytes;
-        if (!pooled) {
-#pragma unroll
-          for (int k = 0; k < RS_KP; ++k) {
-            if (dsto[k] != 0xFFFFFFFFu) {
-              const __nv_bfloat16 *g = px[k] >= 0 ? src + ((size_t)(pixb[k] + px[k]) * C + cc) : P.x0;
-              cp_async16(sbase + dsto[k], g, px[k] >= 0 ? 16u : 0u);
-            }
-          }
-          fence_proxy_async();
-          cp_async_mbar_arrive(bar_rfull + 8 * stage);
-        } else {
-          // 2x2 mean (AveragePooling3D((1,2,2)), train_cs.py:197) through registers; rounded to bf16 once, like a stored
-          // pooled tensor
-#pragma unroll
-          for (int k = 0; k < RS_KP; ++k) {
-            if (dsto[k] != 0xFFFFFFFFu) {
+        const int *pxrow = pxg + cur * 2 * RS_NPIXP + mysel;
+        cur ^= 1;
+        if (!(P.knock & 1)) {
+#pragma unroll 4
+          for (int l = l0; l < RS_NPOS; l += pstep) {
+            const int px = chan_ok ? pxrow[l] : -1;
+            const uint32_t ro = (uint32_t)l * (uint32_t)L.RB;
+            const uint32_t dst = sbase + ro + ((cw ^ ((ro >> 7) & (uint32_t)L.swzMask)) << 4);
+            if (!pooled) {
+              const __nv_bfloat16 *g = px >= 0 ? src + ((size_t)(ptab[l].y * ppb + px) * C + cc) : P.x0;
+              cp_async16(dst, g, px >= 0 ? 16u : 0u);
+            } else {
+              // 2x2 mean (AveragePooling3D((1,2,2)), train_cs.py:197) through registers; rounded to bf16 once, like a
+              // stored pooled tensor
               uint4 o4 = make_uint4(0, 0, 0, 0);
-              if (px[k] >= 0) {
-                const __nv_bfloat16 *g = src + ((size_t)(pixb[k] + px[k]) * C + cc);
+              if (px >= 0) {
+                const __nv_bfloat16 *g = src + ((size_t)(ptab[l].y * ppb + px) * C + cc);
                 const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(g));
                 const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(g + C));
                 const uint4 v2 = __ldg(reinterpret_cast<const uint4 *>(g + (size_t)w2 * C));
@@ -438,25 +463,26 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
                 unpack_bf16x8(v0, a);
                 unpack_bf16x8(v1, t);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) a[e] += t[e];
+                for (int q = 0; q < 8; ++q) a[q] += t[q];
                 unpack_bf16x8(v2, t);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) a[e] += t[e];
+                for (int q = 0; q < 8; ++q) a[q] += t[q];
                 unpack_bf16x8(v3, t);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) a[e] += t[e];
+                for (int q = 0; q < 8; ++q) a[q] += t[q];
                 o4 = make_uint4(pack_bf16x2(0.25f * a[0], 0.25f * a[1]), pack_bf16x2(0.25f * a[2], 0.25f * a[3]),
                                 pack_bf16x2(0.25f * a[4], 0.25f * a[5]), pack_bf16x2(0.25f * a[6], 0.25f * a[7]));
               }
-              st_shared16(sbase + dsto[k], o4);
+              st_shared16(dst, o4);
             }
           }
-          fence_proxy_async();
-          mbar_arrive(bar_rfull + 8 * stage);
         }
-        if (++stage == (uint32_t)L.RSn) { stage = 0; sph ^= 1u; }
+        // the row is published when this lane's copies have landed (register-path stores are already visible)
+        fence_proxy_async();
+        cp_async_mbar_arrive(bar_rfull + 8 * stage);
       }
-      rho += H;
+      m += (uint32_t)(H + 2);
+      rs_advance(W, u);
     }
   }
   tc_fence_before();
@@ -505,6 +531,10 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
   if (d->stride_h != 1 || d->stride_w != 1 || d->dil_h != 1 || d->dil_w != 1) return "stride / dilation 1 only";
   if (d->x_dtype != DLWPCS_BF16 || d->y_dtype != DLWPCS_BF16) return "bf16 in, bf16 out";
   if (d->cout % 8 || d->c0 % 8 || d->c1 % 8) return "channel counts must be multiples of 8";
+  // a 2x2-pooled source goes through registers (four loads + mean per chunk); with one warp per row too few bytes are in
+  // flight -- the classic kernel's 256-thread gather is faster (measured: 34.8 vs 42 us for 32 -> 64 at 24 x 24, batch 64)
+  if ((d->mode0 == DLWPCS_SRC_POOL2 || (d->c1 > 0 && d->mode1 == DLWPCS_SRC_POOL2)) && !rs_env_int("DLWPCS_RS_POOL", 0))
+    return "pooled sources stay on the classic kernel";
   L->CinP = (d->cin + 15) / 16 * 16;
   if (L->CinP > 32) L->CinP = (d->cin + 63) / 64 * 64;
   if (L->CinP > 64) return "more than 64 input channels";
@@ -532,7 +562,9 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
   L->off_w = 0;        // filled below, after the row stages
   const int wB = (L->groupBytes + 1023) / 1024 * 1024;
   const int zeroB = 2 * L->CoutP * 16;
-  const int fixed = wB + (zeroB + 127) / 128 * 128 + 1024 + (3 * L->CoutP * 4 + 127) / 128 * 128 + 8 * 32 * 4 +
+  // per loader warp: {table offset, batch element} of the strip's positions + two double-buffered rows of table entries
+  const int posB = 8 * RS_NPIXP * 8 + 8 * 4 * RS_NPIXP * 4;
+  const int fixed = wB + (zeroB + 127) / 128 * 128 + 1024 + (3 * L->CoutP * 4 + 127) / 128 * 128 + 8 * 32 * 4 + posB +
                     8 * L->stgBytes + 1024 /* alignment slack */;
   int rsn = (RS_SMEM_CAP - fixed) / L->stageBytes;
   const int want = rs_env_int("DLWPCS_RS_STAGES", RS_MAXSTAGES);
@@ -546,6 +578,8 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
   L->off_misc = off; off += 1024;
   L->off_bias = off; off += (3 * L->CoutP * 4 + 127) / 128 * 128;
   L->off_pix = off; off += 8 * 32 * 4;
+  L->off_pos = off; off += 8 * RS_NPIXP * 8;
+  L->off_px = off; off += 8 * 4 * RS_NPIXP * 4;
   L->off_stg = off; off += 8 * L->stgBytes;
   L->smemBytes = off + 1024;
   return nullptr;
@@ -561,7 +595,8 @@ int rs_num_sms() {
   return sms[dev];
 }
 
-unsigned *g_rs_err[kMaxDevices] = {};
+unsigned *g_rs_err[kMaxDevices] = {};        // device pointers of ...
+unsigned *g_rs_err_host[kMaxDevices] = {};   // ... mapped pinned host words: a watchdog code survives the trapped context
 
 }  // namespace
 
@@ -594,6 +629,17 @@ int rs_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_c
 
 int rs_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed, void *y,
                 cudaStream_t st) {
+  {
+    const int dv = current_device_index();
+    if (g_rs_err_host[dv] && *(volatile unsigned *)g_rs_err_host[dv]) {
+      const unsigned c = *(volatile unsigned *)g_rs_err_host[dv];
+      set_error("row-streamed kernel: a pipeline wait timed out (role %u, parity %u, barrier offset 0x%x, CTA %u)", c & 15u,
+                (c >> 4) & 1u, (c >> 8) & 0xFFFu, c >> 20);
+      fprintf(stderr, "[dlwpcs] row-streamed kernel watchdog: role %u parity %u barrier 0x%x CTA %u\n", c & 15u, (c >> 4) & 1u,
+              (c >> 8) & 0xFFFu, c >> 20);
+      return 4;
+    }
+  }
   RsP P;
   memset(&P, 0, sizeof(P));
   const char *r = rs_make_plan(d, g, &P.L);
@@ -625,8 +671,9 @@ int rs_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, co
   if (d->batch == 0) return 0;
   const int dev_i = current_device_index();
   if (!g_rs_err[dev_i]) {
-    CS_CUDA(cudaMalloc(&g_rs_err[dev_i], sizeof(unsigned)));
-    CS_CUDA(cudaMemset(g_rs_err[dev_i], 0, sizeof(unsigned)));
+    CS_CUDA(cudaHostAlloc((void **)&g_rs_err_host[dev_i], sizeof(unsigned), cudaHostAllocMapped));
+    *g_rs_err_host[dev_i] = 0u;
+    CS_CUDA(cudaHostGetDevicePointer((void **)&g_rs_err[dev_i], g_rs_err_host[dev_i], 0));
   }
   P.err = g_rs_err[dev_i];
   typedef void (*kern_t)(const RsP);
@@ -640,12 +687,25 @@ int rs_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, co
   }
   const long long strips = (4LL * d->batch * L.Wv + 127) / 128 + 2 * ((1LL * d->batch * L.Wv + 127) / 128);
   const long long R = strips * g.Hout;
-  CS_CHECK(R < (1LL << 40), "batch too large");
-  P.snap = g.Hout >= 16 ? 4 : (g.Hout >= 8 ? 2 : 1);
+  CS_CHECK(R < (1LL << 30), "batch too large");
+  static const int knock = rs_env_int("DLWPCS_RS_KNOCK", 0);
+  P.knock = knock;
+  // equal shares of the (strip, output row) sequence; a cut closer than `snap` rows to a strip boundary moves onto it (a
+  // unit of h output rows streams h + 2 input rows)
+  const int snap = g.Hout >= 16 ? 4 : (g.Hout >= 8 ? 2 : 1);
   int grid = rs_num_sms();
+  if (grid > RS_MAXGRID) grid = RS_MAXGRID;
   const long long min_rows = 4;
   if ((long long)grid * min_rows > R) grid = (int)((R + min_rows - 1) / min_rows);
   if (grid < 1) grid = 1;
+  for (int c = 0; c <= grid; ++c) {
+    long long b = (long long)c * R / grid;
+    const int r = (int)(b % g.Hout);
+    if (r < snap) b -= r;
+    else if (r > g.Hout - snap) b += g.Hout - r;
+    P.cut_s[c] = (int)(b / g.Hout);
+    P.cut_y[c] = (int)(b % g.Hout);
+  }
   static const int pdl = rs_env_int("DLWPCS_TC_PDL", 1);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
