@@ -176,19 +176,32 @@ def time_layers(eng, flush, reps=10):
     126 MB L2 still holds), not a layer-private warm L2.  Median over the repetitions.  -> list of (name, ms)"""
     from dlwp_cs_b200 import _lib
     launches = []
-    for name, d, s0, s1, dst, packed in eng.plan:
+    fused = getattr(eng, 'fused_head', None)
+    for i, (name, d, s0, s1, dst, packed) in enumerate(eng.plan):
+        if fused is not None and i == fused + 1:
+            continue
         o = eng.ring[0] if dst == 'out' else eng.buf[dst]
-        launches.append((name, d, eng._src(s0, 0), eng._src(s1, 0), packed, o))
-    for _ in range(3):
-        for name, d, a, b, packed, o in launches:
+        if fused is not None and i == fused:          # the 1x1 output layer runs inside this launch
+            head = eng.plan[i + 1]
+            launches.append((name + '+' + head[0], d, eng._src(s0, 0), eng._src(s1, 0), packed, eng.ring[0], head))
+        else:
+            launches.append((name, d, eng._src(s0, 0), eng._src(s1, 0), packed, o, None))
+
+    def go(d, a, b, packed, o, head):
+        if head is None:
             _lib.conv2d_fwd(d, a, b, packed, out=o)
+        else:
+            _lib.conv2d_fwd_head(d, a, b, packed, head[1], head[5], out=o)
+    for _ in range(3):
+        for name, d, a, b, packed, o, head in launches:
+            go(d, a, b, packed, o, head)
     times = {name: [] for name, *_ in launches}
     for _ in range(reps):
         flush.zero_()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(launches) + 1)]
         evs[0].record()
-        for i, (name, d, a, b, packed, o) in enumerate(launches):
-            _lib.conv2d_fwd(d, a, b, packed, out=o)
+        for i, (name, d, a, b, packed, o, head) in enumerate(launches):
+            go(d, a, b, packed, o, head)
             evs[i + 1].record()
         torch.cuda.synchronize()
         for i, (name, *_r) in enumerate(launches):
@@ -410,8 +423,13 @@ def main():
         edges = {name: d.n for name, d, *_ in eng.plan}
         tot = sum(ms for _, ms in lt)
         for name, ms in lt:
-            _, k, ci, co = specs[name]
-            flop, byts = layer_work(k, ci, co, edges[name], args.batch, esz, esz)
+            # a fused launch ('a+b') carries the algorithmic work of both layers (SURVEY 8(d) counts each layer's input
+            # and output; the fused launch moves fewer bytes than that)
+            flop = byts = 0.0
+            for part in name.split('+'):
+                _, k, ci, co = specs[part]
+                f_, b_ = layer_work(k, ci, co, edges[part], args.batch, esz, esz)
+                flop, byts = flop + f_, byts + b_
             tf, gb = flop / ms / 1e9, byts / ms / 1e6
             t_c = flop / (pk['tf_sust'] * 1e12) if dtype == 'bf16' else 0.0
             t_m = byts / (pk['hbm'] * 1e9)

@@ -83,6 +83,8 @@ def load():
         'dlwpcs_pack_weights2': (i32, [dp, wp, i32, i32, vp, vp, vp]),
         'dlwpcs_pad_bwd_act': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, i32, vp]),
         'dlwpcs_conv2d_dgrad_act': (i32, [dp, vp, vp, vp, vp, vp, vp, i32, f32, f32, vp]),
+        'dlwpcs_conv2d_head_fusable': (i32, [dp, dp]),
+        'dlwpcs_conv2d_fwd_head': (i32, [dp, vp, vp, vp, dp, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)          # AttributeError here == header and library out of sync
@@ -100,7 +102,8 @@ EXPORTED = ('dlwpcs_version', 'dlwpcs_last_error', 'dlwpcs_conv_out_edge', 'dlwp
             'dlwpcs_mse_loss_grad', 'dlwpcs_adam_step', 'dlwpcs_adam_step_dev', 'dlwpcs_insolation', 'dlwpcs_pool2',
             'dlwpcs_up2cat_fwd', 'dlwpcs_up2cat_bwd', 'dlwpcs_feed_gather', 'dlwpcs_trace_read',
             'dlwpcs_conv2d_fwd_chained', 'dlwpcs_chain_target', 'dlwpcs_split3',
-            'dlwpcs_pack_weights2', 'dlwpcs_pad_bwd_act', 'dlwpcs_conv2d_dgrad_act')
+            'dlwpcs_pack_weights2', 'dlwpcs_pad_bwd_act', 'dlwpcs_conv2d_dgrad_act', 'dlwpcs_conv2d_head_fusable',
+            'dlwpcs_conv2d_fwd_head')
 
 
 class DlwpcsError(RuntimeError):
@@ -240,6 +243,20 @@ def conv2d_fwd(d, x0, x1, packed, out=None):
     ydt = torch.float32 if d.y_dtype == F32 else torch.bfloat16
     y = out if out is not None else torch.empty(shp, dtype=ydt, device=x0.device)
     check(load().dlwpcs_conv2d_fwd(ctypes.byref(d), ptr(x0), ptr(x1), ptr(packed), ptr(y), stream_ptr()))
+    return y
+
+
+def conv2d_head_fusable(d, head):
+    """True when `head` (a 1x1 CubeSphereConv2D reading only the output of `d`) can run inside the epilogue of `d`."""
+    return bool(load().dlwpcs_conv2d_head_fusable(ctypes.byref(d), ctypes.byref(head)))
+
+
+def conv2d_fwd_head(d, x0, x1, packed, head, head_packed, out=None):
+    """dlwpcs_conv2d_fwd_head: the 3x3 layer `d` and its 1x1 consumer `head` in one launch; returns the head's output."""
+    require_cuda(x0, x1, packed, head_packed, out)
+    y = out if out is not None else torch.empty(out_shape(head), dtype=torch.bfloat16, device=x0.device)
+    check(load().dlwpcs_conv2d_fwd_head(ctypes.byref(d), ptr(x0), ptr(x1), ptr(packed), ctypes.byref(head), ptr(head_packed),
+                                        ptr(y), stream_ptr()))
     return y
 
 

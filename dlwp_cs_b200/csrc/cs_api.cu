@@ -1000,6 +1000,24 @@ int dlwpcs_conv2d_fwd(const dlwpcs_conv_desc *d, const void *x0, const void *x1,
                        (cudaStream_t)stream);
 }
 
+int dlwpcs_conv2d_head_fusable(const dlwpcs_conv_desc *d, const dlwpcs_conv_desc *head) {
+  Geometry g, gh;
+  if (!d || !head || check_common(d, &g) || check_common(head, &gh)) return 0;
+  return rs_head_eligible(d, g, head) ? 1 : 0;
+}
+
+int dlwpcs_conv2d_fwd_head(const dlwpcs_conv_desc *d, const void *x0, const void *x1, const void *packed_w,
+                           const dlwpcs_conv_desc *head, const void *head_packed_w, void *y_head, void *stream) {
+  Geometry g, gh;
+  if (int rc = check_common(d, &g)) return rc;
+  CS_CHECK(head != nullptr, "null head descriptor");
+  if (int rc = check_common(head, &gh)) return rc;
+  CS_CHECK(rs_head_eligible(d, g, head), "this pair of layers cannot be fused (dlwpcs_conv2d_head_fusable)");
+  if (d->batch == 0) return 0;
+  CS_CHECK(x0 && packed_w && head_packed_w && y_head && (d->c1 == 0 || x1), "null tensor pointer");
+  return rs_conv_fwd_head(d, g, x0, x1, packed_w, head, head_packed_w, y_head, (cudaStream_t)stream);
+}
+
 int dlwpcs_conv2d_fwd_chained(const dlwpcs_conv_desc *d, const void *x0, const void *x1, const void *packed_w, void *y,
                               const dlwpcs_chain *chain, void *stream) {
   Geometry g;

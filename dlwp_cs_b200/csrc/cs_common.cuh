@@ -82,6 +82,7 @@ int tc_conv_dgrad(const dlwpcs_conv_desc *d, const Geometry &g, const void *dy, 
                   void *dx, void *workspace, const void *x_in, int in_act, float in_slope, float in_max, cudaStream_t st);
 
 int tc_trace_read(unsigned long long *host_out, int max_launches, int *n_launches, int reset);
+unsigned long long *tc_trace_next(int grid);
 
 // row-streamed kernel (cs_tc_rs.cu): 3x3, stride 1, bf16 in / out, <= 64 input and <= 80 output channels; the three kernel
 // rows are stacked along N.  Its packed-weight image differs from the classic one; dlwpcs_conv2d_fwd uses it whenever
@@ -92,6 +93,12 @@ int rs_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_c
                     void *packed, cudaStream_t st);
 int rs_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed, void *y,
                 cudaStream_t st);
+// 3x3 layer + the 1x1 CubeSphereConv2D that is its only consumer (the output layer of every cubed-sphere network,
+// Azure/train_cs.py:228) in one launch: a second MMA per output row inside the epilogue; the 3x3 layer's output never
+// reaches HBM.  packed_h = the head's classic packed image.
+bool rs_head_eligible(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_desc *dh);
+int rs_conv_fwd_head(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed,
+                     const dlwpcs_conv_desc *dh, const void *packed_h, void *y2, cudaStream_t st);
 
 // patch table of a linearised virtual face (width Wv, G entries per face): physical source pixel or -1; cached per device
 const int32_t *get_patch_table(const Geometry &g, int Wv, int G, int n, int halo, int mode);

@@ -1034,6 +1034,9 @@ int num_sms() {
 
 unsigned long long *g_trace = nullptr;      // [TRACE_LAUNCHES][TRACE_CTAS][8]
 int g_trace_launches = 0;
+}  // namespace
+unsigned long long *tc_trace_next(int grid);
+namespace {
 
 int launch_tc(TcP &P, cudaStream_t st) {
   const TcPlan &L = P.pl_;
@@ -1069,15 +1072,7 @@ int launch_tc(TcP &P, cudaStream_t st) {
     CS_CUDA(cudaMemset(dbg, 0, 16 * sizeof(long long)));
     P.dbg = dbg;
   }
-  static const int tracing = env_int("DLWPCS_TC_TRACE", 0);
-  if (tracing && grid <= TRACE_CTAS) {
-    if (!g_trace) {
-      CS_CUDA(cudaMalloc(&g_trace, sizeof(unsigned long long) * TRACE_LAUNCHES * TRACE_CTAS * 8));
-      CS_CUDA(cudaMemset(g_trace, 0, sizeof(unsigned long long) * TRACE_LAUNCHES * TRACE_CTAS * 8));
-    }
-    P.trace = g_trace + (size_t)(g_trace_launches % TRACE_LAUNCHES) * TRACE_CTAS * 8;
-    ++g_trace_launches;
-  }
+  P.trace = tc_trace_next(grid);
   static const int pdl = env_int("DLWPCS_TC_PDL", 1);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -1107,6 +1102,19 @@ int launch_tc(TcP &P, cudaStream_t st) {
 }
 
 }  // namespace
+
+// trace slot of the next traced launch (nullptr when tracing is off / the grid does not fit); shared with cs_tc_rs.cu
+unsigned long long *tc_trace_next(int grid) {
+  static const int tracing = env_int("DLWPCS_TC_TRACE", 0);
+  if (!tracing || grid > TRACE_CTAS) return nullptr;
+  if (!g_trace) {
+    if (cudaMalloc(&g_trace, sizeof(unsigned long long) * TRACE_LAUNCHES * TRACE_CTAS * 8) != cudaSuccess) return nullptr;
+    cudaMemset(g_trace, 0, sizeof(unsigned long long) * TRACE_LAUNCHES * TRACE_CTAS * 8);
+  }
+  unsigned long long *p = g_trace + (size_t)(g_trace_launches % TRACE_LAUNCHES) * TRACE_CTAS * 8;
+  ++g_trace_launches;
+  return p;
+}
 
 int tc_trace_read(unsigned long long *host_out, int max_launches, int *n_launches, int reset) {
   const int n = g_trace_launches < TRACE_LAUNCHES ? g_trace_launches : TRACE_LAUNCHES;

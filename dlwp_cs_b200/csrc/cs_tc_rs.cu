@@ -54,6 +54,8 @@ struct RsPlan {
   int unitBytes, groupBytes;         // weights of one (kernel column) unit / of one face group
   int stgBytes;                      // output staging per epilogue warp
   int off_w, off_zero, off_misc, off_bias, off_pix, off_pos, off_px, off_stg, smemBytes;
+  // fused 1x1 head (conv_rs_kernel<.., true>): a second MMA per output row inside the epilogue
+  int head, CoutP2, hwBytes, off_hw, off_hbias, off_a2;
 };
 
 struct RsP {
@@ -62,15 +64,31 @@ struct RsP {
   const uint8_t *wpack;
   const float *bias;                 // [3][CoutP]
   __nv_bfloat16 *y;
+  const uint8_t *hw;                 // head: packed 1x1 weights [3][k8][CoutP2][8] (the classic kernel's image)
+  const float *hbias;                // head: [3][CoutP2]
+  __nv_bfloat16 *y2;                 // head output (B,6,Hout,Wout,cout2); y is not written
+  int cout2, act2;
+  float slope2, maxv2;
   int batch, n, Hout, Wout;
   int cin, cout, c0, c1, mode0, mode1, ppb0, ppb1;
   int act;
   float slope, maxv;
   int knock;                         // bottleneck analysis (DLWPCS_RS_KNOCK): 1 no gathers, 2 no MMAs, 4 no epilogue math / stores
   int cut_s[RS_MAXGRID + 1], cut_y[RS_MAXGRID + 1];     // CTA c works on [(cut_s[c], cut_y[c]), (cut_s[c+1], cut_y[c+1]))
+  unsigned long long *trace;         // optional per-CTA %globaltimer stamps (DLWPCS_TC_TRACE=1), same slots as cs_tc.cu
   unsigned *err;                     // watchdog flag (a barrier wait that never completes traps instead of hanging the GPU)
   RsPlan L;
 };
+
+// cross-kernel timeline (DLWPCS_TC_TRACE=1, tools/trace_step.py): slot 0 kernel entry, 1 prologue done, 2 loaders past the
+// grid dependency, 3 first input row landed, 4 first output row complete, 5 last epilogue done, 6 kernel exit, 7 units
+__device__ __forceinline__ void rs_trace(const RsP &P, int slot, bool who) {
+  if (P.trace && who) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.trace[blockIdx.x * 8 + slot] = t;
+  }
+}
 
 // Bounded barrier wait: ~2^26 polls (seconds) then flag + trap.  A pipeline bug must not hang the GPU box.
 __device__ __forceinline__ void rs_wait(uint32_t bar, uint32_t parity, unsigned *err, int code) {
@@ -136,7 +154,7 @@ __device__ __forceinline__ void rs_image(int grp, int i, int &b, int &f) {
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------
-template <int KC16T>
+template <int KC16T, bool HEAD>
 __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_constant__ RsP P) {
   extern __shared__ uint8_t smem_raw[];
   const RsPlan &L = P.L;
@@ -145,12 +163,13 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
   const uint32_t rows0 = base, wbase = base + L.off_w, zbase = base + L.off_zero, misc = base + L.off_misc;
   // barriers (8 bytes each): rfull[16] rempty[16] sfull[16] sempty[16] wfull wempty; tensor-memory slot
   const uint32_t bar_rfull = misc, bar_rempty = misc + 128, bar_sfull = misc + 256, bar_sempty = misc + 384,
-                 bar_wfull = misc + 512, bar_wempty = misc + 520, tmem_slot = misc + 528;
+                 bar_wfull = misc + 512, bar_wempty = misc + 520, tmem_slot = misc + 528, bar_hfull = misc + 544;
   float *s_bias = reinterpret_cast<float *>(gen + L.off_bias);
   int *s_pix = reinterpret_cast<int *>(gen + L.off_pix);
   const uint32_t stg0 = base + L.off_stg;
 
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  rs_trace(P, 0, tid == 0);
 
   RsWork W0;
   W0.s = P.cut_s[blockIdx.x]; W0.y0 = P.cut_y[blockIdx.x];
@@ -170,6 +189,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     }
     mbar_init(bar_wfull, 1);
     mbar_init(bar_wempty, 1);
+    mbar_init(bar_hfull, 1);
+    mbar_init(bar_hfull + 8, 1);
     fence_mbar_init();
   }
   // the zero B operand of the slot-clearing MMA
@@ -183,6 +204,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
   // programmatic dependent launch (see cs_tc.cu): whatever a previous kernel may have written -- activations (loaders),
   // packed weights (TMA lane), bias (epilogue) -- is read behind griddepcontrol.wait
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  rs_trace(P, 1, tid == 0);
 
   if (warp == RS_TMA_WARP) {
     // ===== weight producer: the whole stacked weight set of a face group, once per group change =====
@@ -192,14 +214,19 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
       for (RsWork W = W0; rs_more(W);) {
         const RsUnit u = rs_unit(W);
         if (u.grp != prev) {
+          const bool prev_was_none = prev < 0;
           if (prev >= 0) { rs_wait(bar_wempty, eph, P.err, 1); eph ^= 1; }
           prev = u.grp;
           const uint8_t *wg = P.wpack + (size_t)u.grp * L.groupBytes;
-          mbar_expect_tx(bar_wfull, (uint32_t)L.groupBytes);
+          // the head's weights of all three face groups stay resident (loaded with the first main set): the epilogue's MMAs
+          // of a group's last rows may still be in flight when the main weights of the next group arrive
+          const bool hload = HEAD && prev_was_none;
+          mbar_expect_tx(bar_wfull, (uint32_t)(L.groupBytes + (hload ? 3 * L.hwBytes : 0)));
           for (int o = 0; o < L.groupBytes; o += 32768) {
             const int bytes = min(32768, L.groupBytes - o);
             tma_bulk_g2s(wbase + (uint32_t)o, wg + o, (uint32_t)bytes, bar_wfull);
           }
+          if (hload) tma_bulk_g2s(base + (uint32_t)L.off_hw, P.hw, (uint32_t)(3 * L.hwBytes), bar_wfull);
         }
         rs_advance(W, u);
       }
@@ -221,6 +248,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     // output row that the current input row completes (cs)
     uint32_t stage = 0, sph = 0, zs = 0, zp = 1, cs = 0;
     int prev = -1, fph = 0;
+    bool traced = false;
     for (RsWork W = W0; rs_more(W);) {
       const RsUnit u = rs_unit(W);
       const int H = u.y1 - u.y0, grp = u.grp;
@@ -236,6 +264,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
         if (!(P.knock & 16)) RS_WAIT_MMA(bar_rfull + 8 * stage, sph, 5);
         if (yi < H && !(P.knock & 8)) RS_WAIT_MMA(bar_sempty + 8 * zs, zp, 6);   // first touch of this slot: it must have been drained
         tc_fence_after();
+        if (P.trace && !traced) { rs_trace(P, 3, lane == 0); traced = true; }
         fence_proxy_async();               // the loaders' generic-proxy writes, acquired through the barrier, before the MMAs' reads
         const uint64_t a_row = a_fix | ((rows0 + stage * (uint32_t)L.stageBytes) >> 4);
         if (yi < H && !(P.knock & 2)) umma_bf16_elect(tmem_base + zs * coutp, a_row, z_desc, idesc0 | ((coutp >> 3) << 17), 0u);
@@ -284,6 +313,167 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     asm volatile("griddepcontrol.wait;" ::: "memory");        // the bias sits behind the packed weights
     for (int i = tid - RS_EPI_WARP0 * 32; i < 3 * L.CoutP; i += RS_EPI) s_bias[i] = P.bias[i];
     asm volatile("bar.sync 2, %0;" ::"n"(RS_EPI) : "memory");
+    int nunits = 0;
+    bool etraced = false;
+    if constexpr (HEAD) {
+    // ---- fused 1x1 head: the activated bf16 row is written as the A tile of a second MMA (K = CoutP, N = CoutP2) against
+    // the resident head weights; its accumulators are read back one turn later, while the tensor core works on the next row
+    const uint32_t RBh = (uint32_t)L.CoutP * 2u, hmask = (RBh >> 4) - 1u;
+    const uint32_t a2 = base + (uint32_t)L.off_a2 + (uint32_t)half * (128u * RBh);
+    const float *s_hbias = reinterpret_cast<const float *>(gen + L.off_hbias);
+    const uint32_t d2 = tmem_base + (uint32_t)(L.NS * L.CoutP + half * L.CoutP2);
+    const uint32_t bar_h = bar_hfull + 8u * (uint32_t)half;
+    const uint32_t rowB2 = (uint32_t)P.cout2 * 2u, cpr2 = rowB2 >> 4;
+    const int cprLog2 = (cpr2 & (cpr2 - 1)) == 0 ? 31 - __clz(cpr2) : -1;
+    const uint32_t smask2 = (cpr2 & (cpr2 - 1)) == 0 ? min(cpr2, 8u) - 1u : 0u;
+    const uint64_t a2desc = (((uint64_t)(((8u * RBh) >> 4) | (1u << 14) | ((RBh == 128u ? 2u : 4u) << 29)) << 32) | (1ull << 16)) |
+                            (a2 >> 4);
+    const uint64_t b2fix = ((uint64_t)((128u >> 4) | (1u << 14)) << 32) | ((uint64_t)((uint32_t)L.CoutP2 & 0x3FFFu) << 16);
+    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (8u << 24) | (((uint32_t)L.CoutP2 >> 3) << 17);
+    const bool act2_fast = P.act2 == DLWPCS_ACT_CAPPED_LEAKY_RELU && P.slope2 >= 0.f && P.slope2 <= 1.f;
+    for (int i = tid - RS_EPI_WARP0 * 32; i < 3 * L.CoutP2; i += RS_EPI) const_cast<float *>(s_hbias)[i] = P.hbias[i];
+    asm volatile("bar.sync 2, %0;" ::"n"(RS_EPI) : "memory");
+    uint32_t slot = 0, eph = 0, odd = 0, hph = 0;
+    for (RsWork W = W0; rs_more(W) && !(P.knock & 8);) {
+      const RsUnit u = rs_unit(W);
+      const int H = u.y1 - u.y0;
+      const float *bias = s_bias + u.grp * L.CoutP;
+      const float *bias2 = s_hbias + u.grp * L.CoutP2;
+      const uint64_t b2desc = b2fix | ((base + (uint32_t)L.off_hw + (uint32_t)(u.grp * L.hwBytes)) >> 4);
+      const int p = u.sl * 128 + quarter * 32 + lane;
+      const int img = p / L.Wv, cv = p - img * L.Wv;
+      const bool ok = p < u.Lg && cv < P.Wout;
+      int b, f;
+      rs_image(u.grp, img, b, f);
+      const int opix0 = ((b * 6 + f) * P.Hout + u.y0) * P.Wout + cv;
+      const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+      const int nvalid = __popc(okmask);
+      const uint32_t prow = (uint32_t)__popc(okmask & ((1u << lane) - 1u));
+      __syncwarp();
+      if (ok) pixw[prow] = opix0;
+      __syncwarp();
+      const uint32_t srow = stg + prow * rowB2;
+      const uint32_t total = (uint32_t)nvalid * rowB2;
+      const uint32_t arow = a2 + (uint32_t)(quarter * 32 + lane) * RBh;
+      const uint32_t aswz = (((uint32_t)(quarter * 32 + lane) * RBh) >> 7) & hmask;
+      int pend = -1;                          // output row (within the unit) whose head accumulators are still in tensor memory
+      // read the head accumulators of row `po`, finish (bias, activation, bf16), compact and store
+      auto finish = [&](int po) {
+        rs_wait(bar_h, hph, P.err, 7);
+        hph ^= 1u;
+        tc_fence_after();
+        for (int n0 = 0; n0 < L.CoutP2; n0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(d2 + ((uint32_t)(quarter * 32) << 16) + (uint32_t)n0, v);
+          tmem_ld_wait();
+          if (!ok) continue;
+          float r[16];
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const float4 bv = *reinterpret_cast<const float4 *>(bias2 + n0 + 4 * k4);
+            r[4 * k4 + 0] = __uint_as_float(v[4 * k4 + 0]) + bv.x;
+            r[4 * k4 + 1] = __uint_as_float(v[4 * k4 + 1]) + bv.y;
+            r[4 * k4 + 2] = __uint_as_float(v[4 * k4 + 2]) + bv.z;
+            r[4 * k4 + 3] = __uint_as_float(v[4 * k4 + 3]) + bv.w;
+          }
+          if (act2_fast) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r[e] = fminf(fmaxf(r[e], P.slope2 * r[e]), P.maxv2);
+          } else if (P.act2 != DLWPCS_ACT_NONE) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r[e] = act_apply(r[e], P.act2, P.slope2, P.maxv2);
+          }
+          if (n0 + 8 <= P.cout2)
+            st_shared16(srow + ((((uint32_t)n0 >> 3) ^ (prow & smask2)) << 4),
+                        make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7])));
+          if (n0 + 16 <= P.cout2)
+            st_shared16(srow + (((((uint32_t)n0 >> 3) + 1u) ^ (prow & smask2)) << 4),
+                        make_uint4(pack_bf16x2(r[8], r[9]), pack_bf16x2(r[10], r[11]), pack_bf16x2(r[12], r[13]), pack_bf16x2(r[14], r[15])));
+        }
+        tc_fence_before();
+        __syncwarp();
+        const uint32_t rowoff = (uint32_t)(po * P.Wout);
+        for (uint32_t off = (uint32_t)lane * 16u; off < total; off += 512u) {
+          uint32_t row, ch;
+          if (cprLog2 >= 0) { row = off >> (4 + cprLog2); ch = (off >> 4) & (cpr2 - 1u); }
+          else { row = off / rowB2; ch = (off - row * rowB2) >> 4; }
+          uint4 q;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                       : "r"(stg + row * rowB2 + ((ch ^ (row & smask2)) << 4)));
+          uint8_t *gdst = reinterpret_cast<uint8_t *>(P.y2) + ((size_t)((uint32_t)pixw[row] + rowoff)) * rowB2 + (ch << 4);
+          *reinterpret_cast<uint4 *>(gdst) = q;
+        }
+        __syncwarp();
+      };
+#pragma unroll 1
+      for (int o = 0; o < H; ++o) {
+        const uint32_t slot_o = slot, eph_o = eph, mine = ((int)odd == half);
+        odd ^= 1u;
+        if (++slot == NS) { slot = 0; eph ^= 1u; }
+        if (!mine) continue;
+        if (pend >= 0) finish(pend);          // frees this half's A tile and head accumulators
+        rs_wait(bar_sfull + 8 * slot_o, eph_o, P.err, 2);
+        tc_fence_after();
+        if (P.trace && !etraced) { rs_trace(P, 4, tid == RS_EPI_WARP0 * 32); etraced = true; }
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot_o * (uint32_t)L.CoutP;
+        for (int n0 = 0; n0 < L.CoutP; n0 += 32) {
+          uint32_t v[32];
+          const bool two = n0 + 16 < L.CoutP;
+          tmem_ld16(trow + (uint32_t)n0, v);
+          if (two) tmem_ld16(trow + (uint32_t)n0 + 16u, v + 16);
+          tmem_ld_wait();
+          if (n0 + 32 >= L.CoutP) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_sempty + 8 * slot_o);
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !two) break;
+            const int nb = n0 + 16 * h;
+            float r[16];
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const float4 bv = *reinterpret_cast<const float4 *>(bias + nb + 4 * k4);
+              r[4 * k4 + 0] = __uint_as_float(v[16 * h + 4 * k4 + 0]) + bv.x;
+              r[4 * k4 + 1] = __uint_as_float(v[16 * h + 4 * k4 + 1]) + bv.y;
+              r[4 * k4 + 2] = __uint_as_float(v[16 * h + 4 * k4 + 2]) + bv.z;
+              r[4 * k4 + 3] = __uint_as_float(v[16 * h + 4 * k4 + 3]) + bv.w;
+            }
+            if (act_fast) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) r[e] = fminf(fmaxf(r[e], P.slope * r[e]), P.maxv);
+            } else if (P.act != DLWPCS_ACT_NONE) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) r[e] = act_apply(r[e], P.act, P.slope, P.maxv);
+            }
+            // every lane writes its row of the A tile (rows of dropped lanes only feed their own, dropped, outputs)
+            st_shared16(arow + ((((uint32_t)nb >> 3) ^ aswz) << 4),
+                        make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7])));
+            st_shared16(arow + (((((uint32_t)nb >> 3) + 1u) ^ aswz) << 4),
+                        make_uint4(pack_bf16x2(r[8], r[9]), pack_bf16x2(r[10], r[11]), pack_bf16x2(r[12], r[13]), pack_bf16x2(r[14], r[15])));
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        if (half == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+        else asm volatile("bar.sync 4, 128;" ::: "memory");
+        if (quarter == 0) {
+          tc_fence_after();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j * 16 < L.CoutP)
+              umma_bf16_elect(d2, a2desc + (uint64_t)(2u * (uint32_t)j), b2desc + (uint64_t)((uint32_t)j * (uint32_t)(2 * L.CoutP2)), idesc2,
+                              j > 0 ? 1u : 0u);
+          umma_commit_elect(bar_h);
+        }
+        pend = o;
+      }
+      if (pend >= 0) finish(pend);
+      rs_advance(W, u);
+      ++nunits;
+    }
+    } else {
     uint32_t slot = 0, eph = 0, odd = 0;      // slot / barrier parity / row parity of the next output row of this CTA
     for (RsWork W = W0; rs_more(W) && !(P.knock & 8);) {
       const RsUnit u = rs_unit(W);
@@ -312,6 +502,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
         if (!mine) continue;
         rs_wait(bar_sfull + 8 * slot_o, eph_o, P.err, 2);
         tc_fence_after();
+        if (P.trace && !etraced) { rs_trace(P, 4, tid == RS_EPI_WARP0 * 32); etraced = true; }
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot_o * (uint32_t)L.CoutP;
         for (int n0 = 0; n0 < L.CoutP; n0 += 32) {
           uint32_t v[32];
@@ -369,7 +560,11 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
         __syncwarp();                                 // the staging buffer is rewritten by this warp's next row
       }
       rs_advance(W, u);
+      ++nunits;
     }
+    }
+    rs_trace(P, 5, tid == RS_EPI_WARP0 * 32);
+    if (P.trace && tid == RS_EPI_WARP0 * 32) P.trace[blockIdx.x * 8 + 7] = (unsigned long long)nunits;
   } else if (warp < 8) {
     // ===== loaders: loader warp w gathers the input rows m = w (mod NW) of this CTA's row sequence, one whole row (130
     // positions x Cin) per turn: consecutive lanes copy consecutive 16-byte chunks of consecutive positions.  Every lane owns
@@ -408,7 +603,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
       }
       cp_async_commit();
     };
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    bool waited = false;                  // griddepcontrol.wait sits behind the first table prefetch (the tables are static)
     uint32_t m = 0;                       // rows of this CTA's sequence before the current unit
     for (RsWork W = W0; rs_more(W) && !(P.knock & 16) && warp < NW;) {
       const RsUnit u = rs_unit(W);
@@ -427,6 +622,11 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
         }
         __syncwarp();
         prefetch(u.y0 + yi, 0);
+      }
+      if (!waited) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        rs_trace(P, 2, tid == 0);
+        waited = true;
       }
 #pragma unroll 1
       for (; yi < H + 2; yi += NW) {
@@ -487,6 +687,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  rs_trace(P, 6, tid == 0);
   if (warp == RS_MMA_WARP) tmem_dealloc(tmem_base, 512u);
 }
 
@@ -526,7 +727,7 @@ int rs_env_int(const char *name, int dflt) {
 }
 
 // nullptr when the row-streamed kernel serves the layer, otherwise the reason it does not
-const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L) {
+const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L, const dlwpcs_conv_desc *dh = nullptr) {
   if (d->kh != 3 || d->kw != 3) return "3x3 kernels only";
   if (d->stride_h != 1 || d->stride_w != 1 || d->dil_h != 1 || d->dil_w != 1) return "stride / dilation 1 only";
   if (d->x_dtype != DLWPCS_BF16 || d->y_dtype != DLWPCS_BF16) return "bf16 in, bf16 out";
@@ -549,7 +750,22 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
   if (L->CoutP < 32) L->CoutP = 32;
   L->NT = 3 * L->CoutP;
   if (L->NT > 256) return "more than 80 output channels";
-  L->NS = 512 / L->CoutP;
+  L->head = dh ? 1 : 0;
+  L->CoutP2 = 0;
+  L->hwBytes = 0;
+  if (dh) {
+    // fused 1x1 head: CubeSphereConv2D(cout2, 1) on this layer's output, which is then never written
+    if (dh->kh != 1 || dh->kw != 1 || dh->stride_h != 1 || dh->stride_w != 1 || dh->halo != 0 || dh->same) return "head must be a plain 1x1 convolution";
+    if (dh->cin != d->cout || dh->c1 != 0 || dh->mode0 != DLWPCS_SRC_SAME) return "head must read this layer's output and nothing else";
+    if (dh->batch != d->batch || dh->n != g.Hout || g.Hout != g.Wout) return "head geometry differs";
+    if (dh->x_dtype != DLWPCS_BF16 || dh->y_dtype != DLWPCS_BF16 || dh->cout % 8) return "head: bf16, output channels a multiple of 8";
+    if (L->CoutP != 32 && L->CoutP != 64) return "head needs 32 or 64 (padded) channels in between";
+    L->CoutP2 = (dh->cout + 15) / 16 * 16;
+    if (L->CoutP2 > 64) return "head with more than 64 output channels";
+    L->hwBytes = L->CoutP * L->CoutP2 * 2;
+  }
+  L->NS = (512 - 2 * L->CoutP2) / L->CoutP;
+  L->NS &= ~1;                                       // the two epilogue halves alternate rows: an even ring keeps slot <-> half fixed
   if (L->NS > RS_MAXSLOTS) L->NS = RS_MAXSLOTS;
   L->Wv = g.Wout + 2;
   L->Hv = g.Hout + 2;
@@ -557,14 +773,15 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
   L->stageBytes = (RS_NPIXP * L->RB + 1023) / 1024 * 1024;
   L->unitBytes = L->CinP * L->NT * 2;
   L->groupBytes = 3 * L->unitBytes;
-  L->stgBytes = 32 * d->cout * 2;
+  L->stgBytes = 32 * (dh ? dh->cout : d->cout) * 2;
   int off = 0;
   L->off_w = 0;        // filled below, after the row stages
   const int wB = (L->groupBytes + 1023) / 1024 * 1024;
   const int zeroB = 2 * L->CoutP * 16;
   // per loader warp: {table offset, batch element} of the strip's positions + two double-buffered rows of table entries
   const int posB = 8 * RS_NPIXP * 8 + 8 * 4 * RS_NPIXP * 4;
-  const int fixed = wB + (zeroB + 127) / 128 * 128 + 1024 + (3 * L->CoutP * 4 + 127) / 128 * 128 + 8 * 32 * 4 + posB +
+  const int headB = dh ? (3 * L->hwBytes + 127) / 128 * 128 + (3 * L->CoutP2 * 4 + 127) / 128 * 128 + 2 * 128 * L->CoutP * 2 + 1024 : 0;
+  const int fixed = wB + (zeroB + 127) / 128 * 128 + 1024 + (3 * L->CoutP * 4 + 127) / 128 * 128 + 8 * 32 * 4 + posB + headB +
                     8 * L->stgBytes + 1024 /* alignment slack */;
   int rsn = (RS_SMEM_CAP - fixed) / L->stageBytes;
   const int want = rs_env_int("DLWPCS_RS_STAGES", RS_MAXSTAGES);
@@ -573,6 +790,8 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
   if (rsn < 4) return "stacked weights leave no room for the input-row ring";
   L->RSn = rsn;
   off = rsn * L->stageBytes;
+  L->off_a2 = off;                                   // the head's two A tiles stay 1024-byte aligned (swizzle period)
+  if (dh) off += 2 * 128 * L->CoutP * 2;
   L->off_w = off; off += wB;
   L->off_zero = off; off += (zeroB + 127) / 128 * 128;
   L->off_misc = off; off += 1024;
@@ -580,6 +799,10 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
   L->off_pix = off; off += 8 * 32 * 4;
   L->off_pos = off; off += 8 * RS_NPIXP * 8;
   L->off_px = off; off += 8 * 4 * RS_NPIXP * 4;
+  L->off_hw = off;
+  if (dh) off += (3 * L->hwBytes + 127) / 128 * 128;
+  L->off_hbias = off;
+  if (dh) off += (3 * L->CoutP2 * 4 + 127) / 128 * 128;
   L->off_stg = off; off += 8 * L->stgBytes;
   L->smemBytes = off + 1024;
   return nullptr;
@@ -627,8 +850,29 @@ int rs_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_c
   return 0;
 }
 
+bool rs_head_eligible(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_desc *dh) {
+  static const int enabled = rs_env_int("DLWPCS_RS", 1) && rs_env_int("DLWPCS_RS_HEAD", 1);
+  if (!enabled) return false;
+  RsPlan L;
+  return rs_make_plan(d, g, &L, dh) == nullptr;
+}
+
+static int rs_launch(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed, void *y,
+                     const dlwpcs_conv_desc *dh, const void *packed_h, void *y2, cudaStream_t st);
+
 int rs_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed, void *y,
                 cudaStream_t st) {
+  return rs_launch(d, g, x0, x1, packed, y, nullptr, nullptr, nullptr, st);
+}
+
+// 3x3 layer + 1x1 head in one launch; packed_h = the head's classic packed image (dlwpcs_pack_weights of the 1x1 layer)
+int rs_conv_fwd_head(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed,
+                     const dlwpcs_conv_desc *dh, const void *packed_h, void *y2, cudaStream_t st) {
+  return rs_launch(d, g, x0, x1, packed, nullptr, dh, packed_h, y2, st);
+}
+
+static int rs_launch(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed, void *y,
+                     const dlwpcs_conv_desc *dh, const void *packed_h, void *y2, cudaStream_t st) {
   {
     const int dv = current_device_index();
     if (g_rs_err_host[dv] && *(volatile unsigned *)g_rs_err_host[dv]) {
@@ -642,11 +886,18 @@ int rs_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, co
   }
   RsP P;
   memset(&P, 0, sizeof(P));
-  const char *r = rs_make_plan(d, g, &P.L);
+  const char *r = rs_make_plan(d, g, &P.L, dh);
   CS_CHECK(r == nullptr, "row-streamed kernel does not support this configuration: %s", r);
   const RsPlan &L = P.L;
-  CS_CHECK(rs_aligned16(x0) && (d->c1 == 0 || rs_aligned16(x1)) && rs_aligned16(y) && rs_aligned16(packed),
+  CS_CHECK(rs_aligned16(x0) && (d->c1 == 0 || rs_aligned16(x1)) && rs_aligned16(dh ? y2 : y) && rs_aligned16(packed) &&
+               (!dh || rs_aligned16(packed_h)),
            "bf16 tensors must be 16-byte aligned");
+  if (dh) {
+    P.hw = (const uint8_t *)packed_h;
+    P.hbias = reinterpret_cast<const float *>(P.hw + 3LL * L.hwBytes);
+    P.y2 = (__nv_bfloat16 *)y2;
+    P.cout2 = dh->cout; P.act2 = dh->act; P.slope2 = dh->act_slope; P.maxv2 = dh->act_max;
+  }
   P.x0 = (const __nv_bfloat16 *)x0;
   P.x1 = (const __nv_bfloat16 *)x1;
   P.tab0 = get_patch_table(g, L.Wv, L.G, d->n, d->halo, d->mode0);
@@ -677,13 +928,15 @@ int rs_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, co
   }
   P.err = g_rs_err[dev_i];
   typedef void (*kern_t)(const RsP);
-  static const kern_t kerns[4] = {conv_rs_kernel<1>, conv_rs_kernel<2>, nullptr, conv_rs_kernel<4>};
-  static bool attr_set[kMaxDevices][4] = {};
-  const kern_t kern = kerns[L.KC16 - 1];
+  static const kern_t kerns[2][4] = {{conv_rs_kernel<1, false>, conv_rs_kernel<2, false>, nullptr, conv_rs_kernel<4, false>},
+                                     {conv_rs_kernel<1, true>, conv_rs_kernel<2, true>, nullptr, conv_rs_kernel<4, true>}};
+  static bool attr_set[kMaxDevices][2][4] = {};
+  const int hi = dh ? 1 : 0;
+  const kern_t kern = kerns[hi][L.KC16 - 1];
   CS_CHECK(kern != nullptr, "internal: bad K block");
-  if (!attr_set[dev_i][L.KC16 - 1]) {
+  if (!attr_set[dev_i][hi][L.KC16 - 1]) {
     CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_CAP));
-    attr_set[dev_i][L.KC16 - 1] = true;
+    attr_set[dev_i][hi][L.KC16 - 1] = true;
   }
   const long long strips = (4LL * d->batch * L.Wv + 127) / 128 + 2 * ((1LL * d->batch * L.Wv + 127) / 128);
   const long long R = strips * g.Hout;
@@ -706,6 +959,7 @@ int rs_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, co
     P.cut_s[c] = (int)(b / g.Hout);
     P.cut_y[c] = (int)(b % g.Hout);
   }
+  P.trace = tc_trace_next(grid);
   static const int pdl = rs_env_int("DLWPCS_TC_PDL", 1);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -276,7 +276,7 @@ class RolloutEngine(object):
     """
 
     def __init__(self, model, batch, n, steps, forcing_channels=0, dtype=torch.float32, use_graph=True,
-                 per_step_forcing=False, device=None, input_order=None, chain=None, tensor_cores=False):
+                 per_step_forcing=False, device=None, input_order=None, chain=None, tensor_cores=False, fuse_head=True):
         if n % (1 << model.levels) != 0:
             raise ValueError('%s pools %d times: face edge must be divisible by %d' % (model.arch, model.levels, 1 << model.levels))
         self.model, self.batch, self.n, self.steps = model, batch, n, steps
@@ -357,6 +357,15 @@ class RolloutEngine(object):
                                    layer.flip_north_pole, layer.independent_north_pole, layer.use_bias, fused[0], fused[1],
                                    fused[2], dt, dt, c0, m0, c1, m1)
             self.plan.append([name, d, s0, s1, dst, None])
+        # the 1x1 output layer runs inside the epilogue of the 3x3 layer in front of it when it is that layer's only
+        # reader and the pair qualifies (dlwpcs_conv2d_fwd_head): one launch less, and the 3x3 layer's output never
+        # reaches HBM.  self.fused_head = index of the 3x3 layer in self.plan, or None.
+        self.fused_head = None
+        if fuse_head and dtype == torch.bfloat16 and not self.chain_requested(chain) and len(self.plan) >= 2:
+            last, prev = self.plan[-1], self.plan[-2]
+            readers = sum(1 for it in self.plan for key in (it[2], it[3]) if key == prev[4])
+            if last[2] == prev[4] and last[3] is None and readers == 1 and _lib.conv2d_head_fusable(prev[1], last[1]):
+                self.fused_head = len(self.plan) - 2
         if self.tc32:              # the layers run one after the other: one scratch buffer serves every split
             scratch = torch.empty(scratch_elems, dtype=torch.bfloat16, device=self.device)
             for name, (m0, shape) in list(self._split.items()):
@@ -381,6 +390,10 @@ class RolloutEngine(object):
             self._chain_mem = torch.zeros(nl * self._chain_stride + 1, dtype=torch.int32, device=self.device)
             self._chain_targets = [_lib.chain_target(item[1]) for item in self.plan]
         self.repack()
+
+    @staticmethod
+    def chain_requested(chain):
+        return (os.environ.get('DLWPCS_CHAIN', '0') != '0') if chain is None else bool(chain)
 
     @property
     def chain_error(self):
@@ -415,7 +428,7 @@ class RolloutEngine(object):
 
     @property
     def launches_per_step(self):
-        return len(self.plan) * (2 if self.tc32 else 1)
+        return len(self.plan) * (2 if self.tc32 else 1) - (1 if self.fused_head is not None else 0)
 
     def _src(self, key, t):
         if key is None:
@@ -471,6 +484,13 @@ class RolloutEngine(object):
             chained = False
         nl = len(self.plan)
         for i, (name, d, s0, s1, dst, packed) in enumerate(self.plan):
+            if self.fused_head is not None:
+                if i == self.fused_head:
+                    head = self.plan[i + 1]
+                    _lib.conv2d_fwd_head(d, self._src(s0, t), self._src(s1, t), packed, head[1], head[5], out=self.ring[t])
+                    continue
+                if i == self.fused_head + 1:
+                    continue
             out = self.ring[t] if dst == 'out' else self.buf[dst]
             if self.tc32:
                 m0, xs = self._split[name]

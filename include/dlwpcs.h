@@ -78,9 +78,10 @@ int dlwpcs_pad_bwd_act(const void *dy, const void *y_in, void *dx, int batch, in
                        float maxv, int dtype, void *stream);
 
 /* Weight packing: HWIO float32 -> the per-face-group layouts the kernels read.  `packed` must hold
- * dlwpcs_packed_weight_bytes(desc, transposed) bytes.  transposed = 0: forward; 1: dgrad (taps rotated 180 degrees,
- * cin/cout swapped); 2: forward image for dlwpcs_conv2d_fwd_chained (the same image as 0 today; kept distinct so that a
- * kernel variant with its own weight layout can be dispatched by dlwpcs_conv2d_fwd alone).  Group 0 = equatorial, 1 = south pole, 2 = north pole (polar or independent kernel, rows flipped
+ * dlwpcs_packed_weight_bytes(desc, transposed) bytes.  transposed = 0: forward, in the layout of whichever kernel
+ * dlwpcs_conv2d_fwd runs for the descriptor (3x3 stride-1 bf16 layers with <= 64 input and <= 80 output channels go to the
+ * row-streamed kernel, whose image stacks the three kernel rows along N); 1: dgrad (taps rotated 180 degrees, cin/cout
+ * swapped); 2: forward image for dlwpcs_conv2d_fwd_chained (always the classic kernel's image).  Group 0 = equatorial, 1 = south pole, 2 = north pole (polar or independent kernel, rows flipped
  * when flip_north_pole -- equivalent to custom.py:969/995 for every stride).                           */
 int64_t dlwpcs_packed_weight_bytes(const dlwpcs_conv_desc *d, int transposed);
 int dlwpcs_pack_weights(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, int transposed, void *packed,
@@ -207,6 +208,19 @@ typedef struct dlwpcs_chain {
 int dlwpcs_conv2d_fwd_chained(const dlwpcs_conv_desc *d, const void *x0, const void *x1, const void *packed_w, void *y,
                               const dlwpcs_chain *chain, void *stream);
 uint32_t dlwpcs_chain_target(const dlwpcs_conv_desc *d);
+
+/* A 3x3 CubeSphereConv2D (with its fused padding / sampling / bias / activation) followed by the 1x1 CubeSphereConv2D that
+ * is its ONLY consumer -- the output layer of every cubed-sphere network, Azure/train_cs.py:228 after :225-227 -- in one
+ * launch: the activated bf16 output row of the first layer becomes the A operand of a second tcgen05.mma inside the
+ * epilogue, and never reaches HBM.  Same arithmetic as the two separate launches (one bf16 rounding in between, float32
+ * accumulation of the 1x1 products in the same order): bit-identical results.
+ *   dlwpcs_conv2d_head_fusable: 1 when the pair qualifies (3x3 stride-1 bf16 layer served by the row-streamed kernel with
+ *       32 or 64 padded output channels; head: 1x1, stride 1, no halo, single un-resampled source of d->cout channels,
+ *       bf16, <= 64 output channels in multiples of 8), else 0.
+ *   head_packed_w: dlwpcs_pack_weights(head, ..., transposed = 0).  y_head: (B,6,Hout,Wout,head->cout) bf16.           */
+int dlwpcs_conv2d_head_fusable(const dlwpcs_conv_desc *d, const dlwpcs_conv_desc *head);
+int dlwpcs_conv2d_fwd_head(const dlwpcs_conv_desc *d, const void *x0, const void *x1, const void *packed_w,
+                           const dlwpcs_conv_desc *head, const void *head_packed_w, void *y_head, void *stream);
 
 /* Diagnostics (no reference counterpart): with DLWPCS_TC_TRACE=1 in the environment every launch of the tensor-core
  * convolution kernel records, per CTA, eight %globaltimer values (ns): 0 kernel entry, 1 prologue done, 2 loaders past

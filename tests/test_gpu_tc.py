@@ -529,3 +529,64 @@ def test_rs_kernel_vs_oracle_and_classic_kernel(lib, batch, n, cin, cout, srcs):
     torch.cuda.synchronize()
     diff = (y.float() - yc.float()).abs()
     assert float((diff / (yc.float().abs() + 1e-3)).max()) <= 2.0 ** -6
+
+
+# ---- fused 1x1 head (dlwpcs_conv2d_fwd_head): the output layer inside the epilogue of the 3x3 layer in front of it -----------
+@pytest.mark.parametrize('batch,n,cin,cmid,cout2,srcs,act2', [
+    (3, 24, 32, 32, 16, 1, False),        # the U-Net's tail: 32 -> 32 (ReLU) -> 16 linear
+    (5, 48, 32, 32, 16, 1, False),        # C48, several units per CTA and both weight-group changes
+    (2, 24, 64, 32, 24, 2, True),         # up-sampled + concatenated input, 24 head channels (32 padded), activated head
+    (2, 12, 32, 64, 16, 1, False),        # 64 channels in between (128-byte A rows, K = 64)
+    (3, 24, 16, 24, 8, 1, False),         # 24 channels in between (padded to 32 with exact zeros), 8 head channels
+])
+def test_fused_head_equals_two_launches(lib, batch, n, cin, cmid, cout2, srcs, act2):
+    """Same arithmetic as the two separate launches: one bf16 rounding in between, float32 accumulation of the 1x1 products
+    in the same order -> bit-identical."""
+    g = torch.Generator().manual_seed(11 * n + cin + cout2)
+    mk = lambda *shape: torch.randn(*shape, generator=g)
+    if srcs == 1:
+        x0, x1, c0, c1, m0 = bf(mk(batch, 6, n, n, cin)).cuda(), None, cin, 0, lib.SRC_SAME
+    else:
+        ca = cin // 2
+        x0, x1 = bf(mk(batch, 6, n // 2, n // 2, ca)).cuda(), bf(mk(batch, 6, n, n, cin - ca)).cuda()
+        c0, c1, m0 = ca, cin - ca, lib.SRC_UP2
+    w = [bf(mk(3, 3, cin, cmid) * 0.1).float().cuda() for _ in range(2)]
+    b_ = [(mk(cmid) * 0.1).cuda() for _ in range(2)]
+    wh = [bf(mk(1, 1, cmid, cout2) * 0.2).float().cuda() for _ in range(2)]
+    bh = [(mk(cout2) * 0.1).cuda() for _ in range(2)]
+    d = lib.make_desc(batch, n, cin, cmid, (3, 3), (1, 1), (1, 1), 1, False, True, False, True, lib.ACT_CAPPED_LEAKY_RELU, 0.1,
+                      10.0, lib.BF16, lib.BF16, c0, m0, c1, lib.SRC_SAME)
+    dh = lib.make_desc(batch, n, cmid, cout2, (1, 1), (1, 1), (1, 1), 0, False, True, False, True,
+                       lib.ACT_CAPPED_LEAKY_RELU if act2 else lib.ACT_NONE, 0.1, 10.0, lib.BF16, lib.BF16)
+    assert lib.conv2d_head_fusable(d, dh)
+    packed = lib.pack_weights(d, w[0], w[1], None, b_[0], b_[1], None)
+    packed_h = lib.pack_weights(dh, wh[0], wh[1], None, bh[0], bh[1], None)
+    mid = lib.conv2d_fwd(d, x0, x1, packed)
+    two = lib.conv2d_fwd(dh, mid, None, packed_h)
+    one = lib.conv2d_fwd_head(d, x0, x1, packed, dh, packed_h)
+    torch.cuda.synchronize()
+    assert float(two.float().abs().max()) > 0.1
+    assert torch.equal(one, two)
+    # not fusable: a 3x3 head, a head that reads something else
+    d3 = lib.make_desc(batch, n, cmid, cout2, (3, 3), (1, 1), (1, 1), 1, False, True, False, True, lib.ACT_NONE, 0.1, 10.0,
+                       lib.BF16, lib.BF16)
+    assert not lib.conv2d_head_fusable(d, d3)
+    dw = lib.make_desc(batch, n, cmid + 8, cout2, (1, 1), (1, 1), (1, 1), 0, False, True, False, True, lib.ACT_NONE, 0.1, 10.0,
+                       lib.BF16, lib.BF16)
+    assert not lib.conv2d_head_fusable(d, dw)
+
+
+def test_rollout_engine_fused_head_is_bit_identical():
+    from dlwp_cs_b200.unet import CubeSphereUNet2, RolloutEngine
+    torch.manual_seed(3)
+    model = CubeSphereUNet2(18, 14, base=32).cuda()
+    g = torch.Generator().manual_seed(4)
+    state, forcing = torch.randn(3, 6, 24, 24, 14, generator=g), torch.rand(3, 6, 24, 24, 4, generator=g)
+    outs = []
+    for fuse in (True, False):
+        eng = RolloutEngine(model, 3, 24, 3, forcing_channels=4, dtype=torch.bfloat16, fuse_head=fuse)
+        assert (eng.fused_head is not None) == fuse
+        assert eng.launches_per_step == (10 if fuse else 11)
+        outs.append(eng.run(state, forcing).clone())
+        torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
