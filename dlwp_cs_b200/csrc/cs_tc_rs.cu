@@ -55,7 +55,7 @@ struct RsPlan {
   int stgBytes;                      // output staging per epilogue warp
   int off_w, off_zero, off_misc, off_bias, off_pix, off_pos, off_px, off_stg, smemBytes;
   // fused 1x1 head (conv_rs_kernel<.., true>): a second MMA per output row inside the epilogue
-  int head, CoutP2, hwBytes, off_hw, off_hbias, off_a2;
+  int head, CoutP2, Kh, hwBytes, off_hw, off_hbias, off_a2;     // Kh = K of the head's MMA = its padded input channels
 };
 
 struct RsP {
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
           tc_fence_after();
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (j * 16 < L.CoutP)
+            if (j * 16 < L.Kh)
               umma_bf16_elect(d2, a2desc + (uint64_t)(2u * (uint32_t)j), b2desc + (uint64_t)((uint32_t)j * (uint32_t)(2 * L.CoutP2)), idesc2,
                               j > 0 ? 1u : 0u);
           umma_commit_elect(bar_h);
@@ -752,6 +752,7 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
   if (L->NT > 256) return "more than 80 output channels";
   L->head = dh ? 1 : 0;
   L->CoutP2 = 0;
+  L->Kh = 0;
   L->hwBytes = 0;
   if (dh) {
     // fused 1x1 head: CubeSphereConv2D(cout2, 1) on this layer's output, which is then never written
@@ -762,7 +763,11 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
     if (L->CoutP != 32 && L->CoutP != 64) return "head needs 32 or 64 (padded) channels in between";
     L->CoutP2 = (dh->cout + 15) / 16 * 16;
     if (L->CoutP2 > 64) return "head with more than 64 output channels";
-    L->hwBytes = L->CoutP * L->CoutP2 * 2;
+    // the head's classic image pads its input channels like cs_tc.cu's make_plan: 16 / 32, then multiples of 64
+    L->Kh = (dh->cin + 15) / 16 * 16;
+    if (L->Kh > 32) L->Kh = (dh->cin + 63) / 64 * 64;
+    if (L->Kh > L->CoutP) return "head input channels exceed the padded channels in between";
+    L->hwBytes = L->Kh * L->CoutP2 * 2;
   }
   L->NS = (512 - 2 * L->CoutP2) / L->CoutP;
   L->NS &= ~1;                                       // the two epilogue halves alternate rows: an even ring keeps slot <-> half fixed

@@ -538,6 +538,7 @@ def test_rs_kernel_vs_oracle_and_classic_kernel(lib, batch, n, cin, cout, srcs):
     (2, 24, 64, 32, 24, 2, True),         # up-sampled + concatenated input, 24 head channels (32 padded), activated head
     (2, 12, 32, 64, 16, 1, False),        # 64 channels in between (128-byte A rows, K = 64)
     (3, 24, 16, 24, 8, 1, False),         # 24 channels in between (padded to 32 with exact zeros), 8 head channels
+    (2, 8, 8, 16, 8, 1, False),           # 16 channels in between: the head's K (16) is half the padded A tile
 ])
 def test_fused_head_equals_two_launches(lib, batch, n, cin, cmid, cout2, srcs, act2):
     """Same arithmetic as the two separate launches: one bf16 rounding in between, float32 accumulation of the 1x1 products
