@@ -576,6 +576,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const uint32_t cpr = rowB >> 4;                                             // 16-byte chunks per output row
     const int cprLog = (cpr & (cpr - 1)) == 0 ? 31 - __clz(cpr) : -1;          // rows of 2^k chunks: shifts instead of divisions
     const uint32_t smask = (cpr & (cpr - 1)) == 0 ? min(cpr, 8u) - 1u : 0u;    // XOR swizzle of the chunk index by row
+    // rows shorter than 128 bytes share a bank line: the key advances once per line (keyed by the row itself, the
+    // 16-byte stores of 64-byte rows collide two-way -- ncu: 8 instead of 4 wavefronts per STS.128)
+    const uint32_t kshift = rowB >= 128u ? 0u : (rowB == 64u ? 1u : (rowB == 32u ? 2u : 3u));
     int sa = 0, pa = 0, k = 0;
     if (!chained) asm volatile("griddepcontrol.wait;" ::: "memory");        // the bias sits behind the packed weights
     for (int i = tid - EPI_WARP0 * 32; i < 3 * L.CoutP; i += TC_EPI) s_bias[i] = P.bias[i];
@@ -638,10 +641,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
             if (staged) {
               if (nb + 8 <= P.cout)
-                st_shared16(srow + ((((uint32_t)nb >> 3) ^ (prow & smask)) << 4), make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                st_shared16(srow + ((((uint32_t)nb >> 3) ^ ((prow >> kshift) & smask)) << 4), make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
                                                                   pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
               if (nb + 16 <= P.cout)
-                st_shared16(srow + (((((uint32_t)nb >> 3) + 1u) ^ (prow & smask)) << 4), make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]),
+                st_shared16(srow + (((((uint32_t)nb >> 3) + 1u) ^ ((prow >> kshift) & smask)) << 4), make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]),
                                                                         pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15])));
             } else if (fast_out && nb + 16 <= P.cout) {
               __nv_bfloat16 *yp = reinterpret_cast<__nv_bfloat16 *>(P.y) + opix * P.cout + nb;
@@ -678,7 +681,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             else { row = off / rowB; ch = (off - row * rowB) >> 4; }
             uint4 v;
             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                         : "r"(stg + row * rowB + ((ch ^ (row & smask)) << 4)));
+                         : "r"(stg + row * rowB + ((ch ^ ((row >> kshift) & smask)) << 4)));
             *reinterpret_cast<uint4 *>(gdst + off) = v;
           }
           __syncwarp();                                 // the buffer is rewritten by the next m-block

@@ -309,6 +309,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     const uint32_t cpr = rowB >> 4;
     const int cprLog = (cpr & (cpr - 1)) == 0 ? 31 - __clz(cpr) : -1;
     const uint32_t smask = (cpr & (cpr - 1)) == 0 ? min(cpr, 8u) - 1u : 0u;
+    // XOR key of a staged row: rows shorter than 128 bytes share a 128-byte bank line, so the key advances once per line
+    // (8 consecutive rows then hit 8 different 16-byte bank groups; keyed by the row itself, 64-byte rows collide two-way)
+    const uint32_t kshift = rowB >= 128u ? 0u : (rowB == 64u ? 1u : (rowB == 32u ? 2u : 3u));
     const uint32_t NS = (uint32_t)L.NS;
     asm volatile("griddepcontrol.wait;" ::: "memory");        // the bias sits behind the packed weights
     for (int i = tid - RS_EPI_WARP0 * 32; i < 3 * L.CoutP; i += RS_EPI) s_bias[i] = P.bias[i];
@@ -326,6 +329,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     const uint32_t rowB2 = (uint32_t)P.cout2 * 2u, cpr2 = rowB2 >> 4;
     const int cprLog2 = (cpr2 & (cpr2 - 1)) == 0 ? 31 - __clz(cpr2) : -1;
     const uint32_t smask2 = (cpr2 & (cpr2 - 1)) == 0 ? min(cpr2, 8u) - 1u : 0u;
+    const uint32_t kshift2 = rowB2 >= 128u ? 0u : (rowB2 == 64u ? 1u : (rowB2 == 32u ? 2u : 3u));
     const uint64_t a2desc = (((uint64_t)(((8u * RBh) >> 4) | (1u << 14) | ((RBh == 128u ? 2u : 4u) << 29)) << 32) | (1ull << 16)) |
                             (a2 >> 4);
     const uint64_t b2fix = ((uint64_t)((128u >> 4) | (1u << 14)) << 32) | ((uint64_t)((uint32_t)L.CoutP2 & 0x3FFFu) << 16);
@@ -384,10 +388,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
             for (int e = 0; e < 16; ++e) r[e] = act_apply(r[e], P.act2, P.slope2, P.maxv2);
           }
           if (n0 + 8 <= P.cout2)
-            st_shared16(srow + ((((uint32_t)n0 >> 3) ^ (prow & smask2)) << 4),
+            st_shared16(srow + ((((uint32_t)n0 >> 3) ^ ((prow >> kshift2) & smask2)) << 4),
                         make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7])));
           if (n0 + 16 <= P.cout2)
-            st_shared16(srow + (((((uint32_t)n0 >> 3) + 1u) ^ (prow & smask2)) << 4),
+            st_shared16(srow + (((((uint32_t)n0 >> 3) + 1u) ^ ((prow >> kshift2) & smask2)) << 4),
                         make_uint4(pack_bf16x2(r[8], r[9]), pack_bf16x2(r[10], r[11]), pack_bf16x2(r[12], r[13]), pack_bf16x2(r[14], r[15])));
         }
         tc_fence_before();
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
           else { row = off / rowB2; ch = (off - row * rowB2) >> 4; }
           uint4 q;
           asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
-                       : "r"(stg + row * rowB2 + ((ch ^ (row & smask2)) << 4)));
+                       : "r"(stg + row * rowB2 + ((ch ^ ((row >> kshift2) & smask2)) << 4)));
           uint8_t *gdst = reinterpret_cast<uint8_t *>(P.y2) + ((size_t)((uint32_t)pixw[row] + rowoff)) * rowB2 + (ch << 4);
           *reinterpret_cast<uint4 *>(gdst) = q;
         }
@@ -537,10 +541,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
               for (int e = 0; e < 16; ++e) r[e] = act_apply(r[e], P.act, P.slope, P.maxv);
             }
             if (nb + 8 <= P.cout)
-              st_shared16(srow + ((((uint32_t)nb >> 3) ^ (prow & smask)) << 4),
+              st_shared16(srow + ((((uint32_t)nb >> 3) ^ ((prow >> kshift) & smask)) << 4),
                           make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7])));
             if (nb + 16 <= P.cout)
-              st_shared16(srow + (((((uint32_t)nb >> 3) + 1u) ^ (prow & smask)) << 4),
+              st_shared16(srow + (((((uint32_t)nb >> 3) + 1u) ^ ((prow >> kshift) & smask)) << 4),
                           make_uint4(pack_bf16x2(r[8], r[9]), pack_bf16x2(r[10], r[11]), pack_bf16x2(r[12], r[13]), pack_bf16x2(r[14], r[15])));
           }
         }
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
           else { row = off / rowB; ch = (off - row * rowB) >> 4; }
           uint4 q;
           asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
-                       : "r"(stg + row * rowB + ((ch ^ (row & smask)) << 4)));
+                       : "r"(stg + row * rowB + ((ch ^ ((row >> kshift) & smask)) << 4)));
           uint8_t *gdst = reinterpret_cast<uint8_t *>(P.y) + ((size_t)((uint32_t)pixw[row] + rowoff)) * rowB + (ch << 4);
           *reinterpret_cast<uint4 *>(gdst) = q;
         }
