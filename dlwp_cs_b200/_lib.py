@@ -84,6 +84,7 @@ def load():
         'dlwpcs_pad_bwd_act': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, i32, vp]),
         'dlwpcs_conv2d_dgrad_act': (i32, [dp, vp, vp, vp, vp, vp, vp, i32, f32, f32, vp]),
         'dlwpcs_conv2d_head_fusable': (i32, [dp, dp]),
+        'dlwpcs_rs_work_cuts': (i32, [dp, i32, vp, vp]),
         'dlwpcs_conv2d_fwd_head': (i32, [dp, vp, vp, vp, dp, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
@@ -103,7 +104,7 @@ EXPORTED = ('dlwpcs_version', 'dlwpcs_last_error', 'dlwpcs_conv_out_edge', 'dlwp
             'dlwpcs_up2cat_fwd', 'dlwpcs_up2cat_bwd', 'dlwpcs_feed_gather', 'dlwpcs_trace_read',
             'dlwpcs_conv2d_fwd_chained', 'dlwpcs_chain_target', 'dlwpcs_split3',
             'dlwpcs_pack_weights2', 'dlwpcs_pad_bwd_act', 'dlwpcs_conv2d_dgrad_act', 'dlwpcs_conv2d_head_fusable',
-            'dlwpcs_conv2d_fwd_head')
+            'dlwpcs_conv2d_fwd_head', 'dlwpcs_rs_work_cuts')
 
 
 class DlwpcsError(RuntimeError):
@@ -244,6 +245,16 @@ def conv2d_fwd(d, x0, x1, packed, out=None):
     y = out if out is not None else torch.empty(shp, dtype=ydt, device=x0.device)
     check(load().dlwpcs_conv2d_fwd(ctypes.byref(d), ptr(x0), ptr(x1), ptr(packed), ptr(y), stream_ptr()))
     return y
+
+
+def rs_work_cuts(d, grid):
+    """Work split of the row-streamed kernel (host only): list of (strip, row) cut points, grid + 1 entries, or None when
+    the layer is not served by that kernel."""
+    cs = (ctypes.c_int32 * (grid + 1))()
+    cy = (ctypes.c_int32 * (grid + 1))()
+    if load().dlwpcs_rs_work_cuts(ctypes.byref(d), grid, cs, cy) != grid:
+        return None
+    return [(int(cs[i]), int(cy[i])) for i in range(grid + 1)]
 
 
 def conv2d_head_fusable(d, head):

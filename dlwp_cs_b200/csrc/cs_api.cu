@@ -1000,6 +1000,12 @@ int dlwpcs_conv2d_fwd(const dlwpcs_conv_desc *d, const void *x0, const void *x1,
                        (cudaStream_t)stream);
 }
 
+int dlwpcs_rs_work_cuts(const dlwpcs_conv_desc *d, int grid, int32_t *cut_s, int32_t *cut_y) {
+  Geometry g;
+  if (!d || !cut_s || !cut_y || check_common(d, &g)) return 0;
+  return rs_debug_cuts(d, g, grid, cut_s, cut_y);
+}
+
 int dlwpcs_conv2d_head_fusable(const dlwpcs_conv_desc *d, const dlwpcs_conv_desc *head) {
   Geometry g, gh;
   if (!d || !head || check_common(d, &g) || check_common(head, &gh)) return 0;

@@ -817,6 +817,47 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
   return nullptr;
 }
 
+// Work split of the row-streamed kernel: CTA c works on the (strip, output row) pairs [(cut_s[c], cut_y[c]), (cut_s[c+1],
+// cut_y[c+1])).  Equal COST shares: a unit of h output rows streams h + 2 input rows, and a change of face group reloads the
+// weights and drains the pipeline (~3 rows).  Host only.
+void rs_work_cuts(int batch, int Wv, int Hout, int grid, int *cut_s, int *cut_y) {
+  const long long ns0 = (4LL * batch * Wv + 127) / 128, ns1 = (1LL * batch * Wv + 127) / 128;
+  const long long strips = ns0 + 2 * ns1, R = strips * Hout;
+  const int snap = 1;            // a cut inside a strip costs one more unit (2 rows) wherever it falls: no snapping needed
+  const double unit_cost = 2.0, group_cost = 3.0;
+  const double total = (double)R + unit_cost * (double)(strips + grid - 1) + group_cost * 2.0;
+  const double per = total / grid;
+  long long pos = 0;
+  double acc = 0.0;
+  for (int c = 0; c < grid; ++c) {
+    cut_s[c] = (int)(pos / Hout);
+    cut_y[c] = (int)(pos % Hout);
+    const double target = per * (c + 1);
+    bool first = true;
+    while (pos < R) {
+      const long long sidx = pos / Hout;
+      const int y = (int)(pos % Hout);
+      double enter = (first || y == 0) ? unit_cost : 0.0;
+      if (y == 0 && !first && (sidx == ns0 || sidx == ns0 + ns1)) enter += group_cost;
+      const int left = Hout - y;
+      int x = (int)(target - acc - enter);
+      if (c == grid - 1) x = left;                       // the last CTA takes what remains
+      if (x > left) x = left;
+      if (x < left) {                                    // the share ends inside this strip: snap
+        if (x < snap && !first) break;                   // not worth a new unit: stop at the boundary behind us
+        if (x < snap) x = snap < left ? snap : left;     // a CTA with work left never goes empty-handed
+        if (left - x < snap) x = left;
+      }
+      acc += enter + x;
+      pos += x;
+      first = false;
+      if (x < left) break;
+    }
+  }
+  cut_s[grid] = (int)strips;
+  cut_y[grid] = 0;
+}
+
 bool rs_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int rs_num_sms() {
@@ -831,6 +872,13 @@ unsigned *g_rs_err[kMaxDevices] = {};        // device pointers of ...
 unsigned *g_rs_err_host[kMaxDevices] = {};   // ... mapped pinned host words: a watchdog code survives the trapped context
 
 }  // namespace
+
+int rs_debug_cuts(const dlwpcs_conv_desc *d, const Geometry &g, int grid, int *cut_s, int *cut_y) {
+  RsPlan L;
+  if (rs_make_plan(d, g, &L) || grid < 1 || grid > RS_MAXGRID) return 0;
+  rs_work_cuts(d->batch, L.Wv, g.Hout, grid, cut_s, cut_y);
+  return grid;
+}
 
 bool rs_eligible(const dlwpcs_conv_desc *d, const Geometry &g) {
   static const int enabled = rs_env_int("DLWPCS_RS", 1);
@@ -954,20 +1002,12 @@ static int rs_launch(const dlwpcs_conv_desc *d, const Geometry &g, const void *x
   P.knock = knock;
   // equal shares of the (strip, output row) sequence; a cut closer than `snap` rows to a strip boundary moves onto it (a
   // unit of h output rows streams h + 2 input rows)
-  const int snap = g.Hout >= 16 ? 4 : (g.Hout >= 8 ? 2 : 1);
   int grid = rs_num_sms();
   if (grid > RS_MAXGRID) grid = RS_MAXGRID;
   const long long min_rows = 4;
   if ((long long)grid * min_rows > R) grid = (int)((R + min_rows - 1) / min_rows);
   if (grid < 1) grid = 1;
-  for (int c = 0; c <= grid; ++c) {
-    long long b = (long long)c * R / grid;
-    const int r = (int)(b % g.Hout);
-    if (r < snap) b -= r;
-    else if (r > g.Hout - snap) b += g.Hout - r;
-    P.cut_s[c] = (int)(b / g.Hout);
-    P.cut_y[c] = (int)(b % g.Hout);
-  }
+  rs_work_cuts(d->batch, L.Wv, g.Hout, grid, P.cut_s, P.cut_y);
   P.trace = tc_trace_next(grid);
   static const int pdl = rs_env_int("DLWPCS_TC_PDL", 1);
   cudaLaunchConfig_t cfg;

@@ -222,6 +222,13 @@ int dlwpcs_conv2d_head_fusable(const dlwpcs_conv_desc *d, const dlwpcs_conv_desc
 int dlwpcs_conv2d_fwd_head(const dlwpcs_conv_desc *d, const void *x0, const void *x1, const void *packed_w,
                            const dlwpcs_conv_desc *head, const void *head_packed_w, void *y_head, void *stream);
 
+/* Host only (no GPU needed; diagnostics / tests): the work split of the row-streamed kernel for a layer it serves.  The
+ * (strip, output row) sequence of the layer -- strips of 128 positions over the row-wise concatenated faces of one weight
+ * group, equatorial first -- is cut into `grid` contiguous ranges of equal cost; CTA c works on [(cut_s[c], cut_y[c]),
+ * (cut_s[c+1], cut_y[c+1])).  Both arrays hold grid + 1 entries.  Returns grid, or 0 when the layer is not served by that
+ * kernel or grid is out of range (1..160).                                                                             */
+int dlwpcs_rs_work_cuts(const dlwpcs_conv_desc *d, int grid, int32_t *cut_s, int32_t *cut_y);
+
 /* Diagnostics (no reference counterpart): with DLWPCS_TC_TRACE=1 in the environment every launch of the tensor-core
  * convolution kernel records, per CTA, eight %globaltimer values (ns): 0 kernel entry, 1 prologue done, 2 loaders past
  * the grid dependency, 3 first input patch in shared memory, 4 first accumulators complete, 5 last epilogue done,

@@ -164,3 +164,40 @@ def test_unet2_keras_weight_order_roundtrip():
         b.set_weights([w[1].transpose(3, 2, 0, 1)] + w[1:])
     c = CubeSphereUNet2(18, 14, base=8, independent_north_pole=True)
     assert len(c.get_weights()) == 66
+
+
+@pytest.mark.parametrize('batch,n,cin,cout,grid', [(64, 48, 32, 32, 148), (64, 24, 64, 64, 148), (16, 96, 32, 32, 148),
+                                                   (2, 8, 16, 32, 6), (1, 48, 32, 32, 37), (5, 24, 24, 32, 60),
+                                                   (64, 12, 64, 64, 126), (3, 48, 64, 32, 160)])
+def test_row_streamed_work_cuts(batch, n, cin, cout, grid):
+    """Host logic of the row-streamed kernel's work split (dlwpcs_rs_work_cuts, no GPU): the cut points are monotone, start
+    at (0, 0), end at (strips, 0), no CTA in front of the end is empty, and the cost (rows + 2 per unit) is balanced to within
+    a few rows."""
+    from dlwp_cs_b200 import _lib
+    d = _lib.make_desc(batch, n, cin, cout, (3, 3), (1, 1), (1, 1), 1, False, True, False, True, _lib.ACT_NONE, 0.1, 10.0,
+                       _lib.BF16, _lib.BF16)
+    cuts = _lib.rs_work_cuts(d, grid)
+    assert cuts is not None and len(cuts) == grid + 1
+    wv, hout = n + 2, n
+    strips = -(-4 * batch * wv // 128) + 2 * (-(-batch * wv // 128))
+    snap = 1
+    assert cuts[0] == (0, 0) and cuts[-1] == (strips, 0)
+    lin = [s * hout + y for s, y in cuts]
+    assert all(0 <= y < hout for _, y in cuts)
+    assert all(b >= a for a, b in zip(lin, lin[1:]))
+    for s, y in cuts:
+        assert y == 0 or (snap <= y <= hout - snap), (s, y)
+    sizes = [b - a for a, b in zip(lin, lin[1:])]
+    done = [i for i, v in enumerate(lin) if v == lin[-1]][0]          # first cut that has reached the end
+    assert all(v > 0 for v in sizes[:done])
+    # cost of a CTA: its rows + 2 input rows of overhang per unit (a unit = the part of one strip it covers)
+    costs = []
+    for a, b in zip(lin, lin[1:]):
+        units = 0 if a == b else (b - 1) // hout - a // hout + 1
+        costs.append(b - a + 2 * units)
+    work = [c for c in costs if c > 0]
+    assert max(work) <= sum(work) / len(work) + 6
+    # not served by that kernel: 5x5, 128 input channels
+    d5 = _lib.make_desc(batch, n, cin, cout, (5, 5), (1, 1), (1, 1), 2, False, True, False, True, _lib.ACT_NONE, 0.1, 10.0,
+                        _lib.BF16, _lib.BF16)
+    assert _lib.rs_work_cuts(d5, grid) is None
