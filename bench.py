@@ -226,6 +226,43 @@ def timed_rollout(eng, flush, steps, warmup):
     return sum(s.elapsed_time(e) for s, e in ev) / steps
 
 
+def conv_shape_records(dev, flush, pk):
+    """Single CubeSphereConv2D launches (bf16, 3x3, fused halo, bias + ReLU) at batch 64 on shapes that isolate the
+    convolution kernel from the network: the 32-wide C48 layer, and 64 -> 64 at C48 (arithmetic intensity 288 > ridge: the
+    tensor-bound stress shape).  L2 flushed before every repetition; four back-to-back launches per repetition."""
+    from dlwp_cs_b200 import _lib
+    out = {}
+    for n, cin, cout in ((48, 32, 32), (48, 64, 64)):
+        b = 64
+        g = torch.Generator().manual_seed(n + cin)
+        x = torch.randn(b, 6, n, n, cin, generator=g).bfloat16().to(dev)
+        w = [(torch.randn(3, 3, cin, cout, generator=g) * 0.05).to(dev) for _ in range(2)]
+        bs = [torch.zeros(cout, device=dev) for _ in range(2)]
+        d = _lib.make_desc(b, n, cin, cout, (3, 3), (1, 1), (1, 1), 1, False, True, False, True, _lib.ACT_CAPPED_LEAKY_RELU,
+                           0.1, 10.0, _lib.BF16, _lib.BF16)
+        packed = _lib.pack_weights(d, w[0], w[1], None, bs[0], bs[1], None)
+        y = _lib.conv2d_fwd(d, x, None, packed)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(7):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(4):
+                _lib.conv2d_fwd(d, x, None, packed, out=y)
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e) / 4)
+        ms = sorted(ts)[len(ts) // 2]
+        flop, byts = layer_work(3, cin, cout, n, b, 2, 2)
+        t_c, t_m = flop / (pk['tf_sust'] * 1e12), byts / (pk['hbm'] * 1e9)
+        out['%dto%d_c%d' % (cin, cout, n)] = {
+            'us': round(1e3 * ms, 1), 'tflops': round(flop / ms / 1e9, 1), 'gbs': round(byts / ms / 1e6, 1),
+            'bound': 'tensor' if t_c > t_m else 'hbm', 'frac_of_roof': round(max(t_c, t_m) * 1e3 / ms, 3),
+            'frac_of_bf16_burst_peak': round(flop / ms / 1e9 / pk['tf_burst'], 3)}
+    return out
+
+
 def conv_3to3_record(dev, threads):
     """BASELINE configs[0]: single CubeSphereConv2D forward, C48, 3 -> 3 channels, batch 1, float32."""
     from dlwp_cs_b200 import _lib
@@ -470,6 +507,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_extra and dtype == 'bf16':
         extra = {}
         extra['conv_3to3_b1'] = conv_3to3_record(dev, threads)
+        extra['conv_b64_shapes'] = conv_shape_records(dev, flush, peaks())
         # B = 1 latency of the headline rollout (report both B = 1 latency and batched-ensemble throughput)
         e1 = RolloutEngine(model, 1, n_face, args.rollout_steps, forcing_channels=C_FORC, dtype=tdt)
         e1.load_inputs(h_state[:1], h_forcing[:1])

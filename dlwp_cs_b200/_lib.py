@@ -28,6 +28,11 @@ class ConvWeights(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ('w_eq', 'w_pol', 'w_np', 'b_eq', 'b_pol', 'b_np')]
 
 
+class PackItem(ctypes.Structure):
+    _fields_ = [('desc', ctypes.POINTER(ConvDesc)), ('w', ConvWeights), ('src_cin', ctypes.c_int32),
+                ('src_cout', ctypes.c_int32), ('packed', ctypes.c_void_p), ('packed_t', ctypes.c_void_p)]
+
+
 class Chain(ctypes.Structure):
     _fields_ = [('dep', ctypes.c_void_p), ('dep_target', ctypes.c_uint32), ('done', ctypes.c_void_p),
                 ('tile_counter', ctypes.c_void_p), ('error_flag', ctypes.c_void_p)]
@@ -85,6 +90,7 @@ def load():
         'dlwpcs_conv2d_dgrad_act': (i32, [dp, vp, vp, vp, vp, vp, vp, i32, f32, f32, vp]),
         'dlwpcs_conv2d_head_fusable': (i32, [dp, dp]),
         'dlwpcs_rs_work_cuts': (i32, [dp, i32, vp, vp]),
+        'dlwpcs_pack_weights_batch': (i32, [ctypes.POINTER(PackItem), i32, vp]),
         'dlwpcs_conv2d_fwd_head': (i32, [dp, vp, vp, vp, dp, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
@@ -104,7 +110,7 @@ EXPORTED = ('dlwpcs_version', 'dlwpcs_last_error', 'dlwpcs_conv_out_edge', 'dlwp
             'dlwpcs_up2cat_fwd', 'dlwpcs_up2cat_bwd', 'dlwpcs_feed_gather', 'dlwpcs_trace_read',
             'dlwpcs_conv2d_fwd_chained', 'dlwpcs_chain_target', 'dlwpcs_split3',
             'dlwpcs_pack_weights2', 'dlwpcs_pad_bwd_act', 'dlwpcs_conv2d_dgrad_act', 'dlwpcs_conv2d_head_fusable',
-            'dlwpcs_conv2d_fwd_head', 'dlwpcs_rs_work_cuts')
+            'dlwpcs_conv2d_fwd_head', 'dlwpcs_rs_work_cuts', 'dlwpcs_pack_weights_batch')
 
 
 class DlwpcsError(RuntimeError):
@@ -236,6 +242,39 @@ def pack_weights2(d, w_eq, w_pol, w_np=None, b_eq=None, b_pol=None, b_np=None, f
     check(lib.dlwpcs_pack_weights2(ctypes.byref(d), ctypes.byref(cw), int(w_eq.shape[2]), int(w_eq.shape[3]), ptr(outs[0]),
                                    ptr(outs[1]), stream_ptr()))
     return outs[0], outs[1]
+
+
+def pack_weights_batch(entries, out=None):
+    """dlwpcs_pack_weights_batch: the bf16 images of many layers in ONE launch.  entries: list of (d, (w_eq, w_pol, w_np,
+    b_eq, b_pol, b_np), want_forward, want_transposed); the kernels may have fewer channels than the descriptor (zero
+    extension).  out: the list a previous call returned (its buffers are reused).  -> list of (packed, packed_t)."""
+    lib = load()
+    items = (PackItem * len(entries))()
+    keep, res = [], []
+    for i, (d, ws, want_f, want_t) in enumerate(entries):
+        require_cuda(*ws)
+        ws = [None if t is None else (t.detach() if (t.dtype == torch.float32 and t.is_contiguous())
+                                       else t.detach().to(torch.float32).contiguous()) for t in ws]
+        keep.append(ws)
+        bufs = []
+        for j, (want, tr) in enumerate(((want_f, 0), (want_t, 1))):
+            if not want:
+                bufs.append(None)
+                continue
+            nbytes = lib.dlwpcs_packed_weight_bytes(ctypes.byref(d), tr)
+            if nbytes < 0:
+                check(1)
+            old = out[i][j] if out is not None else None
+            bufs.append(old if (old is not None and old.numel() == nbytes) else
+                        torch.empty(nbytes, dtype=torch.uint8, device=ws[0].device))
+        items[i].desc = ctypes.pointer(d)
+        items[i].w = ConvWeights(*[t.data_ptr() if t is not None else None for t in ws])
+        items[i].src_cin, items[i].src_cout = int(ws[0].shape[2]), int(ws[0].shape[3])
+        items[i].packed = bufs[0].data_ptr() if bufs[0] is not None else None
+        items[i].packed_t = bufs[1].data_ptr() if bufs[1] is not None else None
+        res.append((bufs[0], bufs[1]))
+    check(lib.dlwpcs_pack_weights_batch(items, len(entries), stream_ptr()))
+    return res
 
 
 def conv2d_fwd(d, x0, x1, packed, out=None):

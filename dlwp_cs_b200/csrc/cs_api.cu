@@ -984,6 +984,22 @@ int dlwpcs_pack_weights2(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w
   return tc_pack_weights2(d, g, w, src_cin, src_cout, packed, packed_t, (cudaStream_t)stream);
 }
 
+int dlwpcs_pack_weights_batch(const dlwpcs_pack_item *items, int n_items, void *stream) {
+  CS_CHECK(items != nullptr && n_items >= 0, "null items");
+  for (int i = 0; i < n_items; ++i) {
+    const dlwpcs_pack_item &it = items[i];
+    Geometry g;
+    CS_CHECK(it.desc != nullptr, "item %d: null descriptor", i);
+    if (int rc = check_common(it.desc, &g)) return rc;
+    CS_CHECK(it.desc->x_dtype == DLWPCS_BF16, "dlwpcs_pack_weights_batch serves the bf16 tensor-core path");
+    CS_CHECK(it.w.w_eq && it.w.w_pol && (it.packed || it.packed_t), "item %d: null weights", i);
+    CS_CHECK(!it.desc->independent_north_pole || it.w.w_np, "item %d: independent_north_pole needs w_np", i);
+    CS_CHECK(!it.packed || !it.desc->use_bias || (it.w.b_eq && it.w.b_pol && (!it.desc->independent_north_pole || it.w.b_np)),
+             "item %d: use_bias needs biases", i);
+  }
+  return tc_pack_batch(items, n_items, (cudaStream_t)stream);
+}
+
 int dlwpcs_conv2d_fwd(const dlwpcs_conv_desc *d, const void *x0, const void *x1, const void *packed_w, void *y,
                       void *stream) {
   Geometry g;

@@ -74,6 +74,7 @@ int tc_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_c
                     void *packed, cudaStream_t st);
 int tc_pack_weights2(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, int src_cin,
                      int src_cout, void *packed, void *packed_t, cudaStream_t st, int classic_forward = 0);
+int tc_pack_batch(const dlwpcs_pack_item *items, int n, cudaStream_t st);
 int tc_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed,
                 void *y, const dlwpcs_chain *chain, cudaStream_t st);
 uint32_t tc_chain_target(const dlwpcs_conv_desc *d, const Geometry &g);
@@ -89,8 +90,7 @@ unsigned long long *tc_trace_next(int grid);
 // rs_eligible() says so (DLWPCS_RS=0 disables it).
 bool rs_eligible(const dlwpcs_conv_desc *d, const Geometry &g);
 int64_t rs_packed_weight_bytes(const dlwpcs_conv_desc *d, const Geometry &g);
-int rs_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, int src_cin, int src_cout,
-                    void *packed, cudaStream_t st);
+bool rs_pack_params(const dlwpcs_conv_desc *d, const Geometry &g, int *CinP, int *CoutP, long long *groupElems);
 int rs_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed, void *y,
                 cudaStream_t st);
 // 3x3 layer + the 1x1 CubeSphereConv2D that is its only consumer (the output layer of every cubed-sphere network,

@@ -32,6 +32,7 @@
 #include <vector>
 #include "cs_common.cuh"
 #include "cs_ptx.cuh"
+#include "cs_pack.cuh"
 
 namespace dlwpcs {
 
@@ -827,47 +828,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 // One launch packs the forward image (blockIdx.y = 0) and / or the transposed one (blockIdx.y = 1).  The source kernels
 // have the logical shape (kh, kw, scin, scout) and are zero-extended to the descriptor's (cin, cout): the bf16 path's
 // channel padding never materialises padded copies of the parameters.
-struct PackSide {
-  uint8_t *out;
-  int CinP, CoutP, KC;
-  long long groupElems;
-};
-__global__ void pack_tc_kernel(const float *__restrict__ w_eq, const float *__restrict__ w_pol,
-                               const float *__restrict__ w_np, const float *__restrict__ b_eq,
-                               const float *__restrict__ b_pol, const float *__restrict__ b_np, PackSide fwd, PackSide tr,
-                               int kh, int kw, int cin, int cout, int scin, int scout, int flip, int first_side) {
-  const int transposed = first_side + (int)blockIdx.y;
-  const PackSide S = transposed ? tr : fwd;
-  const long long groupElems = S.groupElems;
-  const int CoutP = S.CoutP, KC = S.KC;
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const int taps = kh * kw;
-  if (i < 3 * groupElems) {
-    const int g = (int)(i / groupElems);
-    long long r = i % groupElems;
-    const int e = (int)(r % 8); r /= 8;
-    const int n = (int)(r % CoutP); r /= CoutP;
-    const int k8 = (int)(r % (KC / 8)); r /= (KC / 8);
-    const int tap = (int)(r % taps);
-    const int kc = (int)(r / taps);
-    const int k = kc * KC + k8 * 8 + e;            // GEMM K index (input channel of this GEMM)
-    int u = tap / kw, v = tap % kw;
-    const int gemm_cin = transposed ? cout : cin, gemm_cout = transposed ? cin : cout;
-    float val = 0.f;
-    if (k < gemm_cin && n < gemm_cout) {
-      const float *src = g == 0 ? w_eq : (g == 1 ? w_pol : (w_np ? w_np : w_pol));
-      if (transposed) { u = kh - 1 - u; v = kw - 1 - v; }
-      const int us = (g == 2 && flip) ? kh - 1 - u : u;
-      const int ci = transposed ? n : k, co = transposed ? k : n;
-      if (ci < scin && co < scout) val = src[(((long long)us * kw + v) * scin + ci) * scout + co];
-    }
-    reinterpret_cast<__nv_bfloat16 *>(S.out)[i] = __float2bfloat16_rn(val);
-  } else if (i < 3 * groupElems + 3LL * CoutP) {
-    const int j = (int)(i - 3 * groupElems), g = j / CoutP, co = j % CoutP;
-    const float *src = g == 0 ? b_eq : (g == 1 ? b_pol : (b_np ? b_np : b_pol));
-    float *bo = reinterpret_cast<float *>(S.out + 3 * groupElems * 2);
-    bo[j] = (src && !transposed && co < scout) ? src[co] : 0.f;
-  }
+// One launch packs any number of images (forward / transposed / row-streamed forward) of any number of layers:
+// blockIdx.y = image, grid-stride over its elements (cs_pack.cuh).
+__global__ void pack_batch_kernel(const __grid_constant__ PackBatch B) {
+  const PackImage &S = B.im[blockIdx.y];
+  const long long total = 3 * S.groupElems + 3LL * S.CoutP;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    pack_element(S, i);
 }
 
 int env_int(const char *name, int dflt) {
@@ -1159,38 +1126,87 @@ int64_t tc_packed_weight_bytes(const dlwpcs_conv_desc *d, const Geometry &g, int
   return 3 * L.groupBytes + 3LL * L.CoutP * 4;
 }
 
+// Fill the image records of one layer (forward image in `packed`, transposed in `packed_t`; either may be null); returns
+// the number of records appended or -1 (error set).
+static int pack_images_of(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, int src_cin, int src_cout,
+                          void *packed, void *packed_t, int classic_forward, PackImage *im) {
+  if (!(src_cin >= 1 && src_cin <= d->cin && src_cout >= 1 && src_cout <= d->cout)) {
+    set_error("source kernel shape (%d, %d) does not fit the descriptor's (%d, %d)", src_cin, src_cout, d->cin, d->cout);
+    return -1;
+  }
+  int n = 0;
+  for (int t = 0; t < 2; ++t) {
+    void *out = t ? packed_t : packed;
+    if (!out) continue;
+    PackImage &I = im[n];
+    memset(&I, 0, sizeof(I));
+    I.w_eq = w->w_eq; I.w_pol = w->w_pol; I.w_np = d->independent_north_pole ? w->w_np : nullptr;
+    I.b_eq = d->use_bias ? w->b_eq : nullptr; I.b_pol = d->use_bias ? w->b_pol : nullptr;
+    I.b_np = (d->use_bias && d->independent_north_pole) ? w->b_np : nullptr;
+    I.out = (uint8_t *)out;
+    I.kh = d->kh; I.kw = d->kw; I.cin = d->cin; I.cout = d->cout; I.scin = src_cin; I.scout = src_cout;
+    I.flip = d->flip_north_pole;
+    if (t == 0 && !classic_forward && rs_eligible(d, g)) {
+      // the forward image goes to the row-streamed kernel's layout; the transposed one (if any) stays classic
+      I.kind = PACK_RS_FWD;
+      if (!rs_pack_params(d, g, &I.CinP, &I.CoutP, &I.groupElems)) return -1;
+      I.KC = I.CinP;
+    } else {
+      TcPlan L;
+      const char *r = make_plan(d, g, t ? d->cout : d->cin, t ? d->cin : d->cout, &L);
+      if (r) {
+        set_error("bf16 tensor-core path does not support this configuration: %s", r);
+        return -1;
+      }
+      I.kind = t ? PACK_CLASSIC_T : PACK_CLASSIC_FWD;
+      I.CinP = L.CinP; I.CoutP = L.CoutP; I.KC = L.KC;
+      I.groupElems = L.groupBytes / 2;
+    }
+    ++n;
+  }
+  return n;
+}
+
+static int launch_pack(const PackBatch &B, cudaStream_t st) {
+  if (B.n == 0) return 0;
+  long long most = 0;
+  for (int i = 0; i < B.n; ++i) {
+    const long long t = 3 * B.im[i].groupElems + 3LL * B.im[i].CoutP;
+    most = t > most ? t : most;
+  }
+  long long blocks = (most + 255) / 256;
+  if (blocks > 296) blocks = 296;                        // grid-stride: two waves of CTAs per image are plenty
+  pack_batch_kernel<<<dim3((unsigned)blocks, (unsigned)B.n), 256, 0, st>>>(B);
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int tc_pack_weights2(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, int src_cin,
                      int src_cout, void *packed, void *packed_t, cudaStream_t st, int classic_forward) {
   CS_CHECK(packed || packed_t, "nothing to pack");
-  if (packed && !classic_forward && rs_eligible(d, g)) {
-    // the forward image goes to the row-streamed kernel's layout; the transposed one (if any) stays classic
-    if (int rc = rs_pack_weights(d, g, w, src_cin, src_cout, packed, st)) return rc;
-    if (!packed_t) return 0;
-    packed = nullptr;
-  }
-  CS_CHECK(src_cin >= 1 && src_cin <= d->cin && src_cout >= 1 && src_cout <= d->cout,
-           "source kernel shape (%d, %d) does not fit the descriptor's (%d, %d)", src_cin, src_cout, d->cin, d->cout);
-  PackSide side[2];
-  long long total = 0;
-  for (int t = 0; t < 2; ++t) {
-    TcPlan L;
-    const char *r = make_plan(d, g, t ? d->cout : d->cin, t ? d->cin : d->cout, &L);
-    CS_CHECK(r == nullptr || !(t ? packed_t : packed), "bf16 tensor-core path does not support this configuration: %s", r);
-    side[t].out = (uint8_t *)(t ? packed_t : packed);
-    side[t].CinP = L.CinP; side[t].CoutP = L.CoutP; side[t].KC = L.KC;
-    side[t].groupElems = L.groupBytes / 2;
-    if (t ? packed_t : packed) {
-      const long long n = 3 * side[t].groupElems + 3LL * L.CoutP;
-      total = n > total ? n : total;
+  PackBatch B;
+  B.n = pack_images_of(d, g, w, src_cin, src_cout, packed, packed_t, classic_forward, B.im);
+  if (B.n < 0) return 1;
+  return launch_pack(B, st);
+}
+
+// Every layer of a network in one launch (or a few: PACK_MAX_IMAGES images per launch)
+int tc_pack_batch(const dlwpcs_pack_item *items, int n, cudaStream_t st) {
+  PackBatch B;
+  B.n = 0;
+  for (int i = 0; i < n; ++i) {
+    const dlwpcs_pack_item &it = items[i];
+    Geometry g;
+    if (int rc = derive_geometry(it.desc, &g)) return rc;
+    if (B.n + 2 > PACK_MAX_IMAGES) {
+      if (int rc = launch_pack(B, st)) return rc;
+      B.n = 0;
     }
+    const int k = pack_images_of(it.desc, g, &it.w, it.src_cin, it.src_cout, it.packed, it.packed_t, 0, B.im + B.n);
+    if (k < 0) return 1;
+    B.n += k;
   }
-  const int first = packed ? 0 : 1, count = (packed && packed_t) ? 2 : 1;
-  pack_tc_kernel<<<dim3((unsigned)((total + 255) / 256), (unsigned)count), 256, 0, st>>>(
-      w->w_eq, w->w_pol, d->independent_north_pole ? w->w_np : nullptr, d->use_bias ? w->b_eq : nullptr,
-      d->use_bias ? w->b_pol : nullptr, (d->use_bias && d->independent_north_pole) ? w->b_np : nullptr, side[0], side[1],
-      d->kh, d->kw, d->cin, d->cout, src_cin, src_cout, d->flip_north_pole, first);
-  CS_CUDA(cudaGetLastError());
-  return 0;
+  return launch_pack(B, st);
 }
 
 int tc_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, int transposed,

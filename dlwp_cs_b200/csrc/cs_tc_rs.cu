@@ -695,36 +695,6 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
   if (warp == RS_MMA_WARP) tmem_dealloc(tmem_base, 512u);
 }
 
-// ---- weight packing: packed[g][v][k8][n = j*CoutP + o][8] bf16, part j = kernel row 2 - j; + fp32 bias[3][CoutP] ----
-__global__ void pack_rs_kernel(const float *__restrict__ w_eq, const float *__restrict__ w_pol, const float *__restrict__ w_np,
-                               const float *__restrict__ b_eq, const float *__restrict__ b_pol, const float *__restrict__ b_np,
-                               uint8_t *out, int CinP, int CoutP, long long groupElems, int cin, int cout, int scin, int scout,
-                               int flip) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const int NT = 3 * CoutP;
-  if (i < 3 * groupElems) {
-    const int g = (int)(i / groupElems);
-    long long r = i % groupElems;
-    const int e = (int)(r % 8); r /= 8;
-    const int n = (int)(r % NT); r /= NT;
-    const int k8 = (int)(r % (CinP / 8));
-    const int v = (int)(r / (CinP / 8));
-    const int j = n / CoutP, o = n - j * CoutP, k = k8 * 8 + e, u = 2 - j;
-    float val = 0.f;
-    if (k < cin && o < cout && k < scin && o < scout) {
-      const float *src = g == 0 ? w_eq : (g == 1 ? w_pol : (w_np ? w_np : w_pol));
-      const int us = (g == 2 && flip) ? 2 - u : u;
-      val = src[(((long long)us * 3 + v) * scin + k) * scout + o];
-    }
-    reinterpret_cast<__nv_bfloat16 *>(out)[i] = __float2bfloat16_rn(val);
-  } else if (i < 3 * groupElems + 3LL * CoutP) {
-    const int jj = (int)(i - 3 * groupElems), g = jj / CoutP, co = jj % CoutP;
-    const float *src = g == 0 ? b_eq : (g == 1 ? b_pol : (b_np ? b_np : b_pol));
-    float *bo = reinterpret_cast<float *>(out + 3 * groupElems * 2);
-    bo[jj] = (src && co < scout) ? src[co] : 0.f;
-  }
-}
-
 int rs_env_int(const char *name, int dflt) {
   const char *s = getenv(name);
   return s && *s ? atoi(s) : dflt;
@@ -893,18 +863,18 @@ int64_t rs_packed_weight_bytes(const dlwpcs_conv_desc *d, const Geometry &g) {
   return 3LL * L.groupBytes + 3LL * L.CoutP * 4;
 }
 
-int rs_pack_weights(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_weights *w, int src_cin, int src_cout,
-                    void *packed, cudaStream_t st) {
+// layout parameters of the row-streamed kernel's packed image (cs_pack.cuh: pack_rs_element), for the pack launch in cs_tc.cu
+bool rs_pack_params(const dlwpcs_conv_desc *d, const Geometry &g, int *CinP, int *CoutP, long long *groupElems) {
   RsPlan L;
   const char *r = rs_make_plan(d, g, &L);
-  CS_CHECK(r == nullptr, "row-streamed kernel does not support this configuration: %s", r);
-  const long long groupElems = L.groupBytes / 2, total = 3 * groupElems + 3LL * L.CoutP;
-  pack_rs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      w->w_eq, w->w_pol, d->independent_north_pole ? w->w_np : nullptr, d->use_bias ? w->b_eq : nullptr,
-      d->use_bias ? w->b_pol : nullptr, (d->use_bias && d->independent_north_pole) ? w->b_np : nullptr, (uint8_t *)packed,
-      L.CinP, L.CoutP, groupElems, d->cin, d->cout, src_cin, src_cout, d->flip_north_pole);
-  CS_CUDA(cudaGetLastError());
-  return 0;
+  if (r) {
+    set_error("row-streamed kernel does not support this configuration: %s", r);
+    return false;
+  }
+  *CinP = L.CinP;
+  *CoutP = L.CoutP;
+  *groupElems = L.groupBytes / 2;
+  return true;
 }
 
 bool rs_head_eligible(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_desc *dh) {

@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 from torch.nn.parameter import UninitializedParameter
 
+from . import _lib
 from . import functional as F_cs
 
 
@@ -229,6 +230,24 @@ class CubeSphereConv2D(nn.modules.lazy.LazyModuleMixin, nn.Module):
         if not fused:
             y = self.activation(y)
         return y
+
+    def pack_descriptor(self, dtype=torch.bfloat16):
+        """(descriptor, parameter tuple) of this layer's packed weight images for activations of `dtype`, as ``forward``
+        builds them (channel counts padded to multiples of 8 on the bf16 path; batch / face edge are placeholders: the
+        images do not depend on them)."""
+        kh, kw, wcin, cout = self.equatorial_kernel.shape
+        bf = dtype == torch.bfloat16
+        pad_in, pad_out = ((-wcin) % 8, (-cout) % 8) if bf else (0, 0)
+        act = F_cs.resolve_activation(self.activation) if self._fused_act is not None else F_cs.resolve_activation(None)
+        n = max(8, (kh - 1) * self.dilation_rate[0] + 1, (kw - 1) * self.dilation_rate[1] + 1)
+        code = _lib.dtype_code(dtype)
+        d = _lib.make_desc(1, n, wcin + pad_in, cout + pad_out, (kh, kw), tuple(self.strides), tuple(self.dilation_rate),
+                           self.fuse_padding, self.padding == 'same', self.flip_north_pole,
+                           self.north_pole_kernel is not None, self.equatorial_bias is not None, act[0], act[1], act[2],
+                           code, code)
+        ws = (self.equatorial_kernel, self.polar_kernel, self.north_pole_kernel, self.equatorial_bias, self.polar_bias,
+              self.north_pole_bias)
+        return d, ws
 
     def compute_output_shape(self, input_shape):
         from ._lib import conv_out_edge

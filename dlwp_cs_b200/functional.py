@@ -65,6 +65,41 @@ def set_grad_sink(sink):
     return prev
 
 
+# Pre-packed weight images (set by the data-parallel trainer for the duration of a step): data_ptr of a layer's equatorial
+# kernel -> (layout key, packed, packed_t).  The trainer packs every layer of the model in ONE launch at the start of the step
+# (dlwpcs_pack_weights_batch) instead of one or two launches per layer inside the layers' forward.
+_PREPACKED = {}
+
+
+def _pack_key(d):
+    return (d.cin, d.cout, d.kh, d.kw, d.stride_h, d.stride_w, d.dil_h, d.dil_w, d.same, d.flip_north_pole,
+            d.independent_north_pole, d.use_bias, d.x_dtype, d.y_dtype)
+
+
+def prepack_model(model, dtype=torch.bfloat16, state=None):
+    """Pack the forward and transposed (dgrad) bf16 weight images of every CubeSphereConv2D of `model` in one launch and
+    publish them for the layers' forward (until ``clear_prepacked``).  state: what a previous call returned (buffers are
+    reused -- CUDA-graph friendly).  The first layer of a layer program needs no transposed image (its input has no
+    gradient)."""
+    from .custom import CubeSphereConv2D
+    layers = [m for m in model.modules() if isinstance(m, CubeSphereConv2D) and not m.has_uninitialized_params()]
+    program = getattr(model, 'program', None)
+    first = getattr(model, program[0]['name']) if program else None
+    entries, keys = [], []
+    for layer in layers:
+        d, ws = layer.pack_descriptor(dtype)
+        entries.append((d, ws, True, layer is not first))
+        keys.append(_pack_key(d))
+    res = _lib.pack_weights_batch(entries, out=state)
+    for layer, key, (packed, packed_t) in zip(layers, keys, res):
+        _PREPACKED[layer.equatorial_kernel.data_ptr()] = (key, packed, packed_t)
+    return res
+
+
+def clear_prepacked():
+    _PREPACKED.clear()
+
+
 def _pad_w(w, pad_in, pad_out):
     return w if (w is None or not (pad_in or pad_out)) else torch.nn.functional.pad(w, (0, pad_out, 0, pad_in))
 
@@ -89,7 +124,10 @@ class _CubeSphereConv(torch.autograd.Function):
                            cfg['flip_north_pole'], w_np is not None, b_eq is not None, cfg['act'][0], cfg['act'][1],
                            cfg['act'][2], _lib.dtype_code(x.dtype), _lib.dtype_code(cfg.get('out_dtype', x.dtype)))
         ctx.packed_t = None
-        if d.x_dtype == _lib.BF16:
+        pre = _PREPACKED.get(w_eq.data_ptr()) if d.x_dtype == _lib.BF16 else None
+        if pre is not None and pre[0] == _pack_key(d) and (pre[2] is not None or not ctx.needs_input_grad[0]):
+            packed, ctx.packed_t = pre[1], pre[2]
+        elif d.x_dtype == _lib.BF16:
             # one launch packs the forward image and -- when the input needs a gradient -- the transposed one for dgrad;
             # the kernels are zero-extended to the padded channel counts inside the pack kernel
             packed, ctx.packed_t = _lib.pack_weights2(d, w_eq, w_pol, w_np, b_eq, b_pol, b_np, forward=True,

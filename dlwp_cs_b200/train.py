@@ -15,6 +15,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+from . import functional as F_cs
 
 
 class FlatBuffers(object):
@@ -134,6 +135,8 @@ class DataParallelTrainer(object):
         self.model = model
         self.distributed = bool(distributed)      # False: a single-rank step even inside an initialised process group
         self.use_graph = use_graph
+        self.prepack = True            # bf16: pack the weight images of all layers in one launch per step
+        self._packed_state = None
         self._graphs = {}
         self.flat = FlatBuffers(model)
         if self.flat.param.device.type != 'cuda':
@@ -274,8 +277,18 @@ class DataParallelTrainer(object):
         _lib.adam_step_dev(self.flat.param, self.flat.grad, self.m, self.v, self.lr, self.beta1, self.beta2, self.eps,
                            self.step_counter, 1.0 / world)
 
+    def _prepack(self, x):
+        """bf16: the weight images of every layer in ONE launch at the start of the step (instead of one or two launches
+        per layer inside the layers' forward)."""
+        if x.dtype == torch.bfloat16 and self.prepack:
+            self._packed_state = F_cs.prepack_model(self.model, torch.bfloat16, state=self._packed_state)
+
     def _step_body(self, x, target):
-        loss = self.forward_backward(x, target)
+        self._prepack(x)
+        try:
+            loss = self.forward_backward(x, target)
+        finally:
+            F_cs.clear_prepacked()
         self._reduce_and_update()
         return loss
 
@@ -329,11 +342,15 @@ class DataParallelTrainer(object):
         solars, targets = rest[:n_steps - 1], rest[n_steps - 1:]
         self.loss.zero_()
         ys, xin = [], x
-        for s in range(n_steps):                 # the same layer objects (shared weights) at every step
-            y = self.model(xin)
-            ys.append(y)
-            if s + 1 < n_steps:
-                xin = repack_reference(y, solars[s], x, t_in, n_var)
+        self._prepack(x)
+        try:
+            for s in range(n_steps):                 # the same layer objects (shared weights) at every step
+                y = self.model(xin)
+                ys.append(y)
+                if s + 1 < n_steps:
+                    xin = repack_reference(y, solars[s], x, t_in, n_var)
+        finally:
+            F_cs.clear_prepacked()
         # keras multi-output loss: sum_s w_s * mse(y_s, t_s) with w_s = 1/S (train_cs.py:424-426)
         dys = [_lib.mse_loss_grad(y.detach(), t, self.loss, scale=1.0 / n_steps) for y, t in zip(ys, targets)]
         # shared layers: every parameter receives one gradient per model step, so the sink (which overwrites) is bypassed

@@ -92,6 +92,17 @@ int dlwpcs_pack_weights(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w,
 int dlwpcs_pack_weights2(const dlwpcs_conv_desc *d, const dlwpcs_conv_weights *w, int src_cin, int src_cout, void *packed,
                          void *packed_t, void *stream);
 
+/* bf16 path: the images of MANY layers in one launch -- what a training step does after every optimizer update (one launch
+ * instead of one or two per layer).  Per item: the layer's descriptor (batch / n are not used), its parameters, the logical
+ * kernel shape as for dlwpcs_pack_weights2, and the destination(s); either of packed / packed_t may be NULL.            */
+typedef struct dlwpcs_pack_item {
+  const dlwpcs_conv_desc *desc;
+  dlwpcs_conv_weights w;
+  int32_t src_cin, src_cout;
+  void *packed, *packed_t;
+} dlwpcs_pack_item;
+int dlwpcs_pack_weights_batch(const dlwpcs_pack_item *items, int n_items, void *stream);
+
 /* CubeSphereConv2D.call (+ optional fused padding / sampling / bias / activation).
  *   x0, x1 : the input source(s), dtype d->x_dtype;   y : (B,6,Hout,Wout,cout), dtype d->y_dtype.                     */
 int dlwpcs_conv2d_fwd(const dlwpcs_conv_desc *d, const void *x0, const void *x1, const void *packed_w, void *y,

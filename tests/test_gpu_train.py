@@ -216,3 +216,39 @@ def test_dgrad_act_equals_dgrad_then_activation_derivative(lib, dtype, halo, k):
         np.testing.assert_allclose(got.float().cpu().numpy(), ref.float().cpu().numpy(), rtol=2.0 ** -7, atol=1e-6)
     else:
         assert torch.equal(got, ref)
+
+
+def test_batch_pack_equals_per_layer_pack_and_trainer_step():
+    """dlwpcs_pack_weights_batch: the images of every layer in one launch are byte-identical to the per-layer packs, and an
+    optimizer step that uses them leaves exactly the same parameters as one that packs inside the layers' forward."""
+    from dlwp_cs_b200 import _lib, functional as F_cs
+    from dlwp_cs_b200.unet import CubeSphereUNet2
+    from dlwp_cs_b200.train import DataParallelTrainer
+    torch.manual_seed(2)
+    model = CubeSphereUNet2(18, 14, base=16).cuda()
+    res = F_cs.prepack_model(model, torch.bfloat16)
+    F_cs.clear_prepacked()
+    layers = model.layers_in_order()
+    assert len(res) == len(layers)
+    for i, (layer, (packed, packed_t)) in enumerate(zip(layers, res)):
+        d, ws = layer.pack_descriptor(torch.bfloat16)
+        one, one_t = _lib.pack_weights2(d, *ws, forward=True, transposed=i > 0)
+        assert torch.equal(packed, one)
+        assert (packed_t is None) == (i == 0)
+        if i > 0:
+            assert torch.equal(packed_t, one_t)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 6, 16, 16, 18, generator=g).cuda().bfloat16()
+    t = torch.randn(2, 6, 16, 16, 14, generator=g).cuda().bfloat16()
+    finals = []
+    for prepack in (True, False):
+        torch.manual_seed(2)
+        m = CubeSphereUNet2(18, 14, base=16).cuda()
+        tr = DataParallelTrainer(m, lr=1e-3, use_graph=False, distributed=False)
+        tr.prepack = prepack
+        for _ in range(2):
+            tr.step(x, t)
+        torch.cuda.synchronize()
+        finals.append(torch.cat([p.detach().flatten() for p in m.parameters()]).clone())
+        tr.close()
+    assert torch.equal(finals[0], finals[1])
