@@ -17,7 +17,8 @@
 //              y+1 into y-1, y, y+1; ...  tcgen05.mma instructions execute in issue order also when their accumulator
 //              column ranges overlap only partially (tools/umma_ring_probe.cu, exact on the B200), so the vertical shift-add
 //              costs nothing: a third of the A reads, and the epilogue reads finished sums exactly as before.
-//              A slot is zeroed by one MMA against a zero B operand (accumulate = 0) right before its first real MMA.
+//              Every MMA accumulates: the slots start at zero and the epilogue warp that drains a slot clears it again
+//              (tcgen05.st, no shared-memory traffic).
 //   pipeline   loaders (8 warps, one input row per stage) -> MMA issuer (1 warp) -> slot ring -> epilogue (8 warps: bias,
 //              capped leaky ReLU, bf16, per-warp compaction in shared memory, coalesced stores), all mbarrier-driven; the
 //              weights of the CTA's face group stay resident in shared memory.
@@ -37,7 +38,7 @@ namespace dlwpcs {
 
 namespace {
 
-constexpr int RS_THREADS = 576, RS_LOADERS = 256, RS_EPI = 256;
+constexpr int RS_THREADS = 576, RS_EPI = 256;
 constexpr int RS_EPI_WARP0 = 8, RS_TMA_WARP = 16, RS_MMA_WARP = 17;
 constexpr int RS_MAXSLOTS = 16, RS_MAXSTAGES = 16;
 constexpr int RS_NPOS = 130;       // 128 lanes + (kw - 1) positions of overhang
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
   const RsPlan &L = P.L;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t rows0 = base, wbase = base + L.off_w, zbase = base + L.off_zero, misc = base + L.off_misc;
+  const uint32_t rows0 = base, wbase = base + L.off_w, misc = base + L.off_misc;
   // barriers (8 bytes each): rfull[16] rempty[16] sfull[16] sempty[16] wfull wempty; tensor-memory slot
   const uint32_t bar_rfull = misc, bar_rempty = misc + 128, bar_sfull = misc + 256, bar_sempty = misc + 384,
                  bar_wfull = misc + 512, bar_wempty = misc + 520, tmem_slot = misc + 528, bar_hfull = misc + 544;
@@ -193,14 +194,21 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     mbar_init(bar_hfull + 8, 1);
     fence_mbar_init();
   }
-  // the zero B operand of the slot-clearing MMA
-  for (int i = tid; i < 2 * L.CoutP * 16 / 16; i += RS_THREADS) st_shared16(zbase + 16u * (uint32_t)i, make_uint4(0, 0, 0, 0));
-  fence_proxy_async();
   if (warp == RS_MMA_WARP) tmem_alloc(tmem_slot, 512u);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(gen + (tmem_slot - base));
+  // Every accumulator slot starts at zero and is cleared again by the epilogue warp that drains it (tcgen05.st, no shared-
+  // memory traffic), so every MMA accumulates: the issue loop has no first-touch special case.
+  if (warp >= RS_EPI_WARP0 && warp < RS_EPI_WARP0 + 8) {
+    const uint32_t lanes = (uint32_t)((warp & 3) * 32) << 16;
+    for (int c = ((warp - RS_EPI_WARP0) >> 2) * 16; c < L.NS * L.CoutP; c += 32) tmem_st16_fill(tmem_base + lanes + (uint32_t)c, 0u);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
   // programmatic dependent launch (see cs_tc.cu): whatever a previous kernel may have written -- activations (loaders),
   // packed weights (TMA lane), bias (epilogue) -- is read behind griddepcontrol.wait
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -240,7 +248,6 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
                            (1ull << 16);
     // B: un-swizzled K-major core matrices [k8][n][8]: SBO = 128 B (next 8 columns), LBO = NT*16 B (next k8)
     const uint64_t b_fix = ((uint64_t)((128u >> 4) | (1u << 14)) << 32) | ((uint64_t)((uint32_t)L.NT & 0x3FFFu) << 16);
-    const uint64_t z_desc = (((uint64_t)((128u >> 4) | (1u << 14)) << 32) | ((uint64_t)(coutp & 0x3FFFu) << 16)) | (zbase >> 4);
     const uint32_t rb16 = (uint32_t)L.RB >> 4, unit16 = (uint32_t)L.unitBytes >> 4, b_jstep = (uint32_t)(2 * L.NT * 16) >> 4;
     const uint64_t b_w = b_fix | (wbase >> 4);
     // ring positions kept incrementally (no divisions in the row loop): row stage + parity; slot of the output row that is
@@ -267,7 +274,6 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
         if (P.trace && !traced) { rs_trace(P, 3, lane == 0); traced = true; }
         fence_proxy_async();               // the loaders' generic-proxy writes, acquired through the barrier, before the MMAs' reads
         const uint64_t a_row = a_fix | ((rows0 + stage * (uint32_t)L.stageBytes) >> 4);
-        if (yi < H && !(P.knock & 2)) umma_bf16_elect(tmem_base + zs * coutp, a_row, z_desc, idesc0 | ((coutp >> 3) << 17), 0u);
         // parts j = 0..2 of the stacked N (kernel rows 2, 1, 0) -> output rows yi - 2 + j, those inside [0, H)
         const int jlo = yi >= 2 ? 0 : 2 - yi, jhi = (H + 1 - yi) < 2 ? (H + 1 - yi) : 2;
         const uint32_t t0 = yi >= 2 ? cs : s0;
@@ -426,7 +432,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
           tmem_ld16(trow + (uint32_t)n0, v);
           if (two) tmem_ld16(trow + (uint32_t)n0 + 16u, v + 16);
           tmem_ld_wait();
+          tmem_st16_fill(trow + (uint32_t)n0, 0u);
+          if (two) tmem_st16_fill(trow + (uint32_t)n0 + 16u, 0u);
           if (n0 + 32 >= L.CoutP) {
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_sempty + 8 * slot_o);
@@ -514,7 +523,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
           tmem_ld16(trow + (uint32_t)n0, v);
           if (two) tmem_ld16(trow + (uint32_t)n0 + 16u, v + 16);
           tmem_ld_wait();
+          tmem_st16_fill(trow + (uint32_t)n0, 0u);          // clear what was read (the next use of the slot accumulates)
+          if (two) tmem_st16_fill(trow + (uint32_t)n0 + 16u, 0u);
           if (n0 + 32 >= L.CoutP) {          // everything of the slot is in registers: hand it back to the MMA issuer
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_sempty + 8 * slot_o);
@@ -579,7 +591,6 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     const bool first = c < P.c0;
     const __nv_bfloat16 *src = first ? P.x0 : P.x1;
     const int C = first ? P.c0 : P.c1, cc = first ? c : c - P.c0, mode = first ? P.mode0 : P.mode1;
-    const int32_t *tab = first ? P.tab0 : P.tab1;
     const int ppb = first ? P.ppb0 : P.ppb1;
     const bool chan_ok = c < P.cin;
     const int pstep = 32 >> L.logS, l0 = lane >> L.logS;
@@ -756,7 +767,7 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
   int off = 0;
   L->off_w = 0;        // filled below, after the row stages
   const int wB = (L->groupBytes + 1023) / 1024 * 1024;
-  const int zeroB = 2 * L->CoutP * 16;
+  const int zeroB = 0;
   // per loader warp: {table offset, batch element} of the strip's positions + two double-buffered rows of table entries
   const int posB = 8 * RS_NPIXP * 8 + 8 * 4 * RS_NPIXP * 4;
   const int headB = dh ? (3 * L->hwBytes + 127) / 128 * 128 + (3 * L->CoutP2 * 4 + 127) / 128 * 128 + 2 * 128 * L->CoutP * 2 + 1024 : 0;

@@ -41,6 +41,8 @@ tr = _lib.trace_read(reset=False)
 # the graph's kernel nodes keep the trace slots they were captured with (after the 11 eager warm-up launches); every
 # replay overwrites them, so the buffer holds the stamps of the last replay
 names = [p[0] for p in eng.plan]
+if getattr(eng, 'fused_head', None) is not None:          # the 1x1 output layer runs inside the launch in front of it
+    names = names[:eng.fused_head] + [names[eng.fused_head] + '+' + names[eng.fused_head + 1]] + names[eng.fused_head + 2:]
 nl = len(names)
 # keep the launches of the last captured model step; subtract in integers (ns since the epoch do not fit a float64)
 total = tr.shape[0]
@@ -52,7 +54,7 @@ last[:, :, 7] = raw[:, :, 7]
 t0 = 0.0
 rows = []
 labels = ['entry', 'prologue', 'dep', 'patch0', 'acc0', 'epi_last', 'exit']
-print('%-12s %5s | ' % ('layer', 'ctas') + ' | '.join('%-22s' % l for l in labels) + ' | tiles')
+print('%-22s %5s | ' % ('layer', 'ctas') + ' | '.join('%-22s' % l for l in labels) + ' | tiles')
 prev_exit = None
 for i, nm in enumerate(names):
     v = valid[i]
@@ -69,7 +71,7 @@ for i, nm in enumerate(names):
         d['gap_prev_last_exit_to_first_patch0_us'] = round(float(r[:, 3].min() - prev_exit), 2)
     prev_exit = float(r[:, 6].max())
     rows.append(d)
-    print('%-12s %5d | ' % (nm, v.sum()) + ' | '.join(cells) + ' | %d-%d' % (tiles.min(), tiles.max()))
+    print('%-22s %5d | ' % (nm, v.sum()) + ' | '.join(cells) + ' | %d-%d' % (tiles.min(), tiles.max()))
 step_us = (last[:, :, 6][valid].max() - t0) / 1e3
 busy = sum(float(np.median((last[i][valid[i]][:, 5] - last[i][valid[i]][:, 3]))) for i in range(nl)) / 1e3
 print('step: %.1f us; sum over layers of median (last epilogue - first patch) = %.1f us' % (step_us, busy))
