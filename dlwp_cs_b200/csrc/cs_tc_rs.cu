@@ -804,36 +804,38 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
 void rs_work_cuts(int batch, int Wv, int Hout, int grid, int *cut_s, int *cut_y) {
   const long long ns0 = (4LL * batch * Wv + 127) / 128, ns1 = (1LL * batch * Wv + 127) / 128;
   const long long strips = ns0 + 2 * ns1, R = strips * Hout;
-  const int snap = 1;            // a cut inside a strip costs one more unit (2 rows) wherever it falls: no snapping needed
   const double unit_cost = 2.0, group_cost = 3.0;
-  const double total = (double)R + unit_cost * (double)(strips + grid - 1) + group_cost * 2.0;
-  const double per = total / grid;
-  long long pos = 0;
-  double acc = 0.0;
-  for (int c = 0; c < grid; ++c) {
-    cut_s[c] = (int)(pos / Hout);
-    cut_y[c] = (int)(pos % Hout);
-    const double target = per * (c + 1);
-    bool first = true;
-    while (pos < R) {
-      const long long sidx = pos / Hout;
-      const int y = (int)(pos % Hout);
-      double enter = (first || y == 0) ? unit_cost : 0.0;
-      if (y == 0 && !first && (sidx == ns0 || sidx == ns0 + ns1)) enter += group_cost;
-      const int left = Hout - y;
-      int x = (int)(target - acc - enter);
-      if (c == grid - 1) x = left;                       // the last CTA takes what remains
-      if (x > left) x = left;
-      if (x < left) {                                    // the share ends inside this strip: snap
-        if (x < snap && !first) break;                   // not worth a new unit: stop at the boundary behind us
-        if (x < snap) x = snap < left ? snap : left;     // a CTA with work left never goes empty-handed
-        if (left - x < snap) x = left;
+  // the total cost depends on the number of units, which depends on the cuts: two passes (the first with an upper bound)
+  double total = (double)R + unit_cost * (double)(strips + grid - 1) + group_cost * 2.0;
+  for (int pass = 0; pass < 3; ++pass) {
+    const double per = total / grid;
+    long long pos = 0;
+    double acc = 0.0;
+    for (int c = 0; c < grid; ++c) {
+      cut_s[c] = (int)(pos / Hout);
+      cut_y[c] = (int)(pos % Hout);
+      const double target = per * (c + 1);
+      bool first = true;
+      while (pos < R) {
+        const long long sidx = pos / Hout;
+        const int y = (int)(pos % Hout);
+        double enter = (first || y == 0) ? unit_cost : 0.0;
+        if (y == 0 && !first && (sidx == ns0 || sidx == ns0 + ns1)) enter += group_cost;
+        const int left = Hout - y;
+        int x = (int)(target - acc - enter + 0.5);
+        if (c == grid - 1) x = left;                       // the last CTA takes what remains
+        if (x > left) x = left;
+        if (x < left) {                                    // the share ends inside this strip
+          if (x < 1 && !first) break;                      // not worth a new unit: stop at the boundary behind us
+          if (x < 1) x = 1;                                // a CTA with work left never goes empty-handed
+        }
+        acc += enter + x;
+        pos += x;
+        first = false;
+        if (x < left) break;
       }
-      acc += enter + x;
-      pos += x;
-      first = false;
-      if (x < left) break;
     }
+    total = acc;                                           // what the cuts actually cost
   }
   cut_s[grid] = (int)strips;
   cut_y[grid] = 0;
