@@ -323,6 +323,8 @@ def main():
     ap.add_argument('--ref-steps', type=int, default=25, help='CPU arm: 6-hour steps per bench step (bounded sample)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--host-chunk', type=int, default=int(os.environ.get('DLWPCS_HOST_CHUNK', '2')),
+                    help='end-to-end arm: model steps per device->host transfer (RolloutEngine.run_to_host chunk)')
     ap.add_argument('--no-train', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the configs[0] / B=1 latency / C96 sub-records')
     ap.add_argument('--train-batch', type=int, default=32, help='training samples per GPU per step')
@@ -414,14 +416,14 @@ def main():
     # ---------------- end-to-end arm: pinned host inputs in, whole forecast out to pinned host memory, every step
     # (RolloutEngine.run_to_host: the device->host transfer of finished model steps overlaps the remaining steps)
     for _ in range(2):
-        h_ring = eng.run_to_host(h_state, h_forcing)
+        h_ring = eng.run_to_host(h_state, h_forcing, chunk=args.host_chunk)
     barrier()
     ev2 = []
     for _ in range(args.steps):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        h_ring = eng.run_to_host(h_state, h_forcing)
+        h_ring = eng.run_to_host(h_state, h_forcing, chunk=args.host_chunk)
         e.record()
         ev2.append((s, e))
     barrier()

@@ -569,25 +569,34 @@ class RolloutEngine(object):
         side = self._side
         if self.chain:
             self._chain_mem.zero_()
-        for t0 in range(0, self.steps, self.host_chunk):
+        nb = len(self._stage)
+        done = [None] * nb                       # event of the transfer that last read each staging buffer
+        for k, t0 in enumerate(range(0, self.steps, self.host_chunk)):
             t1 = min(self.steps, t0 + self.host_chunk)
             for t in range(t0, t1):
                 self._step(t, chained=self.chain and t > 0)
+            # strip the pad channels on the compute stream (a small copy kernel), so that the side stream carries nothing but
+            # back-to-back device -> host transfers
+            stage = self._stage[k % nb]
+            if done[k % nb] is not None:
+                main.wait_event(done[k % nb])
+            stage[:t1 - t0].copy_(self.ring[t0:t1, ..., :self.cp])
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                stage = self._stage[(t0 // self.host_chunk) % 2]
-                stage[:t1 - t0].copy_(self.ring[t0:t1, ..., :self.cp])            # strip the pad channels on the device
                 self.host_ring[t0:t1].copy_(stage[:t1 - t0], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                done[k % nb] = ev
         main.wait_stream(side)
 
-    def run_to_host(self, state, forcing=None, chunk=5):
+    def run_to_host(self, state, forcing=None, chunk=2):
         """Initial conditions from (pinned) host tensors in, whole forecast (steps,B,6,N,N,Cout) out in pinned host memory
         owned by the engine.  Everything is enqueued on the current stream; synchronise before reading the result."""
         if self.host_ring is None or self.host_chunk != chunk:
             self.host_chunk = chunk
             shape = (self.steps, self.batch, 6, self.n, self.n, self.cp)
             self.host_ring = torch.empty(shape, dtype=self.dtype).pin_memory()
-            self._stage = [torch.empty((chunk,) + shape[1:], dtype=self.dtype, device=self.device) for _ in range(2)]
+            self._stage = [torch.empty((chunk,) + shape[1:], dtype=self.dtype, device=self.device) for _ in range(4)]
             self._side = torch.cuda.Stream(device=self.device)
             self.graph_host = None
         self.load_inputs(state, forcing)
