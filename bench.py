@@ -184,12 +184,16 @@ def time_layers(eng, flush, reps=10):
         if fused is not None and i == fused:          # the 1x1 output layer runs inside this launch
             head = eng.plan[i + 1]
             launches.append((name + '+' + head[0], d, eng._src(s0, 0), eng._src(s1, 0), packed, eng.ring[0], head))
+        elif i in getattr(eng, 'pool_out', {}):       # this launch also writes the 2x2 mean of its output
+            launches.append((name, d, eng._src(s0, 0), eng._src(s1, 0), packed, o, ('pool', eng.buf[eng.pool_out[i]])))
         else:
             launches.append((name, d, eng._src(s0, 0), eng._src(s1, 0), packed, o, None))
 
     def go(d, a, b, packed, o, head):
         if head is None:
             _lib.conv2d_fwd(d, a, b, packed, out=o)
+        elif head[0] == 'pool':
+            _lib.conv2d_fwd_pool(d, a, b, packed, out=o, out_pool=head[1])
         else:
             _lib.conv2d_fwd_head(d, a, b, packed, head[1], head[5], out=o)
     for _ in range(3):

@@ -90,6 +90,8 @@ def load():
         'dlwpcs_conv2d_dgrad_act': (i32, [dp, vp, vp, vp, vp, vp, vp, i32, f32, f32, vp]),
         'dlwpcs_conv2d_head_fusable': (i32, [dp, dp]),
         'dlwpcs_rs_work_cuts': (i32, [dp, i32, vp, vp]),
+        'dlwpcs_conv2d_pool_fusable': (i32, [dp]),
+        'dlwpcs_conv2d_fwd_pool': (i32, [dp, vp, vp, vp, vp, vp, vp]),
         'dlwpcs_pack_weights_batch': (i32, [ctypes.POINTER(PackItem), i32, vp]),
         'dlwpcs_conv2d_fwd_head': (i32, [dp, vp, vp, vp, dp, vp, vp, vp]),
     }
@@ -110,7 +112,8 @@ EXPORTED = ('dlwpcs_version', 'dlwpcs_last_error', 'dlwpcs_conv_out_edge', 'dlwp
             'dlwpcs_up2cat_fwd', 'dlwpcs_up2cat_bwd', 'dlwpcs_feed_gather', 'dlwpcs_trace_read',
             'dlwpcs_conv2d_fwd_chained', 'dlwpcs_chain_target', 'dlwpcs_split3',
             'dlwpcs_pack_weights2', 'dlwpcs_pad_bwd_act', 'dlwpcs_conv2d_dgrad_act', 'dlwpcs_conv2d_head_fusable',
-            'dlwpcs_conv2d_fwd_head', 'dlwpcs_rs_work_cuts', 'dlwpcs_pack_weights_batch')
+            'dlwpcs_conv2d_fwd_head', 'dlwpcs_rs_work_cuts', 'dlwpcs_pack_weights_batch', 'dlwpcs_conv2d_pool_fusable',
+            'dlwpcs_conv2d_fwd_pool')
 
 
 class DlwpcsError(RuntimeError):
@@ -294,6 +297,22 @@ def rs_work_cuts(d, grid):
     if load().dlwpcs_rs_work_cuts(ctypes.byref(d), grid, cs, cy) != grid:
         return None
     return [(int(cs[i]), int(cy[i])) for i in range(grid + 1)]
+
+
+def conv2d_pool_fusable(d):
+    """True when the layer `d` can write the 2x2 mean of its output itself (dlwpcs_conv2d_fwd_pool)."""
+    return bool(load().dlwpcs_conv2d_pool_fusable(ctypes.byref(d)))
+
+
+def conv2d_fwd_pool(d, x0, x1, packed, out=None, out_pool=None):
+    """dlwpcs_conv2d_fwd_pool: -> (y, 2x2 mean of y), both bf16."""
+    require_cuda(x0, x1, packed, out, out_pool)
+    shp = out_shape(d)
+    y = out if out is not None else torch.empty(shp, dtype=torch.bfloat16, device=x0.device)
+    yp = out_pool if out_pool is not None else torch.empty((shp[0], 6, shp[2] // 2, shp[3] // 2, shp[4]), dtype=torch.bfloat16,
+                                                            device=x0.device)
+    check(load().dlwpcs_conv2d_fwd_pool(ctypes.byref(d), ptr(x0), ptr(x1), ptr(packed), ptr(y), ptr(yp), stream_ptr()))
+    return y, yp
 
 
 def conv2d_head_fusable(d, head):

@@ -1022,6 +1022,22 @@ int dlwpcs_rs_work_cuts(const dlwpcs_conv_desc *d, int grid, int32_t *cut_s, int
   return rs_debug_cuts(d, g, grid, cut_s, cut_y);
 }
 
+int dlwpcs_conv2d_pool_fusable(const dlwpcs_conv_desc *d) {
+  Geometry g;
+  if (!d || check_common(d, &g)) return 0;
+  return rs_pool_eligible(d, g) ? 1 : 0;
+}
+
+int dlwpcs_conv2d_fwd_pool(const dlwpcs_conv_desc *d, const void *x0, const void *x1, const void *packed_w, void *y,
+                           void *y_pool, void *stream) {
+  Geometry g;
+  if (int rc = check_common(d, &g)) return rc;
+  CS_CHECK(rs_pool_eligible(d, g), "this layer cannot write its pooled output itself (dlwpcs_conv2d_pool_fusable)");
+  if (d->batch == 0) return 0;
+  CS_CHECK(x0 && packed_w && y && y_pool && (d->c1 == 0 || x1), "null tensor pointer");
+  return rs_conv_fwd_pool(d, g, x0, x1, packed_w, y, y_pool, (cudaStream_t)stream);
+}
+
 int dlwpcs_conv2d_head_fusable(const dlwpcs_conv_desc *d, const dlwpcs_conv_desc *head) {
   Geometry g, gh;
   if (!d || !head || check_common(d, &g) || check_common(head, &gh)) return 0;

@@ -96,6 +96,10 @@ int rs_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, co
 // 3x3 layer + the 1x1 CubeSphereConv2D that is its only consumer (the output layer of every cubed-sphere network,
 // Azure/train_cs.py:228) in one launch: a second MMA per output row inside the epilogue; the 3x3 layer's output never
 // reaches HBM.  packed_h = the head's classic packed image.
+// the layer's output and its 2x2 mean (AveragePooling3D((1,2,2)), train_cs.py:197: the next layer's input) from one launch
+bool rs_pool_eligible(const dlwpcs_conv_desc *d, const Geometry &g);
+int rs_conv_fwd_pool(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed, void *y,
+                     void *ypool, cudaStream_t st);
 int rs_debug_cuts(const dlwpcs_conv_desc *d, const Geometry &g, int grid, int *cut_s, int *cut_y);
 bool rs_head_eligible(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs_conv_desc *dh);
 int rs_conv_fwd_head(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed,

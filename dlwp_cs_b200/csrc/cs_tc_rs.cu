@@ -68,6 +68,7 @@ struct RsP {
   const uint8_t *hw;                 // head: packed 1x1 weights [3][k8][CoutP2][8] (the classic kernel's image)
   const float *hbias;                // head: [3][CoutP2]
   __nv_bfloat16 *y2;                 // head output (B,6,Hout,Wout,cout2); y is not written
+  __nv_bfloat16 *ypool;              // pool mode: second output (B,6,Hout/2,Wout/2,cout) = AveragePooling3D((1,2,2)) of y
   int cout2, act2;
   float slope2, maxv2;
   int batch, n, Hout, Wout;
@@ -155,8 +156,10 @@ __device__ __forceinline__ void rs_image(int grp, int i, int &b, int &f) {
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------
-template <int KC16T, bool HEAD>
+// MODE: 0 plain, 1 fused 1x1 head (section 4.7 of DESIGN.md), 2 second output = 2x2 mean of the output (pooled copy)
+template <int KC16T, int MODE>
 __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_constant__ RsP P) {
+  constexpr bool HEAD = MODE == 1;
   extern __shared__ uint8_t smem_raw[];
   const RsPlan &L = P.L;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -486,6 +489,146 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
       rs_advance(W, u);
       ++nunits;
     }
+    } else if constexpr (MODE == 2) {
+    // ---- pool mode (32 padded output channels): besides the layer's output, its 2x2 mean (AveragePooling3D((1,2,2)),
+    // train_cs.py:197) is written as a second tensor, so that the next layer reads a plain source (a quarter of the bytes, and
+    // through asynchronous copies instead of registers).  The two warps of a lane quarter take alternate ROW PAIRS; lanes
+    // 2i, 2i+1 hold horizontally adjacent pixels (Wv is even).  The mean is taken over the bf16-rounded outputs in the order
+    // (r,c), (r,c+1), (r+1,c), (r+1,c+1) and rounded to bf16 once, like the classic kernel's pooled load.
+    int *pixp = s_pix + 256 + (warp - RS_EPI_WARP0) * 32;
+    const int Hp = P.Hout >> 1, Wp = P.Wout >> 1;
+    uint32_t slot = 0, eph = 0, nrow = 0;
+    for (RsWork W = W0; rs_more(W) && !(P.knock & 8);) {
+      const RsUnit u = rs_unit(W);
+      const int H = u.y1 - u.y0;                  // even, and u.y0 is even (host cuts)
+      const float *bias = s_bias + u.grp * L.CoutP;
+      const int p = u.sl * 128 + quarter * 32 + lane;
+      const int img = p / L.Wv, cv = p - img * L.Wv;
+      const bool ok = p < u.Lg && cv < P.Wout;
+      int b, f;
+      rs_image(u.grp, img, b, f);
+      const int opix0 = ((b * 6 + f) * P.Hout + u.y0) * P.Wout + cv;
+      const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+      const int nvalid = __popc(okmask);
+      const uint32_t prow = (uint32_t)__popc(okmask & ((1u << lane) - 1u));
+      const bool okp = ok && !(lane & 1);         // this lane writes the pooled pixel of columns cv, cv + 1
+      const unsigned okpmask = __ballot_sync(0xffffffffu, okp);
+      const int nvalidp = __popc(okpmask);
+      const uint32_t prowp = (uint32_t)__popc(okpmask & ((1u << lane) - 1u));
+      __syncwarp();
+      if (ok) pixw[prow] = opix0;
+      if (okp) pixp[prowp] = ((b * 6 + f) * Hp + (u.y0 >> 1)) * Wp + (cv >> 1);
+      __syncwarp();
+      const uint32_t srow = stg + prow * rowB, srowp = stg + prowp * rowB;
+      const uint32_t total = (uint32_t)nvalid * rowB, totalp = (uint32_t)nvalidp * rowB;
+      uint32_t prev[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) prev[i] = 0u;
+#pragma unroll 1
+      for (int o = 0; o < H; ++o) {
+        const uint32_t slot_o = slot, eph_o = eph, mine = ((int)((nrow >> 1) & 1u) == half);
+        ++nrow;
+        if (++slot == NS) { slot = 0; eph ^= 1u; }
+        if (!mine) continue;
+        rs_wait(bar_sfull + 8 * slot_o, eph_o, P.err, 2);
+        tc_fence_after();
+        if (P.trace && !etraced) { rs_trace(P, 4, tid == RS_EPI_WARP0 * 32); etraced = true; }
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot_o * (uint32_t)L.CoutP;
+        uint32_t v[32], cur[16];
+        tmem_ld16(trow, v);
+        tmem_ld16(trow + 16u, v + 16);
+        tmem_ld_wait();
+        tmem_st16_fill(trow, 0u);
+        tmem_st16_fill(trow + 16u, 0u);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sempty + 8 * slot_o);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float r[16];
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const float4 bv = *reinterpret_cast<const float4 *>(bias + 16 * h + 4 * k4);
+            r[4 * k4 + 0] = __uint_as_float(v[16 * h + 4 * k4 + 0]) + bv.x;
+            r[4 * k4 + 1] = __uint_as_float(v[16 * h + 4 * k4 + 1]) + bv.y;
+            r[4 * k4 + 2] = __uint_as_float(v[16 * h + 4 * k4 + 2]) + bv.z;
+            r[4 * k4 + 3] = __uint_as_float(v[16 * h + 4 * k4 + 3]) + bv.w;
+          }
+          if (act_fast) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r[e] = fminf(fmaxf(r[e], P.slope * r[e]), P.maxv);
+          } else if (P.act != DLWPCS_ACT_NONE) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r[e] = act_apply(r[e], P.act, P.slope, P.maxv);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cur[8 * h + j] = pack_bf16x2(r[2 * j], r[2 * j + 1]);
+        }
+        if (ok) {
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8)
+            if (8 * c8 + 8 <= P.cout)
+              st_shared16(srow + (((uint32_t)c8 ^ ((prow >> kshift) & smask)) << 4),
+                          make_uint4(cur[4 * c8], cur[4 * c8 + 1], cur[4 * c8 + 2], cur[4 * c8 + 3]));
+        }
+        __syncwarp();
+        {
+          const uint32_t rowoff = (uint32_t)(o * P.Wout);
+          for (uint32_t off = (uint32_t)lane * 16u; off < total; off += 512u) {
+            uint32_t row, ch;
+            if (cprLog >= 0) { row = off >> (4 + cprLog); ch = (off >> 4) & (cpr - 1u); }
+            else { row = off / rowB; ch = (off - row * rowB) >> 4; }
+            uint4 q;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                         : "r"(stg + row * rowB + ((ch ^ ((row >> kshift) & smask)) << 4)));
+            uint8_t *gdst = reinterpret_cast<uint8_t *>(P.y) + ((size_t)((uint32_t)pixw[row] + rowoff)) * rowB + (ch << 4);
+            *reinterpret_cast<uint4 *>(gdst) = q;
+          }
+        }
+        __syncwarp();
+        if (!(o & 1)) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) prev[i] = cur[i];
+          continue;
+        }
+        // second row of the pair: 2x2 mean with the neighbour lane's columns
+        uint32_t pl[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t a2 = __shfl_xor_sync(0xffffffffu, prev[i], 1), b2 = __shfl_xor_sync(0xffffffffu, cur[i], 1);
+          const float lo = 0.25f * (((__uint_as_float(prev[i] << 16) + __uint_as_float(a2 << 16)) + __uint_as_float(cur[i] << 16)) +
+                                    __uint_as_float(b2 << 16));
+          const float hi = 0.25f * (((__uint_as_float(prev[i] & 0xFFFF0000u) + __uint_as_float(a2 & 0xFFFF0000u)) +
+                                     __uint_as_float(cur[i] & 0xFFFF0000u)) + __uint_as_float(b2 & 0xFFFF0000u));
+          pl[i] = pack_bf16x2(lo, hi);
+        }
+        if (okp) {
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8)
+            if (8 * c8 + 8 <= P.cout)
+              st_shared16(srowp + (((uint32_t)c8 ^ ((prowp >> kshift) & smask)) << 4),
+                          make_uint4(pl[4 * c8], pl[4 * c8 + 1], pl[4 * c8 + 2], pl[4 * c8 + 3]));
+        }
+        __syncwarp();
+        {
+          const uint32_t rowoff = (uint32_t)((o >> 1) * Wp);
+          for (uint32_t off = (uint32_t)lane * 16u; off < totalp; off += 512u) {
+            uint32_t row, ch;
+            if (cprLog >= 0) { row = off >> (4 + cprLog); ch = (off >> 4) & (cpr - 1u); }
+            else { row = off / rowB; ch = (off - row * rowB) >> 4; }
+            uint4 q;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                         : "r"(stg + row * rowB + ((ch ^ ((row >> kshift) & smask)) << 4)));
+            uint8_t *gdst = reinterpret_cast<uint8_t *>(P.ypool) + ((size_t)((uint32_t)pixp[row] + rowoff)) * rowB + (ch << 4);
+            *reinterpret_cast<uint4 *>(gdst) = q;
+          }
+        }
+        __syncwarp();
+      }
+      rs_advance(W, u);
+      ++nunits;
+    }
     } else {
     uint32_t slot = 0, eph = 0, odd = 0;      // slot / barrier parity / row parity of the next output row of this CTA
     for (RsWork W = W0; rs_more(W) && !(P.knock & 8);) {
@@ -712,7 +855,8 @@ int rs_env_int(const char *name, int dflt) {
 }
 
 // nullptr when the row-streamed kernel serves the layer, otherwise the reason it does not
-const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L, const dlwpcs_conv_desc *dh = nullptr) {
+const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L, const dlwpcs_conv_desc *dh = nullptr,
+                         bool pool = false) {
   if (d->kh != 3 || d->kw != 3) return "3x3 kernels only";
   if (d->stride_h != 1 || d->stride_w != 1 || d->dil_h != 1 || d->dil_w != 1) return "stride / dilation 1 only";
   if (d->x_dtype != DLWPCS_BF16 || d->y_dtype != DLWPCS_BF16) return "bf16 in, bf16 out";
@@ -754,6 +898,12 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
     if (L->Kh > L->CoutP) return "head input channels exceed the padded channels in between";
     L->hwBytes = L->Kh * L->CoutP2 * 2;
   }
+  if (pool) {
+    // second output = 2x2 mean: lane pairs are pixel pairs only for even widths, row pairs stay on one epilogue warp
+    if (dh) return "pool mode and a fused head exclude each other";
+    if (L->CoutP != 32) return "pool mode serves layers with up to 32 output channels";
+    if ((g.Hout & 1) || (g.Wout & 1)) return "pool mode needs even face edges";
+  }
   L->NS = (512 - 2 * L->CoutP2) / L->CoutP;
   L->NS &= ~1;                                       // the two epilogue halves alternate rows: an even ring keeps slot <-> half fixed
   if (L->NS > RS_MAXSLOTS) L->NS = RS_MAXSLOTS;
@@ -771,7 +921,7 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
   // per loader warp: {table offset, batch element} of the strip's positions + two double-buffered rows of table entries
   const int posB = 8 * RS_NPIXP * 8 + 8 * 4 * RS_NPIXP * 4;
   const int headB = dh ? (3 * L->hwBytes + 127) / 128 * 128 + (3 * L->CoutP2 * 4 + 127) / 128 * 128 + 2 * 128 * L->CoutP * 2 + 1024 : 0;
-  const int fixed = wB + (zeroB + 127) / 128 * 128 + 1024 + (3 * L->CoutP * 4 + 127) / 128 * 128 + 8 * 32 * 4 + posB + headB +
+  const int fixed = wB + (zeroB + 127) / 128 * 128 + 1024 + (3 * L->CoutP * 4 + 127) / 128 * 128 + 2 * 8 * 32 * 4 + posB + headB +
                     8 * L->stgBytes + 1024 /* alignment slack */;
   int rsn = (RS_SMEM_CAP - fixed) / L->stageBytes;
   const int want = rs_env_int("DLWPCS_RS_STAGES", RS_MAXSTAGES);
@@ -786,7 +936,7 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
   L->off_zero = off; off += (zeroB + 127) / 128 * 128;
   L->off_misc = off; off += 1024;
   L->off_bias = off; off += (3 * L->CoutP * 4 + 127) / 128 * 128;
-  L->off_pix = off; off += 8 * 32 * 4;
+  L->off_pix = off; off += 2 * 8 * 32 * 4;
   L->off_pos = off; off += 8 * RS_NPIXP * 8;
   L->off_px = off; off += 8 * 4 * RS_NPIXP * 4;
   L->off_hw = off;
@@ -801,7 +951,7 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
 // Work split of the row-streamed kernel: CTA c works on the (strip, output row) pairs [(cut_s[c], cut_y[c]), (cut_s[c+1],
 // cut_y[c+1])).  Equal COST shares: a unit of h output rows streams h + 2 input rows, and a change of face group reloads the
 // weights and drains the pipeline (~3 rows).  Host only.
-void rs_work_cuts(int batch, int Wv, int Hout, int grid, int *cut_s, int *cut_y) {
+void rs_work_cuts(int batch, int Wv, int Hout, int grid, int *cut_s, int *cut_y, int quantum = 1) {
   const long long ns0 = (4LL * batch * Wv + 127) / 128, ns1 = (1LL * batch * Wv + 127) / 128;
   const long long strips = ns0 + 2 * ns1, R = strips * Hout;
   const double unit_cost = 2.0, group_cost = 3.0;
@@ -823,11 +973,12 @@ void rs_work_cuts(int batch, int Wv, int Hout, int grid, int *cut_s, int *cut_y)
         if (y == 0 && !first && (sidx == ns0 || sidx == ns0 + ns1)) enter += group_cost;
         const int left = Hout - y;
         int x = (int)(target - acc - enter + 0.5);
+        x -= x % quantum;                                  // pool mode: units start and end on even rows
         if (c == grid - 1) x = left;                       // the last CTA takes what remains
         if (x > left) x = left;
         if (x < left) {                                    // the share ends inside this strip
-          if (x < 1 && !first) break;                      // not worth a new unit: stop at the boundary behind us
-          if (x < 1) x = 1;                                // a CTA with work left never goes empty-handed
+          if (x < quantum && !first) break;                // not worth a new unit: stop at the boundary behind us
+          if (x < quantum) x = quantum;                    // a CTA with work left never goes empty-handed
         }
         acc += enter + x;
         pos += x;
@@ -898,21 +1049,34 @@ bool rs_head_eligible(const dlwpcs_conv_desc *d, const Geometry &g, const dlwpcs
 }
 
 static int rs_launch(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed, void *y,
-                     const dlwpcs_conv_desc *dh, const void *packed_h, void *y2, cudaStream_t st);
+                     const dlwpcs_conv_desc *dh, const void *packed_h, void *y2, void *ypool, cudaStream_t st);
 
 int rs_conv_fwd(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed, void *y,
                 cudaStream_t st) {
-  return rs_launch(d, g, x0, x1, packed, y, nullptr, nullptr, nullptr, st);
+  return rs_launch(d, g, x0, x1, packed, y, nullptr, nullptr, nullptr, nullptr, st);
 }
 
 // 3x3 layer + 1x1 head in one launch; packed_h = the head's classic packed image (dlwpcs_pack_weights of the 1x1 layer)
 int rs_conv_fwd_head(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed,
                      const dlwpcs_conv_desc *dh, const void *packed_h, void *y2, cudaStream_t st) {
-  return rs_launch(d, g, x0, x1, packed, nullptr, dh, packed_h, y2, st);
+  return rs_launch(d, g, x0, x1, packed, nullptr, dh, packed_h, y2, nullptr, st);
+}
+
+bool rs_pool_eligible(const dlwpcs_conv_desc *d, const Geometry &g) {
+  static const int enabled = rs_env_int("DLWPCS_RS", 1) && rs_env_int("DLWPCS_RS_POOLOUT", 1);
+  if (!enabled) return false;
+  RsPlan L;
+  return rs_make_plan(d, g, &L, nullptr, true) == nullptr;
+}
+
+// the layer's output AND its 2x2 mean (the next layer's pooled input) from one launch
+int rs_conv_fwd_pool(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed, void *y,
+                     void *ypool, cudaStream_t st) {
+  return rs_launch(d, g, x0, x1, packed, y, nullptr, nullptr, nullptr, ypool, st);
 }
 
 static int rs_launch(const dlwpcs_conv_desc *d, const Geometry &g, const void *x0, const void *x1, const void *packed, void *y,
-                     const dlwpcs_conv_desc *dh, const void *packed_h, void *y2, cudaStream_t st) {
+                     const dlwpcs_conv_desc *dh, const void *packed_h, void *y2, void *ypool, cudaStream_t st) {
   {
     const int dv = current_device_index();
     if (g_rs_err_host[dv] && *(volatile unsigned *)g_rs_err_host[dv]) {
@@ -926,9 +1090,11 @@ static int rs_launch(const dlwpcs_conv_desc *d, const Geometry &g, const void *x
   }
   RsP P;
   memset(&P, 0, sizeof(P));
-  const char *r = rs_make_plan(d, g, &P.L, dh);
+  const char *r = rs_make_plan(d, g, &P.L, dh, ypool != nullptr);
   CS_CHECK(r == nullptr, "row-streamed kernel does not support this configuration: %s", r);
   const RsPlan &L = P.L;
+  CS_CHECK(!ypool || rs_aligned16(ypool), "bf16 tensors must be 16-byte aligned");
+  P.ypool = (__nv_bfloat16 *)ypool;
   CS_CHECK(rs_aligned16(x0) && (d->c1 == 0 || rs_aligned16(x1)) && rs_aligned16(dh ? y2 : y) && rs_aligned16(packed) &&
                (!dh || rs_aligned16(packed_h)),
            "bf16 tensors must be 16-byte aligned");
@@ -968,10 +1134,11 @@ static int rs_launch(const dlwpcs_conv_desc *d, const Geometry &g, const void *x
   }
   P.err = g_rs_err[dev_i];
   typedef void (*kern_t)(const RsP);
-  static const kern_t kerns[2][4] = {{conv_rs_kernel<1, false>, conv_rs_kernel<2, false>, nullptr, conv_rs_kernel<4, false>},
-                                     {conv_rs_kernel<1, true>, conv_rs_kernel<2, true>, nullptr, conv_rs_kernel<4, true>}};
-  static bool attr_set[kMaxDevices][2][4] = {};
-  const int hi = dh ? 1 : 0;
+  static const kern_t kerns[3][4] = {{conv_rs_kernel<1, 0>, conv_rs_kernel<2, 0>, nullptr, conv_rs_kernel<4, 0>},
+                                     {conv_rs_kernel<1, 1>, conv_rs_kernel<2, 1>, nullptr, conv_rs_kernel<4, 1>},
+                                     {conv_rs_kernel<1, 2>, conv_rs_kernel<2, 2>, nullptr, conv_rs_kernel<4, 2>}};
+  static bool attr_set[kMaxDevices][3][4] = {};
+  const int hi = dh ? 1 : (ypool ? 2 : 0);
   const kern_t kern = kerns[hi][L.KC16 - 1];
   CS_CHECK(kern != nullptr, "internal: bad K block");
   if (!attr_set[dev_i][hi][L.KC16 - 1]) {
@@ -990,7 +1157,7 @@ static int rs_launch(const dlwpcs_conv_desc *d, const Geometry &g, const void *x
   const long long min_rows = 4;
   if ((long long)grid * min_rows > R) grid = (int)((R + min_rows - 1) / min_rows);
   if (grid < 1) grid = 1;
-  rs_work_cuts(d->batch, L.Wv, g.Hout, grid, P.cut_s, P.cut_y);
+  rs_work_cuts(d->batch, L.Wv, g.Hout, grid, P.cut_s, P.cut_y, ypool ? 2 : 1);
   P.trace = tc_trace_next(grid);
   static const int pdl = rs_env_int("DLWPCS_TC_PDL", 1);
   cudaLaunchConfig_t cfg;

@@ -276,7 +276,8 @@ class RolloutEngine(object):
     """
 
     def __init__(self, model, batch, n, steps, forcing_channels=0, dtype=torch.float32, use_graph=True,
-                 per_step_forcing=False, device=None, input_order=None, chain=None, tensor_cores=False, fuse_head=True):
+                 per_step_forcing=False, device=None, input_order=None, chain=None, tensor_cores=False, fuse_head=True,
+                 pool_out=None):
         if n % (1 << model.levels) != 0:
             raise ValueError('%s pools %d times: face edge must be divisible by %d' % (model.arch, model.levels, 1 << model.levels))
         self.model, self.batch, self.n, self.steps = model, batch, n, steps
@@ -366,6 +367,28 @@ class RolloutEngine(object):
             readers = sum(1 for it in self.plan for key in (it[2], it[3]) if key == prev[4])
             if last[2] == prev[4] and last[3] is None and readers == 1 and _lib.conv2d_head_fusable(prev[1], last[1]):
                 self.fused_head = len(self.plan) - 2
+        # a layer whose output is read through a 2x2 pooling writes the pooled tensor itself when it can
+        # (dlwpcs_conv2d_fwd_pool): the pooled layer then reads a plain source.  self.pool_out: producer index -> buffer key
+        # OFF by default (DLWPCS_POOL_OUT=1 / pool_out=True enables it): measured on the B200 at C48 / 64 members it is a wash --
+        # conv_2d_2 gets 10 us faster (25.6 instead of 35.6), conv_2d_1_2 10 us slower (the row-streamed kernel is bound by
+        # its instruction issue rate, and the 2x2 mean costs ~300 more instructions per lane and row pair).
+        self.pool_out = {}
+        if pool_out is None:
+            pool_out = os.environ.get('DLWPCS_POOL_OUT', '0') != '0'
+        if pool_out and dtype == torch.bfloat16 and not self.chain_requested(chain):
+            for i, item in enumerate(self.plan):
+                d = item[1]
+                if d.mode0 != _lib.SRC_POOL2 or item[2] in ('state', 'forcing'):
+                    continue
+                prod = [j for j, it in enumerate(self.plan) if it[4] == item[2]]
+                if len(prod) != 1 or prod[0] == self.fused_head or not _lib.conv2d_pool_fusable(self.plan[prod[0]][1]):
+                    continue
+                key = item[2] + ':pool'
+                if key not in self.buf:
+                    self.buf[key] = mk(d.n, d.c0)
+                    self.pool_out[prod[0]] = key
+                item[1] = _lib.copy_desc(d, mode0=_lib.SRC_SAME)
+                item[2] = key
         if self.tc32:              # the layers run one after the other: one scratch buffer serves every split
             scratch = torch.empty(scratch_elems, dtype=torch.bfloat16, device=self.device)
             for name, (m0, shape) in list(self._split.items()):
@@ -498,7 +521,11 @@ class RolloutEngine(object):
                 _lib.conv2d_fwd(d, xs, None, packed, out=out)
                 continue
             if not self.chain:
-                _lib.conv2d_fwd(d, self._src(s0, t), self._src(s1, t), packed, out=out)
+                if i in self.pool_out:
+                    _lib.conv2d_fwd_pool(d, self._src(s0, t), self._src(s1, t), packed, out=out,
+                                         out_pool=self.buf[self.pool_out[i]])
+                else:
+                    _lib.conv2d_fwd(d, self._src(s0, t), self._src(s1, t), packed, out=out)
                 continue
             li = t * nl + i
             blk = self._chain_mem[li * self._chain_stride:(li + 1) * self._chain_stride]

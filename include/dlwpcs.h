@@ -233,6 +233,16 @@ int dlwpcs_conv2d_head_fusable(const dlwpcs_conv_desc *d, const dlwpcs_conv_desc
 int dlwpcs_conv2d_fwd_head(const dlwpcs_conv_desc *d, const void *x0, const void *x1, const void *packed_w,
                            const dlwpcs_conv_desc *head, const void *head_packed_w, void *y_head, void *stream);
 
+/* A CubeSphereConv2D whose output is also read through AveragePooling3D((1,2,2)) (Azure/train_cs.py:197: the encoder layers
+ * in front of a pooling, e.g. conv_2d_1_2 -> conv_2d_2) writes that 2x2 mean itself, as a second tensor y_pool
+ * (B,6,Hout/2,Wout/2,cout) bf16: the pooled layer then reads a plain source -- a quarter of the bytes, through asynchronous
+ * copies.  The mean is taken over the bf16-rounded outputs in float32 and rounded to bf16 once, exactly what the fused
+ * pooled load (DLWPCS_SRC_POOL2) computes.  dlwpcs_conv2d_pool_fusable: 1 for 3x3 stride-1 bf16 layers served by the
+ * row-streamed kernel with <= 32 output channels and even face edges.                                                    */
+int dlwpcs_conv2d_pool_fusable(const dlwpcs_conv_desc *d);
+int dlwpcs_conv2d_fwd_pool(const dlwpcs_conv_desc *d, const void *x0, const void *x1, const void *packed_w, void *y,
+                           void *y_pool, void *stream);
+
 /* Host only (no GPU needed; diagnostics / tests): the work split of the row-streamed kernel for a layer it serves.  The
  * (strip, output row) sequence of the layer -- strips of 128 positions over the row-wise concatenated faces of one weight
  * group, equatorial first -- is cut into `grid` contiguous ranges of equal cost; CTA c works on [(cut_s[c], cut_y[c]),

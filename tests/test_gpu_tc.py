@@ -591,3 +591,63 @@ def test_rollout_engine_fused_head_is_bit_identical():
         outs.append(eng.run(state, forcing).clone())
         torch.cuda.synchronize()
     assert torch.equal(outs[0], outs[1])
+
+
+# ---- pooled second output (dlwpcs_conv2d_fwd_pool): the producer of a pooled layer writes the 2x2 mean itself ----------------
+@pytest.mark.parametrize('batch,n,cin,cout,srcs', [(3, 24, 32, 32, 1), (5, 48, 24, 32, 1), (2, 8, 16, 24, 1), (7, 48, 64, 32, 2),
+                                                    (1, 12, 32, 16, 1)])
+def test_pool_output_equals_pooling_the_output(lib, batch, n, cin, cout, srcs):
+    """y is bit-identical to the plain launch, y_pool == the 2x2 mean of the bf16 y taken in float32 and rounded to bf16 once
+    (what the fused pooled load of the next layer computes); then the pooled layer gives the same result from either."""
+    g = torch.Generator().manual_seed(13 * n + cin)
+    mk = lambda *shape: torch.randn(*shape, generator=g)
+    if srcs == 1:
+        x0, x1, c0, c1, m0 = bf(mk(batch, 6, n, n, cin)).cuda(), None, cin, 0, lib.SRC_SAME
+    else:
+        ca = cin // 2
+        x0, x1 = bf(mk(batch, 6, n // 2, n // 2, ca)).cuda(), bf(mk(batch, 6, n, n, cin - ca)).cuda()
+        c0, c1, m0 = ca, cin - ca, lib.SRC_UP2
+    w = [bf(mk(3, 3, cin, cout) * 0.1).float().cuda() for _ in range(2)]
+    b_ = [(mk(cout) * 0.1).cuda() for _ in range(2)]
+    d = lib.make_desc(batch, n, cin, cout, (3, 3), (1, 1), (1, 1), 1, False, True, False, True, lib.ACT_CAPPED_LEAKY_RELU, 0.1,
+                      10.0, lib.BF16, lib.BF16, c0, m0, c1, lib.SRC_SAME)
+    assert lib.conv2d_pool_fusable(d)
+    packed = lib.pack_weights(d, w[0], w[1], None, b_[0], b_[1], None)
+    y_ref = lib.conv2d_fwd(d, x0, x1, packed)
+    y, yp = lib.conv2d_fwd_pool(d, x0, x1, packed)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref)
+    f = y.float()
+    want = (0.25 * (((f[:, :, 0::2, 0::2] + f[:, :, 0::2, 1::2]) + f[:, :, 1::2, 0::2]) + f[:, :, 1::2, 1::2])).bfloat16()
+    assert torch.equal(yp, want)
+    # the next layer: pooled load of y == plain load of y_pool, bit for bit (classic kernel both times: a 5x5 layer)
+    w2 = [bf(mk(5, 5, cout, 16) * 0.1).float().cuda() for _ in range(2)]
+    dp = lib.make_desc(batch, n // 2, cout, 16, (5, 5), (1, 1), (1, 1), 2, False, True, False, False, lib.ACT_NONE, 0.1, 10.0,
+                       lib.BF16, lib.BF16, cout, lib.SRC_POOL2, 0, lib.SRC_SAME)
+    ds = lib.copy_desc(dp, mode0=lib.SRC_SAME)
+    pk2 = lib.pack_weights(dp, w2[0], w2[1], None, None, None, None)
+    za = lib.conv2d_fwd(dp, y, None, pk2)
+    zb = lib.conv2d_fwd(ds, yp, None, pk2)
+    torch.cuda.synchronize()
+    assert torch.equal(za, zb)
+    # not fusable: more than 32 output channels, odd face edge
+    assert not lib.conv2d_pool_fusable(lib.copy_desc(d, cout=64))
+    assert not lib.conv2d_pool_fusable(lib.make_desc(batch, 9, cin, cout, (3, 3), (1, 1), (1, 1), 1, False, True, False, True,
+                                                     lib.ACT_NONE, 0.1, 10.0, lib.BF16, lib.BF16))
+
+
+def test_rollout_engine_pool_outputs():
+    from dlwp_cs_b200.unet import CubeSphereUNet2, RolloutEngine
+    torch.manual_seed(3)
+    model = CubeSphereUNet2(18, 14, base=32).cuda()
+    g = torch.Generator().manual_seed(4)
+    state, forcing = torch.randn(3, 6, 24, 24, 14, generator=g), torch.rand(3, 6, 24, 24, 4, generator=g)
+    outs = []
+    for pool in (True, False):
+        eng = RolloutEngine(model, 3, 24, 3, forcing_channels=4, dtype=torch.bfloat16, pool_out=pool)
+        assert (len(eng.pool_out) == 1) == pool          # conv_2d_1_2 (32 channels) feeds the pooled conv_2d_2
+        outs.append(eng.run(state, forcing).float().clone())
+        torch.cuda.synchronize()
+    # the pooled layer runs on the other kernel (another float32 summation order): equal up to the bf16 rounding of layers
+    scale = float(outs[1].abs().max())
+    assert float((outs[0] - outs[1]).abs().max()) <= 2.0 ** -6 * scale
