@@ -19,11 +19,16 @@
 //              costs nothing: a third of the A reads, and the epilogue reads finished sums exactly as before.
 //              Every MMA accumulates: the slots start at zero and the epilogue warp that drains a slot clears it again
 //              (tcgen05.st, no shared-memory traffic).
-//   pipeline   loaders (8 warps, one input row per stage) -> MMA issuer (1 warp) -> slot ring -> epilogue (8 warps: bias,
-//              capped leaky ReLU, bf16, per-warp compaction in shared memory, coalesced stores), all mbarrier-driven; the
-//              weights of the CTA's face group stay resident in shared memory.
-//   work       every CTA gets a contiguous range of (strip, output row) pairs of equal length (cut at strip boundaries into
-//              units; a unit of h output rows streams h + 2 input rows).
+//   pipeline   loaders (8 warps; warp w gathers the rows m = w (mod 8) of the CTA's row sequence, a whole row per turn, its
+//              patch-table entries prefetched one turn ahead by 4-byte cp.async) -> MMA issuer (1 warp, descriptors in uniform
+//              registers) -> slot ring -> epilogue (8 warps: bias, capped leaky ReLU, bf16, per-warp compaction in shared
+//              memory, coalesced stores; two warps per lane quarter take alternate rows), all mbarrier-driven; the weights of
+//              the CTA's face group stay resident in shared memory.
+//   work       every CTA gets a contiguous range of (strip, output row) pairs of equal COST, cut on the host and passed in
+//              the kernel parameters (rs_work_cuts; units = the parts of a range inside one strip; a unit of h output rows
+//              streams h + 2 input rows).
+//   modes      MODE 1: the 1x1 layer that follows runs as a second MMA inside the epilogue (dlwpcs_conv2d_fwd_head);
+//              MODE 2: the 2x2 mean of the output is written as a second tensor (dlwpcs_conv2d_fwd_pool).
 //
 // Reference semantics: DLWP/custom.py:921-1002 (CubeSphereConv2D.call) with the preceding CubeSpherePadding2D
 // (custom.py:1198-1308) and the U-Net's pool / upsample / concatenate (Azure/train_cs.py:197-199, 282-299) folded into the
@@ -43,7 +48,6 @@ constexpr int RS_EPI_WARP0 = 8, RS_TMA_WARP = 16, RS_MMA_WARP = 17;
 constexpr int RS_MAXSLOTS = 16, RS_MAXSTAGES = 16;
 constexpr int RS_NPOS = 130;       // 128 lanes + (kw - 1) positions of overhang
 constexpr int RS_NPIXP = 136;      // rows of one stage (multiple of 8)
-//          // positions per loader lane and batch of table lookups (S = 4: the whole row in one batch)
 constexpr int RS_SMEM_CAP = 227 * 1024;
 constexpr int RS_MAXGRID = 160;
 
@@ -55,7 +59,7 @@ struct RsPlan {
   int unitBytes, groupBytes;         // weights of one (kernel column) unit / of one face group
   int stgBytes;                      // output staging per epilogue warp
   int off_w, off_zero, off_misc, off_bias, off_pix, off_pos, off_px, off_stg, smemBytes;
-  // fused 1x1 head (conv_rs_kernel<.., true>): a second MMA per output row inside the epilogue
+  // fused 1x1 head (conv_rs_kernel<.., 1>): a second MMA per output row inside the epilogue
   int head, CoutP2, Kh, hwBytes, off_hw, off_hbias, off_a2;     // Kh = K of the head's MMA = its padded input channels
 };
 
