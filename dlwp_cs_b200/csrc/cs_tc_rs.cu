@@ -201,21 +201,29 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     mbar_init(bar_hfull + 8, 1);
     fence_mbar_init();
   }
-  if (warp == RS_MMA_WARP) tmem_alloc(tmem_slot, 512u);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(gen + (tmem_slot - base));
-  // Every accumulator slot starts at zero and is cleared again by the epilogue warp that drains it (tcgen05.st, no shared-
-  // memory traffic), so every MMA accumulates: the issue loop has no first-touch special case.
-  if (warp >= RS_EPI_WARP0 && warp < RS_EPI_WARP0 + 8) {
-    const uint32_t lanes = (uint32_t)((warp & 3) * 32) << 16;
-    for (int c = ((warp - RS_EPI_WARP0) >> 2) * 16; c < L.NS * L.CoutP; c += 32) tmem_st16_fill(tmem_base + lanes + (uint32_t)c, 0u);
-    tmem_st_wait();
+  __syncthreads();                       // the barriers exist: loaders and the weight producer go on from here
+  // Tensor memory concerns the MMA issuer and the epilogue warps only (named barrier 5, 288 threads): allocation, then every
+  // accumulator slot is cleared -- it is cleared again by the epilogue warp that drains it (tcgen05.st, no shared-memory
+  // traffic), so every MMA accumulates and the issue loop has no first-touch special case.  The loaders meanwhile build
+  // their tables and wait for the grid dependency.
+  uint32_t tmem_base = 0;
+  if (warp >= RS_EPI_WARP0) {
+    if (warp == RS_MMA_WARP) tmem_alloc(tmem_slot, 512u);
+    if (warp == RS_MMA_WARP || warp < RS_EPI_WARP0 + 8) {
+      tc_fence_before();
+      asm volatile("bar.sync 5, 288;" ::: "memory");
+      tc_fence_after();
+      tmem_base = *reinterpret_cast<volatile uint32_t *>(gen + (tmem_slot - base));
+      if (warp < RS_EPI_WARP0 + 8) {
+        const uint32_t lanes = (uint32_t)((warp & 3) * 32) << 16;
+        for (int c = ((warp - RS_EPI_WARP0) >> 2) * 16; c < L.NS * L.CoutP; c += 32) tmem_st16_fill(tmem_base + lanes + (uint32_t)c, 0u);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      asm volatile("bar.sync 5, 288;" ::: "memory");
+      tc_fence_after();
+    }
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
   // programmatic dependent launch (see cs_tc.cu): whatever a previous kernel may have written -- activations (loaders),
   // packed weights (TMA lane), bias (epilogue) -- is read behind griddepcontrol.wait
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
