@@ -201,3 +201,43 @@ def test_row_streamed_work_cuts(batch, n, cin, cout, grid):
     d5 = _lib.make_desc(batch, n, cin, cout, (5, 5), (1, 1), (1, 1), 2, False, True, False, True, _lib.ACT_NONE, 0.1, 10.0,
                         _lib.BF16, _lib.BF16)
     assert _lib.rs_work_cuts(d5, grid) is None
+
+
+def test_kernel_dispatch_rules_host_side():
+    """Which bf16 forward layers the row-streamed kernel serves, and which pairs / layers can be fused -- the host-side
+    rules behind dlwpcs_packed_weight_bytes / dlwpcs_conv2d_head_fusable / dlwpcs_conv2d_pool_fusable (no GPU needed)."""
+    from dlwp_cs_b200 import _lib
+    lib = _lib.load()
+    import ctypes
+
+    def desc(cin, cout, k=3, halo=1, n=48, batch=4, dt=_lib.BF16, m0=_lib.SRC_SAME, stride=1, dil=1):
+        return _lib.make_desc(batch, n, cin, cout, (k, k), (stride, stride), (dil, dil), halo, False, True, False, True,
+                              _lib.ACT_CAPPED_LEAKY_RELU, 0.1, 10.0, dt, dt, cin, m0, 0, _lib.SRC_SAME)
+
+    def nbytes(d, tr):
+        return lib.dlwpcs_packed_weight_bytes(ctypes.byref(d), tr)
+
+    # row-streamed image: 3 kernel columns x CinP x (3 x CoutP) bf16 per face group + float32 bias[3][CoutP]
+    d = desc(32, 32)
+    assert nbytes(d, 0) == 3 * (3 * 32 * 96 * 2) + 3 * 32 * 4
+    assert nbytes(d, 2) == 3 * (9 * 32 * 32 * 2) + 3 * 32 * 4          # classic image (chained launches)
+    assert nbytes(d, 1) == nbytes(d, 2)                                 # transposed (dgrad): classic layout, cin == cout here
+    assert _lib.rs_work_cuts(d, 148) is not None
+    # not served by the row-streamed kernel: 128 input channels, 5x5, dilation, stride, a pooled source, a 1x1 layer
+    for other in (desc(128, 64), desc(32, 32, k=5, halo=2), desc(32, 32, dil=2, halo=2), desc(32, 32, m0=_lib.SRC_POOL2, n=24),
+                  desc(32, 16, k=1, halo=0)):
+        assert _lib.rs_work_cuts(other, 148) is None
+        assert nbytes(other, 0) == nbytes(other, 2)
+    # fused 1x1 head
+    head = desc(32, 16, k=1, halo=0)
+    assert _lib.conv2d_head_fusable(d, head)
+    assert not _lib.conv2d_head_fusable(d, desc(32, 16, k=3, halo=1))           # not a 1x1 layer
+    assert not _lib.conv2d_head_fusable(d, desc(40, 16, k=1, halo=0))           # reads something else
+    assert not _lib.conv2d_head_fusable(d, desc(32, 16, k=1, halo=0, n=24))     # another resolution
+    assert not _lib.conv2d_head_fusable(desc(128, 64), desc(64, 16, k=1, halo=0))   # the 3x3 layer is not row-streamed
+    assert _lib.conv2d_head_fusable(desc(64, 64), desc(64, 16, k=1, halo=0))
+    # pooled second output: <= 32 output channels, even face edges
+    assert _lib.conv2d_pool_fusable(d)
+    assert not _lib.conv2d_pool_fusable(desc(64, 64))
+    assert not _lib.conv2d_pool_fusable(desc(32, 32, n=9))
+    assert not _lib.conv2d_pool_fusable(desc(128, 32))
