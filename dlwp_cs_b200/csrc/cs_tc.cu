@@ -870,6 +870,10 @@ const char *make_plan(const dlwpcs_conv_desc *d, const Geometry &g, int gemm_cin
   L->groupBytes = (int64_t)L->NU * L->unitBytes;
   L->resident = (L->nstages <= MAX_STAGES && (int64_t)L->nstages * L->stageBytes <= 96 * 1024) ? 1 : 0;
   L->NST = L->resident ? L->nstages : 3;
+  if (!L->resident) {
+    const int want = env_int("DLWPCS_TC_NST", 3);
+    if (want >= 2 && want <= MAX_STAGES) L->NST = want;
+  }
   L->Wv = g.Wout + (d->kw - 1) * d->dil_w;
   L->Hv = g.Hout + (d->kh - 1) * d->dil_h;
   L->Q = (g.Hout - 1) * L->Wv + g.Wout;
@@ -882,6 +886,14 @@ const char *make_plan(const dlwpcs_conv_desc *d, const Geometry &g, int gemm_cin
   // bf16 outputs with 16-byte rows are compacted in shared memory and written with TMA bulk stores
   L->stgBytes = (d->y_dtype == DLWPCS_BF16 && gemm_cout % 8 == 0 && !env_int("DLWPCS_TC_NOSTAGE", 0)) ? 32 * gemm_cout * 2 : 0;
   L->stgBufs = L->stgBytes ? 1 : 0;
+  // Streamed weights and >= 128 output channels (256-byte rows: a lane's direct 16-byte stores fill whole sectors anyway): the
+  // staging buffers' 64 KB go to a deeper weight ring instead (measured, 64 -> 128 at 12 x 12, batch 64: 18.4 instead of 21.8 us;
+  // with 128-byte rows the direct stores cost more than the ring gains)
+  if (!L->resident && L->stgBytes && gemm_cout * 2 >= 256 && env_int("DLWPCS_TC_WIDE_DIRECT", 1)) {
+    L->stgBytes = 0;
+    L->stgBufs = 0;
+    if (L->NST == 3) L->NST = 5;
+  }
   int fixed0 = 1024 + 512 + MAX_UNITS * 8 + 3 * L->CoutP * 4 + L->NST * L->stageBytes + 8 * L->stgBufs * L->stgBytes + 128;
   auto patch_for = [&](int MB, int *npixp) {
     const int np = ((MB * 128 + L->haloExt + 7) / 8) * 8;
