@@ -504,11 +504,14 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     } else if constexpr (MODE == 2) {
     // ---- pool mode (32 padded output channels): besides the layer's output, its 2x2 mean (AveragePooling3D((1,2,2)),
     // train_cs.py:197) is written as a second tensor, so that the next layer reads a plain source (a quarter of the bytes, and
-    // through asynchronous copies instead of registers).  The two warps of a lane quarter take alternate ROW PAIRS; lanes
-    // 2i, 2i+1 hold horizontally adjacent pixels (Wv is even).  The mean is taken over the bf16-rounded outputs in the order
-    // (r,c), (r,c+1), (r+1,c), (r+1,c+1) and rounded to bf16 once, like the classic kernel's pooled load.
+    // through asynchronous copies instead of registers).  The two warps of a lane quarter take alternate ROW PAIRS and keep
+    // both staged rows (two staging buffers per warp); lanes 2i, 2i+1 hold horizontally adjacent pixels (Wv is even), valid
+    // lanes come in such pairs, so the pooled pixel j is the mean of the compacted rows 2j, 2j+1 of both buffers -- taken
+    // over the bf16-rounded outputs in the order (r,c), (r,c+1), (r+1,c), (r+1,c+1) and rounded to bf16 once, like the
+    // classic kernel's pooled load.
     int *pixp = s_pix + 256 + (warp - RS_EPI_WARP0) * 32;
     const int Hp = P.Hout >> 1, Wp = P.Wout >> 1;
+    const uint32_t stgA = stg0 + (uint32_t)(2 * (warp - RS_EPI_WARP0)) * L.stgBytes, stgB = stgA + (uint32_t)L.stgBytes;
     uint32_t slot = 0, eph = 0, nrow = 0;
     for (RsWork W = W0; rs_more(W) && !(P.knock & 8);) {
       const RsUnit u = rs_unit(W);
@@ -523,19 +526,12 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
       const unsigned okmask = __ballot_sync(0xffffffffu, ok);
       const int nvalid = __popc(okmask);
       const uint32_t prow = (uint32_t)__popc(okmask & ((1u << lane) - 1u));
-      const bool okp = ok && !(lane & 1);         // this lane writes the pooled pixel of columns cv, cv + 1
-      const unsigned okpmask = __ballot_sync(0xffffffffu, okp);
-      const int nvalidp = __popc(okpmask);
-      const uint32_t prowp = (uint32_t)__popc(okpmask & ((1u << lane) - 1u));
       __syncwarp();
       if (ok) pixw[prow] = opix0;
-      if (okp) pixp[prowp] = ((b * 6 + f) * Hp + (u.y0 >> 1)) * Wp + (cv >> 1);
+      if (ok && !(lane & 1)) pixp[prow >> 1] = ((b * 6 + f) * Hp + (u.y0 >> 1)) * Wp + (cv >> 1);
       __syncwarp();
-      const uint32_t srow = stg + prow * rowB, srowp = stg + prowp * rowB;
-      const uint32_t total = (uint32_t)nvalid * rowB, totalp = (uint32_t)nvalidp * rowB;
-      uint32_t prev[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) prev[i] = 0u;
+      const uint32_t total = (uint32_t)nvalid * rowB;
+      const uint32_t items = (uint32_t)(nvalid >> 1) * cpr;          // 16-byte chunks of the pooled row
 #pragma unroll 1
       for (int o = 0; o < H; ++o) {
         const uint32_t slot_o = slot, eph_o = eph, mine = ((int)((nrow >> 1) & 1u) == half);
@@ -546,7 +542,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
         tc_fence_after();
         if (P.trace && !etraced) { rs_trace(P, 4, tid == RS_EPI_WARP0 * 32); etraced = true; }
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot_o * (uint32_t)L.CoutP;
-        uint32_t v[32], cur[16];
+        const uint32_t sb = (o & 1) ? stgB : stgA, srow = sb + prow * rowB;
+        uint32_t v[32];
         tmem_ld16(trow, v);
         tmem_ld16(trow + 16u, v + 16);
         tmem_ld_wait();
@@ -556,33 +553,33 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_sempty + 8 * slot_o);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float r[16];
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const float4 bv = *reinterpret_cast<const float4 *>(bias + 16 * h + 4 * k4);
-            r[4 * k4 + 0] = __uint_as_float(v[16 * h + 4 * k4 + 0]) + bv.x;
-            r[4 * k4 + 1] = __uint_as_float(v[16 * h + 4 * k4 + 1]) + bv.y;
-            r[4 * k4 + 2] = __uint_as_float(v[16 * h + 4 * k4 + 2]) + bv.z;
-            r[4 * k4 + 3] = __uint_as_float(v[16 * h + 4 * k4 + 3]) + bv.w;
-          }
-          if (act_fast) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) r[e] = fminf(fmaxf(r[e], P.slope * r[e]), P.maxv);
-          } else if (P.act != DLWPCS_ACT_NONE) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) r[e] = act_apply(r[e], P.act, P.slope, P.maxv);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) cur[8 * h + j] = pack_bf16x2(r[2 * j], r[2 * j + 1]);
-        }
         if (ok) {
 #pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8)
-            if (8 * c8 + 8 <= P.cout)
-              st_shared16(srow + (((uint32_t)c8 ^ ((prow >> kshift) & smask)) << 4),
-                          make_uint4(cur[4 * c8], cur[4 * c8 + 1], cur[4 * c8 + 2], cur[4 * c8 + 3]));
+          for (int h = 0; h < 2; ++h) {
+            float r[16];
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const float4 bv = *reinterpret_cast<const float4 *>(bias + 16 * h + 4 * k4);
+              r[4 * k4 + 0] = __uint_as_float(v[16 * h + 4 * k4 + 0]) + bv.x;
+              r[4 * k4 + 1] = __uint_as_float(v[16 * h + 4 * k4 + 1]) + bv.y;
+              r[4 * k4 + 2] = __uint_as_float(v[16 * h + 4 * k4 + 2]) + bv.z;
+              r[4 * k4 + 3] = __uint_as_float(v[16 * h + 4 * k4 + 3]) + bv.w;
+            }
+            if (act_fast) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) r[e] = fminf(fmaxf(r[e], P.slope * r[e]), P.maxv);
+            } else if (P.act != DLWPCS_ACT_NONE) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) r[e] = act_apply(r[e], P.act, P.slope, P.maxv);
+            }
+            const int nb = 16 * h;
+            if (nb + 8 <= P.cout)
+              st_shared16(srow + ((((uint32_t)nb >> 3) ^ ((prow >> kshift) & smask)) << 4),
+                          make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7])));
+            if (nb + 16 <= P.cout)
+              st_shared16(srow + (((((uint32_t)nb >> 3) + 1u) ^ ((prow >> kshift) & smask)) << 4),
+                          make_uint4(pack_bf16x2(r[8], r[9]), pack_bf16x2(r[10], r[11]), pack_bf16x2(r[12], r[13]), pack_bf16x2(r[14], r[15])));
+          }
         }
         __syncwarp();
         {
@@ -593,50 +590,39 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
             else { row = off / rowB; ch = (off - row * rowB) >> 4; }
             uint4 q;
             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
-                         : "r"(stg + row * rowB + ((ch ^ ((row >> kshift) & smask)) << 4)));
+                         : "r"(sb + row * rowB + ((ch ^ ((row >> kshift) & smask)) << 4)));
             uint8_t *gdst = reinterpret_cast<uint8_t *>(P.y) + ((size_t)((uint32_t)pixw[row] + rowoff)) * rowB + (ch << 4);
             *reinterpret_cast<uint4 *>(gdst) = q;
           }
         }
-        __syncwarp();
-        if (!(o & 1)) {
+        if (!(o & 1)) continue;           // (the other buffer is written next; this one is read again below)
+        // second row of the pair: one 16-byte chunk (8 channels) of one pooled pixel per item, straight to HBM
+        const uint32_t rowoffp = (uint32_t)((o >> 1) * Wp);
+        for (uint32_t it = (uint32_t)lane; it < items; it += 32u) {
+          uint32_t j, ch;
+          if (cprLog >= 0) { j = it >> cprLog; ch = it & (cpr - 1u); }
+          else { j = it / cpr; ch = it - j * cpr; }
+          const uint32_t r0 = 2u * j, r1 = r0 + 1u;
+          const uint32_t o0 = r0 * rowB + ((ch ^ ((r0 >> kshift) & smask)) << 4), o1 = r1 * rowB + ((ch ^ ((r1 >> kshift) & smask)) << 4);
+          uint4 q[4];
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q[0].x), "=r"(q[0].y), "=r"(q[0].z), "=r"(q[0].w) : "r"(stgA + o0));
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q[1].x), "=r"(q[1].y), "=r"(q[1].z), "=r"(q[1].w) : "r"(stgA + o1));
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q[2].x), "=r"(q[2].y), "=r"(q[2].z), "=r"(q[2].w) : "r"(stgB + o0));
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q[3].x), "=r"(q[3].y), "=r"(q[3].z), "=r"(q[3].w) : "r"(stgB + o1));
+          float a[8], t[8];
+          unpack_bf16x8(q[0], a);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) prev[i] = cur[i];
-          continue;
-        }
-        // second row of the pair: 2x2 mean with the neighbour lane's columns
-        uint32_t pl[16];
+          for (int s4 = 1; s4 < 4; ++s4) {
+            unpack_bf16x8(q[s4], t);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const uint32_t a2 = __shfl_xor_sync(0xffffffffu, prev[i], 1), b2 = __shfl_xor_sync(0xffffffffu, cur[i], 1);
-          const float lo = 0.25f * (((__uint_as_float(prev[i] << 16) + __uint_as_float(a2 << 16)) + __uint_as_float(cur[i] << 16)) +
-                                    __uint_as_float(b2 << 16));
-          const float hi = 0.25f * (((__uint_as_float(prev[i] & 0xFFFF0000u) + __uint_as_float(a2 & 0xFFFF0000u)) +
-                                     __uint_as_float(cur[i] & 0xFFFF0000u)) + __uint_as_float(b2 & 0xFFFF0000u));
-          pl[i] = pack_bf16x2(lo, hi);
-        }
-        if (okp) {
-#pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8)
-            if (8 * c8 + 8 <= P.cout)
-              st_shared16(srowp + (((uint32_t)c8 ^ ((prowp >> kshift) & smask)) << 4),
-                          make_uint4(pl[4 * c8], pl[4 * c8 + 1], pl[4 * c8 + 2], pl[4 * c8 + 3]));
-        }
-        __syncwarp();
-        {
-          const uint32_t rowoff = (uint32_t)((o >> 1) * Wp);
-          for (uint32_t off = (uint32_t)lane * 16u; off < totalp; off += 512u) {
-            uint32_t row, ch;
-            if (cprLog >= 0) { row = off >> (4 + cprLog); ch = (off >> 4) & (cpr - 1u); }
-            else { row = off / rowB; ch = (off - row * rowB) >> 4; }
-            uint4 q;
-            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
-                         : "r"(stg + row * rowB + ((ch ^ ((row >> kshift) & smask)) << 4)));
-            uint8_t *gdst = reinterpret_cast<uint8_t *>(P.ypool) + ((size_t)((uint32_t)pixp[row] + rowoff)) * rowB + (ch << 4);
-            *reinterpret_cast<uint4 *>(gdst) = q;
+            for (int e = 0; e < 8; ++e) a[e] += t[e];
           }
+          const uint4 pl = make_uint4(pack_bf16x2(0.25f * a[0], 0.25f * a[1]), pack_bf16x2(0.25f * a[2], 0.25f * a[3]),
+                                      pack_bf16x2(0.25f * a[4], 0.25f * a[5]), pack_bf16x2(0.25f * a[6], 0.25f * a[7]));
+          uint8_t *gdst = reinterpret_cast<uint8_t *>(P.ypool) + ((size_t)((uint32_t)pixp[j] + rowoffp)) * rowB + (ch << 4);
+          *reinterpret_cast<uint4 *>(gdst) = pl;
         }
-        __syncwarp();
+        __syncwarp();                     // both buffers are rewritten by this warp's next pair
       }
       rs_advance(W, u);
       ++nunits;
@@ -926,6 +912,7 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
   L->unitBytes = L->CinP * L->NT * 2;
   L->groupBytes = 3 * L->unitBytes;
   L->stgBytes = 32 * (dh ? dh->cout : d->cout) * 2;
+  const int stgPerWarp = pool ? 2 : 1;              // pool mode keeps both rows of a pair staged
   int off = 0;
   L->off_w = 0;        // filled below, after the row stages
   const int wB = (L->groupBytes + 1023) / 1024 * 1024;
@@ -934,7 +921,7 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
   const int posB = 8 * RS_NPIXP * 8 + 8 * 4 * RS_NPIXP * 4;
   const int headB = dh ? (3 * L->hwBytes + 127) / 128 * 128 + (3 * L->CoutP2 * 4 + 127) / 128 * 128 + 2 * 128 * L->CoutP * 2 + 1024 : 0;
   const int fixed = wB + (zeroB + 127) / 128 * 128 + 1024 + (3 * L->CoutP * 4 + 127) / 128 * 128 + 2 * 8 * 32 * 4 + posB + headB +
-                    8 * L->stgBytes + 1024 /* alignment slack */;
+                    8 * stgPerWarp * L->stgBytes + 1024 /* alignment slack */;
   int rsn = (RS_SMEM_CAP - fixed) / L->stageBytes;
   const int want = rs_env_int("DLWPCS_RS_STAGES", RS_MAXSTAGES);
   if (rsn > want) rsn = want;
@@ -955,7 +942,7 @@ const char *rs_make_plan(const dlwpcs_conv_desc *d, const Geometry &g, RsPlan *L
   if (dh) off += (3 * L->hwBytes + 127) / 128 * 128;
   L->off_hbias = off;
   if (dh) off += (3 * L->CoutP2 * 4 + 127) / 128 * 128;
-  L->off_stg = off; off += 8 * L->stgBytes;
+  L->off_stg = off; off += 8 * stgPerWarp * L->stgBytes;
   L->smemBytes = off + 1024;
   return nullptr;
 }

@@ -369,12 +369,11 @@ class RolloutEngine(object):
                 self.fused_head = len(self.plan) - 2
         # a layer whose output is read through a 2x2 pooling writes the pooled tensor itself when it can
         # (dlwpcs_conv2d_fwd_pool): the pooled layer then reads a plain source.  self.pool_out: producer index -> buffer key
-        # OFF by default (DLWPCS_POOL_OUT=1 / pool_out=True enables it): measured on the B200 at C48 / 64 members it is a wash --
-        # conv_2d_2 gets 10 us faster (25.6 instead of 35.6), conv_2d_1_2 10 us slower (the row-streamed kernel is bound by
-        # its instruction issue rate, and the 2x2 mean costs ~300 more instructions per lane and row pair).
+        # On by default (DLWPCS_POOL_OUT=0 / pool_out=False disables it): at C48 / 64 members conv_2d_2 gets 10 us faster (25.7
+        # instead of 35.8), conv_2d_1_2 6 us slower (two staged rows per warp, the mean read back from them).
         self.pool_out = {}
         if pool_out is None:
-            pool_out = os.environ.get('DLWPCS_POOL_OUT', '0') != '0'
+            pool_out = os.environ.get('DLWPCS_POOL_OUT', '1') != '0'
         if pool_out and dtype == torch.bfloat16 and not self.chain_requested(chain):
             for i, item in enumerate(self.plan):
                 d = item[1]

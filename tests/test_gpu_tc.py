@@ -645,7 +645,7 @@ def test_rollout_engine_pool_outputs():
     outs = []
     for pool in (True, False):
         eng = RolloutEngine(model, 3, 24, 3, forcing_channels=4, dtype=torch.bfloat16, pool_out=pool)
-        assert (len(eng.pool_out) == 1) == pool          # conv_2d_1_2 (32 channels) feeds the pooled conv_2d_2
+        assert (len(eng.pool_out) == 1) == pool          # conv_2d_1_2 (32 channels) feeds the pooled conv_2d_2 (on by default)
         outs.append(eng.run(state, forcing).float().clone())
         torch.cuda.synchronize()
     # the pooled layer runs on the other kernel (another float32 summation order): equal up to the bf16 rounding of layers
